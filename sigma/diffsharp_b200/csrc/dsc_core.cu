@@ -1,0 +1,651 @@
+// Context lifecycle, stream-ordered pool allocator, device data buffers (the device twin of
+// ISigmaDiffDataBuffer, reference src/DiffSharp/Util.fs:133-165), CUDA events and CUDA-graph capture.
+#include <stdarg.h>
+
+#include <algorithm>
+
+#include "dsc_internal.cuh"
+
+namespace dsc {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+// ---- pool ---------------------------------------------------------------------------------
+// Bin sizes: multiples of 512 B up to 1 MiB, multiples of 64 KiB up to 64 MiB, multiples of 2 MiB
+// above.  The tape of one MLP step asks for a handful of distinct sizes thousands of times
+// (two zero adjoints per node, AD.Float32.fs:1834-1835,3746), so exact-bin reuse hits ~100 %.
+static size_t round_bin(size_t bytes) {
+    if (bytes == 0) bytes = 1;
+    if (bytes <= (1u << 20)) return (bytes + 511) & ~size_t(511);
+    if (bytes <= (64u << 20)) return (bytes + 65535) & ~size_t(65535);
+    return (bytes + (2u << 20) - 1) & ~size_t((2u << 20) - 1);
+}
+
+int pool_alloc(Ctx* ctx, size_t bytes, Block** out) {
+    size_t bin = round_bin(bytes);
+    Pool& pool = ctx->capturing ? ctx->arena_pool : ctx->pool;
+    void* p = nullptr;
+    if (!(ctx->flags & DSC_FLAG_NO_POOL)) {
+        auto it = pool.free_blocks.find(bin);
+        if (it != pool.free_blocks.end()) {
+            p = it->second;
+            pool.free_blocks.erase(it);
+            pool.hits++;
+        }
+    }
+    if (!p) {
+        cudaError_t e = cudaMalloc(&p, bin);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            // release everything cached and retry once
+            for (auto& kv : ctx->pool.free_blocks) {
+                cudaFree(kv.second);
+                ctx->pool.reserved -= kv.first;
+            }
+            ctx->pool.free_blocks.clear();
+            e = cudaMalloc(&p, bin);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return fail(DSC_E_OOM, "device allocation of %zu bytes failed: %s", bin,
+                            cudaGetErrorString(e));
+            }
+        }
+        pool.misses++;
+        pool.reserved += bin;
+    }
+    pool.in_use += bin;
+    Block* b = new Block();
+    b->ptr = p;
+    b->bytes = bin;
+    b->refs = 1;
+    b->ctx = ctx;
+    b->arena = ctx->capturing ? ctx->cur_arena : 0;
+    if (ctx->capturing) ctx->arena_blocks.push_back(b);
+    *out = b;
+    return DSC_OK;
+}
+
+void block_release(Block* blk) {
+    if (!blk) return;
+    if (--blk->refs > 0) return;
+    Ctx* ctx = blk->ctx;
+    if (blk->arena == 0) {
+        ctx->pool.in_use -= blk->bytes;
+        if (ctx->flags & DSC_FLAG_NO_POOL) {
+            cudaFree(blk->ptr);
+            ctx->pool.reserved -= blk->bytes;
+        } else {
+            ctx->pool.free_blocks.emplace(blk->bytes, blk->ptr);
+        }
+        delete blk;
+    } else if (blk->arena < 0) {
+        // orphan of a destroyed graph
+        cudaFree(blk->ptr);
+        delete blk;
+    } else if (ctx->capturing && blk->arena == ctx->cur_arena) {
+        // temporaries of the step being captured are recycled inside the capture: the graph is a
+        // linear chain on one stream, so reuse is ordered exactly as in eager mode.
+        ctx->arena_pool.in_use -= blk->bytes;
+        ctx->arena_pool.free_blocks.emplace(blk->bytes, blk->ptr);
+        // the Block record itself stays in arena_blocks only through its pointer; mark it dead
+        blk->ptr = nullptr;
+    }
+    // else: block belongs to a finished graph; the graph keeps the memory reserved.
+}
+
+int buf_new(Ctx* ctx, int dtype, int32_t n, Buf** out) {
+    if (n < 0) return fail(DSC_E_INVALID, "negative buffer length %d", n);
+    Buf* b = new Buf();
+    b->dtype = dtype;
+    b->ctx = ctx;
+    b->len = n;
+    b->off = 0;
+    if (n > 0) {
+        int s = pool_alloc(ctx, (size_t)n * dtype_size(dtype), &b->block);
+        if (s != DSC_OK) {
+            delete b;
+            return s;
+        }
+    }
+    *out = b;
+    return DSC_OK;
+}
+
+int out_buf(Ctx* ctx, int dtype, int32_t n, dsc_buf_t* out, Buf** res) {
+    if (!out) return fail(DSC_E_INVALID, "null output handle pointer");
+    if (*out == 0) {
+        Buf* b = nullptr;
+        DSC_TRY(buf_new(ctx, dtype, n, &b));
+        *out = reinterpret_cast<dsc_buf_t>(b);
+        *res = b;
+        return DSC_OK;
+    }
+    Buf* b = as_buf(*out);
+    if (!b) return fail(DSC_E_INVALID, "output handle is not a live buffer");
+    if (b->ctx != ctx) return fail(DSC_E_INVALID, "output buffer belongs to another context");
+    if (b->dtype != dtype) return fail(DSC_E_DTYPE, "output buffer has the wrong dtype");
+    if (b->len != n) return fail(DSC_E_SHAPE, "output buffer has length %d, expected %d", b->len, n);
+    *res = b;
+    return DSC_OK;
+}
+
+int in_buf(Ctx* ctx, int dtype, dsc_buf_t h, Buf** res, const char* what) {
+    Buf* b = as_buf(h);
+    if (!b) return fail(DSC_E_INVALID, "%s is not a live buffer handle", what);
+    if (b->ctx != ctx) return fail(DSC_E_INVALID, "%s belongs to another context", what);
+    if (b->dtype != dtype) return fail(DSC_E_DTYPE, "%s has the wrong dtype", what);
+    *res = b;
+    return DSC_OK;
+}
+
+int ensure_red_scratch(Ctx* ctx, size_t bytes) {
+    if (ctx->red_scratch_bytes >= bytes) return DSC_OK;
+    if (ctx->capturing) return fail(DSC_E_INVALID, "reduction scratch cannot grow while capturing");
+    if (ctx->red_scratch) cudaFree(ctx->red_scratch);
+    ctx->red_scratch = nullptr;
+    ctx->red_scratch_bytes = 0;
+    DSC_CUDA_CHECK(cudaMalloc(&ctx->red_scratch, bytes));
+    DSC_CUDA_CHECK(cudaMemsetAsync(ctx->red_scratch, 0, bytes, ctx->stream));
+    ctx->red_scratch_bytes = bytes;
+    return DSC_OK;
+}
+
+int ensure_gemm_ws(Ctx* ctx, size_t bytes) {
+    if (ctx->gemm_ws_bytes >= bytes) return DSC_OK;
+    if (ctx->capturing) return fail(DSC_E_INVALID, "GEMM workspace cannot grow while capturing (run the step once eagerly first)");
+    if (ctx->gemm_ws) {
+        DSC_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->gemm_ws);
+    }
+    ctx->gemm_ws = nullptr;
+    ctx->gemm_ws_bytes = 0;
+    size_t want = (bytes + (8u << 20) - 1) & ~size_t((8u << 20) - 1);
+    DSC_CUDA_CHECK(cudaMalloc(&ctx->gemm_ws, want));
+    ctx->gemm_ws_bytes = want;
+    return DSC_OK;
+}
+
+template <typename T>
+__global__ void fill_kernel(T* __restrict__ p, size_t n, T v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+
+static int fill_window(Ctx* ctx, Buf* b, int32_t off, int32_t n, double v) {
+    if (n == 0) return DSC_OK;
+    size_t es = dtype_size(b->dtype);
+    char* base = reinterpret_cast<char*>(b->block->ptr) + (b->off + off) * es;
+    if (v == 0.0) {
+        DSC_CUDA_CHECK(cudaMemsetAsync(base, 0, (size_t)n * es, ctx->stream));
+        ctx->stats.kernel_launches++;
+        return DSC_OK;
+    }
+    int grid = grid_for(n, 256 * 8, ctx->sm_count * 8);
+    if (b->dtype == DSC_F32)
+        fill_kernel<float><<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<float*>(base), n, (float)v);
+    else
+        fill_kernel<double><<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<double*>(base), n, v);
+    DSC_LAUNCH_CHECK(ctx);
+    return DSC_OK;
+}
+
+// strided 2-D gather used by GetStackedValues (Util.fs:204-210)
+template <typename T>
+__global__ void gather2d_kernel(const T* __restrict__ src, T* __restrict__ dst, int cols, int r0,
+                                int c0, int orows, int ocols) {
+    size_t n = (size_t)orows * ocols;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        int r = (int)(i / ocols), c = (int)(i % ocols);
+        dst[i] = src[(size_t)(r0 + r) * cols + (c0 + c)];
+    }
+}
+
+}  // namespace dsc
+
+using namespace dsc;
+
+extern "C" {
+
+int dsc_version(void) { return DSC_VERSION; }
+
+const char* dsc_last_error(void) { return g_err; }
+
+int dsc_device_count(int* count) {
+    if (!count) return fail(DSC_E_INVALID, "null count");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *count = 0;
+        return fail(DSC_E_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return DSC_OK;
+}
+
+int dsc_create(int device, uint32_t flags, dsc_ctx_t* out) {
+    if (!out) return fail(DSC_E_INVALID, "null ctx pointer");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(DSC_E_CUDA, "no CUDA device available (%s); this backend has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= ndev) return fail(DSC_E_INVALID, "device %d out of range [0,%d)", device, ndev);
+    DSC_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    DSC_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(DSC_E_CUDA, "device %d is sm_%d%d; libdiffsharp_cuda is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    Ctx* ctx = new Ctx();
+    ctx->device = device;
+    ctx->flags = flags;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    DSC_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    DSC_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    DSC_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming));
+    DSC_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
+    DSC_CUDA_CHECK(cudaMallocHost(&ctx->red_host, 256));
+    int s = ensure_red_scratch(ctx, 1u << 20);
+    if (s != DSC_OK) return s;
+    *out = reinterpret_cast<dsc_ctx_t>(ctx);
+    return DSC_OK;
+}
+
+int dsc_comm_destroy(dsc_ctx_t c);
+
+int dsc_destroy(dsc_ctx_t c) {
+    if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
+    Ctx* ctx = as_ctx(c);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->comm_stream);
+    if (ctx->nccl_comm) dsc_comm_destroy(c);
+    for (auto& kv : ctx->pool.free_blocks) cudaFree(kv.second);
+    ctx->pool.free_blocks.clear();
+    if (ctx->red_scratch) cudaFree(ctx->red_scratch);
+    if (ctx->red_host) cudaFreeHost(ctx->red_host);
+    if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    if (ctx->gemm_ws) cudaFree(ctx->gemm_ws);
+    cudaEventDestroy(ctx->ev_compute);
+    cudaEventDestroy(ctx->ev_comm);
+    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->comm_stream);
+    ctx->magic = 0;
+    delete ctx;
+    return DSC_OK;
+}
+
+int dsc_comm_join(dsc_ctx_t c);
+
+int dsc_sync(dsc_ctx_t c) {
+    if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
+    Ctx* ctx = as_ctx(c);
+    if (ctx->capturing) return fail(DSC_E_INVALID, "dsc_sync while capturing a graph");
+    DSC_TRY(dsc_comm_join(c));
+    DSC_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return DSC_OK;
+}
+
+int dsc_get_stats(dsc_ctx_t c, dsc_stats* out) {
+    if (!ctx_ok(c) || !out) return fail(DSC_E_INVALID, "bad context or null stats");
+    Ctx* ctx = as_ctx(c);
+    ctx->stats.pool_bytes_reserved = ctx->pool.reserved;
+    ctx->stats.pool_bytes_in_use = ctx->pool.in_use;
+    ctx->stats.pool_hits = ctx->pool.hits;
+    ctx->stats.pool_misses = ctx->pool.misses;
+    *out = ctx->stats;
+    return DSC_OK;
+}
+
+int dsc_get_stream(dsc_ctx_t c, void** s) {
+    if (!ctx_ok(c) || !s) return fail(DSC_E_INVALID, "bad context or null stream pointer");
+    *s = as_ctx(c)->stream;
+    return DSC_OK;
+}
+
+int dsc_trim_pool(dsc_ctx_t c) {
+    if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
+    Ctx* ctx = as_ctx(c);
+    if (ctx->capturing) return fail(DSC_E_INVALID, "dsc_trim_pool while capturing");
+    DSC_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (auto& kv : ctx->pool.free_blocks) {
+        cudaFree(kv.second);
+        ctx->pool.reserved -= kv.first;
+    }
+    ctx->pool.free_blocks.clear();
+    return DSC_OK;
+}
+
+// ---- events -------------------------------------------------------------------------------
+int dsc_event_create(dsc_ctx_t c, dsc_event_t* ev) {
+    if (!ctx_ok(c) || !ev) return fail(DSC_E_INVALID, "bad context or null event pointer");
+    cudaEvent_t e;
+    DSC_CUDA_CHECK(cudaEventCreate(&e));
+    *ev = reinterpret_cast<dsc_event_t>(e);
+    return DSC_OK;
+}
+int dsc_event_record(dsc_ctx_t c, dsc_event_t ev) {
+    if (!ctx_ok(c) || !ev) return fail(DSC_E_INVALID, "bad context or event");
+    DSC_CUDA_CHECK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev), as_ctx(c)->stream));
+    return DSC_OK;
+}
+int dsc_event_elapsed_ms(dsc_ctx_t c, dsc_event_t a, dsc_event_t b, float* ms) {
+    if (!ctx_ok(c) || !a || !b || !ms) return fail(DSC_E_INVALID, "bad context, event or pointer");
+    DSC_CUDA_CHECK(cudaEventSynchronize(reinterpret_cast<cudaEvent_t>(b)));
+    DSC_CUDA_CHECK(cudaEventElapsedTime(ms, reinterpret_cast<cudaEvent_t>(a), reinterpret_cast<cudaEvent_t>(b)));
+    return DSC_OK;
+}
+int dsc_event_destroy(dsc_ctx_t c, dsc_event_t ev) {
+    if (!ctx_ok(c) || !ev) return fail(DSC_E_INVALID, "bad context or event");
+    DSC_CUDA_CHECK(cudaEventDestroy(reinterpret_cast<cudaEvent_t>(ev)));
+    return DSC_OK;
+}
+
+int dsc_flush_l2(dsc_ctx_t c) {
+    if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
+    Ctx* ctx = as_ctx(c);
+    const size_t bytes = 256u << 20;  // 2x the 126 MB L2
+    if (!ctx->flush_buf) {
+        if (ctx->capturing) return fail(DSC_E_INVALID, "first dsc_flush_l2 while capturing");
+        DSC_CUDA_CHECK(cudaMalloc(&ctx->flush_buf, bytes));
+        ctx->flush_bytes = bytes;
+    }
+    DSC_CUDA_CHECK(cudaMemsetAsync(ctx->flush_buf, 1, ctx->flush_bytes, ctx->stream));
+    return DSC_OK;
+}
+
+// ---- graphs -------------------------------------------------------------------------------
+int dsc_graph_begin(dsc_ctx_t c) {
+    if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
+    Ctx* ctx = as_ctx(c);
+    if (ctx->capturing) return fail(DSC_E_INVALID, "already capturing");
+    DSC_TRY(dsc_comm_join(c));
+    DSC_CUDA_CHECK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    ctx->capturing = true;
+    ctx->cur_arena = ctx->next_arena++;
+    ctx->arena_pool = Pool();
+    ctx->arena_blocks.clear();
+    return DSC_OK;
+}
+
+int dsc_graph_end(dsc_ctx_t c, dsc_graph_t* out) {
+    if (!ctx_ok(c) || !out) return fail(DSC_E_INVALID, "bad context or null graph pointer");
+    Ctx* ctx = as_ctx(c);
+    if (!ctx->capturing) return fail(DSC_E_INVALID, "not capturing");
+    if (ctx->comm_pending) {
+        // join the communication stream back into the origin stream before ending the capture
+        cudaEventRecord(ctx->ev_comm, ctx->comm_stream);
+        cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0);
+        ctx->comm_pending = false;
+    }
+    Graph* g = new Graph();
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &g->graph);
+    ctx->capturing = false;
+    g->arena = ctx->cur_arena;
+    // Blocks released inside the capture were recycled through arena_pool; what remains cached there
+    // plus what is still referenced is the graph's private memory.
+    for (Block* b : ctx->arena_blocks) {
+        if (b->ptr == nullptr) delete b;  // record of a recycled block (memory lives on in another record or the pool)
+        else g->blocks.push_back(b);
+    }
+    for (auto& kv : ctx->arena_pool.free_blocks) {
+        Block* b = new Block();
+        b->ptr = kv.second;
+        b->bytes = kv.first;
+        b->refs = 0;
+        b->ctx = ctx;
+        b->arena = g->arena;
+        g->blocks.push_back(b);
+    }
+    ctx->arena_blocks.clear();
+    ctx->arena_pool = Pool();
+    ctx->cur_arena = 0;
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        delete g;
+        return fail(DSC_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    }
+    e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaGraphDestroy(g->graph);
+        delete g;
+        return fail(DSC_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    }
+    *out = reinterpret_cast<dsc_graph_t>(g);
+    return DSC_OK;
+}
+
+int dsc_graph_launch(dsc_ctx_t c, dsc_graph_t gh) {
+    if (!ctx_ok(c) || !gh) return fail(DSC_E_INVALID, "bad context or graph");
+    Ctx* ctx = as_ctx(c);
+    Graph* g = reinterpret_cast<Graph*>(gh);
+    DSC_CUDA_CHECK(cudaGraphLaunch(g->exec, ctx->stream));
+    return DSC_OK;
+}
+
+int dsc_graph_destroy(dsc_ctx_t c, dsc_graph_t gh) {
+    if (!ctx_ok(c) || !gh) return fail(DSC_E_INVALID, "bad context or graph");
+    Ctx* ctx = as_ctx(c);
+    Graph* g = reinterpret_cast<Graph*>(gh);
+    cudaStreamSynchronize(ctx->stream);
+    cudaGraphExecDestroy(g->exec);
+    cudaGraphDestroy(g->graph);
+    for (Block* b : g->blocks) {
+        if (b->refs <= 0) {
+            cudaFree(b->ptr);
+            delete b;
+        } else {
+            b->arena = -1;  // still referenced by a live buffer: freed when that buffer goes
+        }
+    }
+    delete g;
+    return DSC_OK;
+}
+
+// ---- buffers ------------------------------------------------------------------------------
+int dsc_buf_alloc(dsc_ctx_t c, int dtype, int32_t n, dsc_buf_t* out) {
+    if (!ctx_ok(c) || !out) return fail(DSC_E_INVALID, "bad context or null out");
+    if (dtype != DSC_F32 && dtype != DSC_F64) return fail(DSC_E_DTYPE, "unknown dtype %d", dtype);
+    Buf* b = nullptr;
+    DSC_TRY(buf_new(as_ctx(c), dtype, n, &b));
+    *out = reinterpret_cast<dsc_buf_t>(b);
+    return DSC_OK;
+}
+
+int dsc_buf_alloc_fill(dsc_ctx_t c, int dtype, int32_t n, double v, dsc_buf_t* out) {
+    DSC_TRY(dsc_buf_alloc(c, dtype, n, out));
+    Buf* b = as_buf(*out);
+    int s = fill_window(as_ctx(c), b, 0, n, v);
+    if (s != DSC_OK) {
+        dsc_buf_free(*out);
+        *out = 0;
+    }
+    return s;
+}
+
+int dsc_buf_free(dsc_buf_t h) {
+    if (h == 0) return DSC_OK;
+    Buf* b = as_buf(h);
+    if (!b) return fail(DSC_E_INVALID, "dsc_buf_free: not a live buffer handle");
+    block_release(b->block);
+    b->magic = 0;
+    delete b;
+    return DSC_OK;
+}
+
+static int check_range(Buf* b, int32_t off, int32_t n, const char* what) {
+    if (off < 0 || n < 0 || (int64_t)off + n > b->len)
+        return fail(DSC_E_SHAPE, "%s: range [%d,%d) outside buffer of length %d", what, off, off + n, b->len);
+    return DSC_OK;
+}
+
+int dsc_buf_upload(dsc_buf_t h, int32_t off, const void* host, int32_t n) {
+    Buf* b = as_buf(h);
+    if (!b) return fail(DSC_E_INVALID, "upload: bad handle");
+    DSC_TRY(check_range(b, off, n, "upload"));
+    if (n == 0) return DSC_OK;
+    if (!host) return fail(DSC_E_INVALID, "upload: null host pointer");
+    Ctx* ctx = b->ctx;
+    size_t es = dtype_size(b->dtype);
+    char* dst = reinterpret_cast<char*>(b->block->ptr) + (b->off + off) * es;
+    DSC_CUDA_CHECK(cudaMemcpyAsync(dst, host, (size_t)n * es, cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->capturing) DSC_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // pageable source may be reused by the caller
+    ctx->stats.memcpy_h2d_bytes += (size_t)n * es;
+    return DSC_OK;
+}
+
+int dsc_buf_upload_async(dsc_buf_t h, int32_t off, const void* host, int32_t n) {
+    Buf* b = as_buf(h);
+    if (!b) return fail(DSC_E_INVALID, "upload_async: bad handle");
+    DSC_TRY(check_range(b, off, n, "upload_async"));
+    if (n == 0) return DSC_OK;
+    if (!host) return fail(DSC_E_INVALID, "upload_async: null host pointer");
+    Ctx* ctx = b->ctx;
+    size_t es = dtype_size(b->dtype);
+    char* dst = reinterpret_cast<char*>(b->block->ptr) + (b->off + off) * es;
+    DSC_CUDA_CHECK(cudaMemcpyAsync(dst, host, (size_t)n * es, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.memcpy_h2d_bytes += (size_t)n * es;
+    return DSC_OK;
+}
+
+int dsc_buf_download(dsc_buf_t h, int32_t off, void* host, int32_t n) {
+    Buf* b = as_buf(h);
+    if (!b) return fail(DSC_E_INVALID, "download: bad handle");
+    DSC_TRY(check_range(b, off, n, "download"));
+    if (n == 0) return DSC_OK;
+    if (!host) return fail(DSC_E_INVALID, "download: null host pointer");
+    Ctx* ctx = b->ctx;
+    if (ctx->capturing) return fail(DSC_E_INVALID, "synchronous download while capturing a graph");
+    DSC_TRY(dsc_comm_join(reinterpret_cast<dsc_ctx_t>(ctx)));
+    size_t es = dtype_size(b->dtype);
+    const char* src = reinterpret_cast<const char*>(b->block->ptr) + (b->off + off) * es;
+    DSC_CUDA_CHECK(cudaMemcpyAsync(host, src, (size_t)n * es, cudaMemcpyDeviceToHost, ctx->stream));
+    DSC_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.memcpy_d2h_bytes += (size_t)n * es;
+    return DSC_OK;
+}
+
+int dsc_buf_download_async(dsc_buf_t h, int32_t off, void* host, int32_t n) {
+    Buf* b = as_buf(h);
+    if (!b) return fail(DSC_E_INVALID, "download_async: bad handle");
+    DSC_TRY(check_range(b, off, n, "download_async"));
+    if (n == 0) return DSC_OK;
+    if (!host) return fail(DSC_E_INVALID, "download_async: null host pointer");
+    Ctx* ctx = b->ctx;
+    size_t es = dtype_size(b->dtype);
+    const char* src = reinterpret_cast<const char*>(b->block->ptr) + (b->off + off) * es;
+    DSC_CUDA_CHECK(cudaMemcpyAsync(host, src, (size_t)n * es, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats.memcpy_d2h_bytes += (size_t)n * es;
+    return DSC_OK;
+}
+
+int dsc_buf_fill(dsc_buf_t h, int32_t off, int32_t n, double v) {
+    Buf* b = as_buf(h);
+    if (!b) return fail(DSC_E_INVALID, "fill: bad handle");
+    DSC_TRY(check_range(b, off, n, "fill"));
+    return fill_window(b->ctx, b, off, n, v);
+}
+
+int dsc_buf_view(dsc_buf_t h, int32_t off, int32_t n, dsc_buf_t* out) {
+    Buf* b = as_buf(h);
+    if (!b || !out) return fail(DSC_E_INVALID, "view: bad handle or null out");
+    DSC_TRY(check_range(b, off, n, "view"));
+    Buf* v = new Buf();
+    v->dtype = b->dtype;
+    v->ctx = b->ctx;
+    v->len = n;
+    if (n > 0) {
+        v->block = b->block;
+        v->block->refs++;
+        v->off = b->off + off;
+    }
+    *out = reinterpret_cast<dsc_buf_t>(v);
+    return DSC_OK;
+}
+
+int dsc_buf_copy(dsc_buf_t h, dsc_buf_t* out) {
+    Buf* b = as_buf(h);
+    if (!b || !out) return fail(DSC_E_INVALID, "copy: bad handle or null out");
+    Ctx* ctx = b->ctx;
+    Buf* o = nullptr;
+    DSC_TRY(out_buf(ctx, b->dtype, b->len, out, &o));
+    if (b->len == 0) return DSC_OK;
+    size_t es = dtype_size(b->dtype);
+    DSC_CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<char*>(o->block->ptr) + o->off * es,
+                                   reinterpret_cast<const char*>(b->block->ptr) + b->off * es,
+                                   (size_t)b->len * es, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->stats.kernel_launches++;
+    return DSC_OK;
+}
+
+int dsc_buf_gather2d(dsc_buf_t h, int32_t rows, int32_t cols, int32_t r0, int32_t r1, int32_t c0,
+                     int32_t c1, dsc_buf_t* out) {
+    Buf* b = as_buf(h);
+    if (!b || !out) return fail(DSC_E_INVALID, "gather2d: bad handle or null out");
+    if (rows < 0 || cols < 0 || (int64_t)rows * cols > b->len)
+        return fail(DSC_E_SHAPE, "gather2d: %d x %d exceeds buffer length %d", rows, cols, b->len);
+    if (r0 < 0 || r1 >= rows || c0 < 0 || c1 >= cols || r1 < r0 - 1 || c1 < c0 - 1)
+        return fail(DSC_E_SHAPE, "gather2d: slice [%d..%d, %d..%d] outside %d x %d", r0, r1, c0, c1, rows, cols);
+    int orows = r1 - r0 + 1, ocols = c1 - c0 + 1;
+    Ctx* ctx = b->ctx;
+    Buf* o = nullptr;
+    DSC_TRY(out_buf(ctx, b->dtype, orows * ocols, out, &o));
+    if (orows * ocols == 0) return DSC_OK;
+    int grid = grid_for((size_t)orows * ocols, 256 * 4, ctx->sm_count * 8);
+    if (b->dtype == DSC_F32)
+        gather2d_kernel<float><<<grid, 256, 0, ctx->stream>>>(b->ptr<float>(), o->ptr<float>(), cols, r0, c0, orows, ocols);
+    else
+        gather2d_kernel<double><<<grid, 256, 0, ctx->stream>>>(b->ptr<double>(), o->ptr<double>(), cols, r0, c0, orows, ocols);
+    DSC_LAUNCH_CHECK(ctx);
+    return DSC_OK;
+}
+
+int dsc_buf_info(dsc_buf_t h, int* dtype, int32_t* length, int32_t* offset, int32_t* alloc_length,
+                 void** device_ptr) {
+    Buf* b = as_buf(h);
+    if (!b) return fail(DSC_E_INVALID, "info: bad handle");
+    if (dtype) *dtype = b->dtype;
+    if (length) *length = b->len;
+    if (offset) *offset = (int32_t)b->off;
+    if (alloc_length) *alloc_length = b->block ? (int32_t)std::min<size_t>(b->block->bytes / dtype_size(b->dtype), 0x7fffffff) : 0;
+    if (device_ptr) *device_ptr = b->block ? reinterpret_cast<char*>(b->block->ptr) + b->off * dtype_size(b->dtype) : nullptr;
+    return DSC_OK;
+}
+
+int dsc_host_alloc_pinned(size_t bytes, void** out) {
+    if (!out) return fail(DSC_E_INVALID, "null out");
+    DSC_CUDA_CHECK(cudaMallocHost(out, bytes ? bytes : 1));
+    return DSC_OK;
+}
+
+int dsc_host_free_pinned(void* p) {
+    if (!p) return DSC_OK;
+    DSC_CUDA_CHECK(cudaFreeHost(p));
+    return DSC_OK;
+}
+
+}  // extern "C"

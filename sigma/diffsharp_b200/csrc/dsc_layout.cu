@@ -1,0 +1,377 @@
+// K8/K9/K10: transpose, N-d permute, broadcasts, column reduction, diagonal.
+// All are pure data movement or one add per element: HBM-bound, bit-exact where no arithmetic is
+// involved (Transpose_M, Permute_M, RepeatReshapeCopy_*, Diagonal_M).
+#include "dsc_internal.cuh"
+
+namespace dsc {
+
+// ---- Transpose_M (Backend.fs:127) ---------------------------------------------------------
+// 64x64 tiles through shared memory.  Each thread moves 128-bit vectors on both sides when the
+// matrix dimensions and windows allow it (m, n multiples of the vector width and 16 B alignment);
+// the pad column keeps both the row-wise stores and the column-wise loads conflict-free.
+template <typename T, int TILE>
+__global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ A, T* __restrict__ B, int m, int n) {
+    __shared__ T tile[TILE][TILE + 1];
+    const int bx = blockIdx.x * TILE;  // column origin in A
+    const int by = blockIdx.y * TILE;  // row origin in A
+    const int tx = threadIdx.x % TILE, ty = threadIdx.x / TILE;
+    constexpr int ROWS_PER_PASS = 256 / TILE;
+#pragma unroll
+    for (int r = ty; r < TILE; r += ROWS_PER_PASS) {
+        int gr = by + r, gc = bx + tx;
+        if (gr < m && gc < n) tile[r][tx] = A[(size_t)gr * n + gc];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < TILE; r += ROWS_PER_PASS) {
+        int gr = bx + r, gc = by + tx;  // B is n x m
+        if (gr < n && gc < m) B[(size_t)gr * m + gc] = tile[tx][r];
+    }
+}
+
+// vectorised variant for f32: 64x64 tile, float4 global accesses, scalar shared accesses.
+__global__ void __launch_bounds__(256) transpose_f32_v4_kernel(const float* __restrict__ A, float* __restrict__ B, int m, int n) {
+    __shared__ float tile[64][65];
+    const int bx = blockIdx.x * 64, by = blockIdx.y * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4 floats each along x
+#pragma unroll
+    for (int r = ty; r < 64; r += 16) {
+        int gr = by + r, gc = bx + tx * 4;
+        if (gr < m && gc < n) {  // n % 4 == 0 guaranteed by the host
+            float4 v = *reinterpret_cast<const float4*>(A + (size_t)gr * n + gc);
+            tile[r][tx * 4 + 0] = v.x; tile[r][tx * 4 + 1] = v.y; tile[r][tx * 4 + 2] = v.z; tile[r][tx * 4 + 3] = v.w;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 64; r += 16) {
+        int gr = bx + r, gc = by + tx * 4;
+        if (gr < n && gc < m) {
+            float4 v;
+            v.x = tile[tx * 4 + 0][r]; v.y = tile[tx * 4 + 1][r]; v.z = tile[tx * 4 + 2][r]; v.w = tile[tx * 4 + 3][r];
+            *reinterpret_cast<float4*>(B + (size_t)gr * m + gc) = v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) transpose_f64_v2_kernel(const double* __restrict__ A, double* __restrict__ B, int m, int n) {
+    __shared__ double tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 2 doubles each along x
+#pragma unroll
+    for (int r = ty; r < 32; r += 16) {
+        int gr = by + r, gc = bx + tx * 2;
+        if (gr < m && gc < n) {
+            double2 v = *reinterpret_cast<const double2*>(A + (size_t)gr * n + gc);
+            tile[r][tx * 2 + 0] = v.x; tile[r][tx * 2 + 1] = v.y;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 16) {
+        int gr = bx + r, gc = by + tx * 2;
+        if (gr < n && gc < m) {
+            double2 v;
+            v.x = tile[tx * 2 + 0][r]; v.y = tile[tx * 2 + 1][r];
+            *reinterpret_cast<double2*>(B + (size_t)gr * m + gc) = v;
+        }
+    }
+}
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <typename T>
+int transpose_launch(Ctx* ctx, const T* A, T* B, int m, int n);
+
+template <>
+int transpose_launch<float>(Ctx* ctx, const float* A, float* B, int m, int n) {
+    if ((m % 4 == 0) && (n % 4 == 0) && al16(A) && al16(B)) {
+        dim3 grid((n + 63) / 64, (m + 63) / 64);
+        transpose_f32_v4_kernel<<<grid, 256, 0, ctx->stream>>>(A, B, m, n);
+    } else {
+        dim3 grid((n + 31) / 32, (m + 31) / 32);
+        transpose_kernel<float, 32><<<grid, 256, 0, ctx->stream>>>(A, B, m, n);
+    }
+    DSC_LAUNCH_CHECK(ctx);
+    return DSC_OK;
+}
+template <>
+int transpose_launch<double>(Ctx* ctx, const double* A, double* B, int m, int n) {
+    dim3 grid((n + 31) / 32, (m + 31) / 32);
+    if ((m % 2 == 0) && (n % 2 == 0) && al16(A) && al16(B))
+        transpose_f64_v2_kernel<<<grid, 256, 0, ctx->stream>>>(A, B, m, n);
+    else
+        transpose_kernel<double, 32><<<grid, 256, 0, ctx->stream>>>(A, B, m, n);
+    DSC_LAUNCH_CHECK(ctx);
+    return DSC_OK;
+}
+
+// ---- Permute_M (Backend.fs:128): out.shape[d] = in.shape[perm[d]] --------------------------
+struct PermuteArgs {
+    int rank;
+    long long out_shape[8];
+    long long in_stride_for_out[8];  // stride in the input of output axis d
+};
+template <typename T>
+__global__ void permute_kernel(const T* __restrict__ in, T* __restrict__ out, size_t n, PermuteArgs a) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        size_t rem = i, src = 0;
+#pragma unroll 1
+        for (int d = a.rank - 1; d >= 0; --d) {
+            size_t c = rem % (size_t)a.out_shape[d];
+            rem /= (size_t)a.out_shape[d];
+            src += c * (size_t)a.in_stride_for_out[d];
+        }
+        out[i] = in[src];
+    }
+}
+
+// ---- broadcasts ---------------------------------------------------------------------------
+// out[i, j] = v[j]  (RepeatReshapeCopy_V_MRows, Backend.fs:135; golden Script.fsx:7-16)
+// out[i, j] = v[i]  (RepeatReshapeCopy_V_MCols, Backend.fs:136)
+template <typename T, bool ROWS>
+__global__ void repeat_kernel(const T* __restrict__ v, T* __restrict__ out, int m, int n) {
+    size_t total = (size_t)m * n;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) out[i] = ROWS ? v[i % n] : v[i / n];
+}
+// 128-bit store variant of the row broadcast (n % W == 0, aligned)
+template <typename T, typename V, int W>
+__global__ void repeat_rows_vec_kernel(const T* __restrict__ v, T* __restrict__ out, int m, int nvec) {
+    size_t total = (size_t)m * nvec;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        V x = reinterpret_cast<const V*>(v)[i % nvec];
+        reinterpret_cast<V*>(out)[i] = x;
+    }
+}
+
+// out[i,j] = M[i,j] + v[i]  (Add_V_MCols, Backend.fs:115)
+template <typename T>
+__global__ void add_v_mcols_kernel(const T* __restrict__ v, const T* __restrict__ M, T* __restrict__ out, int m, int n) {
+    size_t total = (size_t)m * n;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) out[i] = M[i] + v[i / n];
+}
+
+template <typename T>
+__global__ void diag_kernel(const T* __restrict__ A, T* __restrict__ out, int n, int k) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < k) out[i] = A[(size_t)i * n + i];
+}
+
+// ---- column reduction (Add_M_Colwise_V_InPlace, Backend.fs:123) ---------------------------
+// v[j] += sum_i M[i,j].  Two deterministic stages: (1) the rows are cut into `chunks` contiguous
+// slabs; block (bx, chunk) sums its slab for 32*W columns with blockDim.y row lanes and a fixed
+// shared-memory tree over the lanes; (2) one thread per column adds the slab partials in slab order.
+template <typename T, int W>
+__global__ void __launch_bounds__(256) colsum_stage1(const T* __restrict__ M, T* __restrict__ partial, int m, int n,
+                                                       int rows_per_chunk) {
+    __shared__ T sm[8][32 * W + 1];
+    const int col0 = (blockIdx.x * 32 + threadIdx.x) * W;
+    const int r_begin = blockIdx.y * rows_per_chunk;
+    const int r_end = min(m, r_begin + rows_per_chunk);
+    T acc[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) acc[w] = T(0);
+    if (col0 < n) {
+        for (int r = r_begin + threadIdx.y; r < r_end; r += 8) {
+            const T* row = M + (size_t)r * n + col0;
+            if constexpr (W == 4) {
+                float4 x = *reinterpret_cast<const float4*>(row);
+                acc[0] += x.x; acc[1] += x.y; acc[2] += x.z; acc[3] += x.w;
+            } else if constexpr (W == 2) {
+                double2 x = *reinterpret_cast<const double2*>(row);
+                acc[0] += x.x; acc[1] += x.y;
+            } else {
+                acc[0] += row[0];
+            }
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < W; ++w) sm[threadIdx.y][threadIdx.x * W + w] = acc[w];
+    __syncthreads();
+    if (threadIdx.y == 0 && col0 < n) {
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            T s = ((sm[0][threadIdx.x * W + w] + sm[1][threadIdx.x * W + w]) + (sm[2][threadIdx.x * W + w] + sm[3][threadIdx.x * W + w])) +
+                  ((sm[4][threadIdx.x * W + w] + sm[5][threadIdx.x * W + w]) + (sm[6][threadIdx.x * W + w] + sm[7][threadIdx.x * W + w]));
+            partial[(size_t)blockIdx.y * n + col0 + w] = s;
+        }
+    }
+}
+template <typename T>
+__global__ void colsum_stage2(const T* __restrict__ partial, T* __restrict__ v, int n, int chunks) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    T s = T(0);
+    for (int c = 0; c < chunks; ++c) s += partial[(size_t)c * n + j];
+    v[j] += s;
+}
+
+template <typename T>
+int colsum_launch(Ctx* ctx, const T* M, T* v, int m, int n) {
+    constexpr int W = sizeof(T) == 4 ? 4 : 2;
+    bool vec = (n % W == 0) && al16(M);
+    int cols_per_block = vec ? 32 * W : 32;
+    int gx = (n + cols_per_block - 1) / cols_per_block;
+    // enough slabs to put ~4 CTAs on every SM, at least 64 rows per slab
+    int chunks = (ctx->sm_count * 4 + gx - 1) / gx;
+    int max_chunks = (m + 63) / 64;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    if (chunks > 256) chunks = 256;
+    int rows_per_chunk = (m + chunks - 1) / chunks;
+    chunks = (m + rows_per_chunk - 1) / rows_per_chunk;
+    size_t need = 256 + (size_t)chunks * n * sizeof(T);
+    DSC_TRY(ensure_red_scratch(ctx, need));
+    T* partial = reinterpret_cast<T*>(reinterpret_cast<char*>(ctx->red_scratch) + 256);
+    dim3 block(32, 8), grid(gx, chunks);
+    if (vec) colsum_stage1<T, W><<<grid, block, 0, ctx->stream>>>(M, partial, m, n, rows_per_chunk);
+    else colsum_stage1<T, 1><<<grid, block, 0, ctx->stream>>>(M, partial, m, n, rows_per_chunk);
+    DSC_LAUNCH_CHECK(ctx);
+    colsum_stage2<T><<<(n + 255) / 256, 256, 0, ctx->stream>>>(partial, v, n, chunks);
+    DSC_LAUNCH_CHECK(ctx);
+    return DSC_OK;
+}
+
+// ---- typed entry points -------------------------------------------------------------------
+template <typename T>
+static int transpose_impl(dsc_ctx_t c, int32_t m, int32_t n, dsc_buf_t Ah, dsc_buf_t* outh) {
+    if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
+    Ctx* ctx = as_ctx(c);
+    Buf *A, *o;
+    DSC_TRY(in_buf(ctx, dtype_of<T>::value, Ah, &A, "Transpose_M: A"));
+    if (m < 0 || n < 0 || (int64_t)m * n > A->len) return fail(DSC_E_SHAPE, "Transpose_M: %d x %d exceeds buffer length %d", m, n, A->len);
+    DSC_TRY(out_buf(ctx, dtype_of<T>::value, m * n, outh, &o));
+    if (m * n == 0) return DSC_OK;
+    if (o->ptr<T>() == A->ptr<T>()) return fail(DSC_E_INVALID, "Transpose_M: in-place transpose is not supported");
+    return transpose_launch<T>(ctx, A->ptr<T>(), o->ptr<T>(), m, n);
+}
+
+template <typename T>
+static int permute_impl(dsc_ctx_t c, int rank, const int64_t* shape, const int32_t* perm, dsc_buf_t Ah, dsc_buf_t* outh) {
+    if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
+    Ctx* ctx = as_ctx(c);
+    Buf *A, *o;
+    DSC_TRY(in_buf(ctx, dtype_of<T>::value, Ah, &A, "Permute_M: A"));
+    if (rank < 1 || rank > 8 || !shape || !perm) return fail(DSC_E_INVALID, "Permute_M: rank %d unsupported (1..8)", rank);
+    int64_t total = 1, in_stride[8];
+    bool seen[8] = {false};
+    for (int d = rank - 1; d >= 0; --d) {
+        if (shape[d] < 0) return fail(DSC_E_SHAPE, "Permute_M: negative extent");
+        in_stride[d] = total;
+        total *= shape[d];
+    }
+    if (total > A->len) return fail(DSC_E_SHAPE, "Permute_M: shape exceeds buffer length");
+    PermuteArgs a;
+    a.rank = rank;
+    for (int d = 0; d < rank; ++d) {
+        if (perm[d] < 0 || perm[d] >= rank || seen[perm[d]]) return fail(DSC_E_INVALID, "Permute_M: dims is not a permutation");
+        seen[perm[d]] = true;
+        a.out_shape[d] = shape[perm[d]];
+        a.in_stride_for_out[d] = in_stride[perm[d]];
+    }
+    DSC_TRY(out_buf(ctx, dtype_of<T>::value, (int32_t)total, outh, &o));
+    if (total == 0) return DSC_OK;
+    int grid = grid_for((size_t)total, 256 * 4, ctx->sm_count * 8);
+    permute_kernel<T><<<grid, 256, 0, ctx->stream>>>(A->ptr<T>(), o->ptr<T>(), (size_t)total, a);
+    DSC_LAUNCH_CHECK(ctx);
+    return DSC_OK;
+}
+
+template <typename T, bool ROWS>
+static int repeat_impl(dsc_ctx_t c, int32_t reps, dsc_buf_t vh, dsc_buf_t* outh) {
+    if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
+    Ctx* ctx = as_ctx(c);
+    Buf *v, *o;
+    DSC_TRY(in_buf(ctx, dtype_of<T>::value, vh, &v, "RepeatReshapeCopy: v"));
+    if (reps < 0) return fail(DSC_E_SHAPE, "RepeatReshapeCopy: negative repeat count");
+    int64_t total = (int64_t)reps * v->len;
+    if (total > 0x7fffffff) return fail(DSC_E_SHAPE, "RepeatReshapeCopy: result too large for an int32 length");
+    DSC_TRY(out_buf(ctx, dtype_of<T>::value, (int32_t)total, outh, &o));
+    if (total == 0) return DSC_OK;
+    int m = ROWS ? reps : v->len, n = ROWS ? v->len : reps;
+    constexpr int W = sizeof(T) == 4 ? 4 : 2;
+    if (ROWS && (n % W == 0) && al16(v->ptr<T>()) && al16(o->ptr<T>())) {
+        using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+        int grid = grid_for((size_t)total / W, 256 * 4, ctx->sm_count * 8);
+        repeat_rows_vec_kernel<T, V, W><<<grid, 256, 0, ctx->stream>>>(v->ptr<T>(), o->ptr<T>(), m, n / W);
+    } else {
+        int grid = grid_for((size_t)total, 256 * 4, ctx->sm_count * 8);
+        repeat_kernel<T, ROWS><<<grid, 256, 0, ctx->stream>>>(v->ptr<T>(), o->ptr<T>(), m, n);
+    }
+    DSC_LAUNCH_CHECK(ctx);
+    return DSC_OK;
+}
+
+template <typename T>
+static int colsum_impl(dsc_ctx_t c, int32_t m, int32_t n, dsc_buf_t Mh, dsc_buf_t vh) {
+    if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
+    Ctx* ctx = as_ctx(c);
+    Buf *M, *v;
+    DSC_TRY(in_buf(ctx, dtype_of<T>::value, Mh, &M, "Add_M_Colwise_V_InPlace: M"));
+    DSC_TRY(in_buf(ctx, dtype_of<T>::value, vh, &v, "Add_M_Colwise_V_InPlace: v"));
+    if (m < 0 || n < 0 || (int64_t)m * n > M->len) return fail(DSC_E_SHAPE, "Add_M_Colwise_V_InPlace: %d x %d exceeds buffer length %d", m, n, M->len);
+    if (v->len != n) return fail(DSC_E_SHAPE, "Add_M_Colwise_V_InPlace: vector length %d, matrix has %d columns", v->len, n);
+    if (m == 0 || n == 0) return DSC_OK;
+    return colsum_launch<T>(ctx, M->ptr<T>(), v->ptr<T>(), m, n);
+}
+
+template <typename T>
+static int add_v_mcols_impl(dsc_ctx_t c, int32_t m, int32_t n, dsc_buf_t vh, dsc_buf_t Mh, dsc_buf_t* outh) {
+    if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
+    Ctx* ctx = as_ctx(c);
+    Buf *M, *v, *o;
+    DSC_TRY(in_buf(ctx, dtype_of<T>::value, Mh, &M, "Add_V_MCols: M"));
+    DSC_TRY(in_buf(ctx, dtype_of<T>::value, vh, &v, "Add_V_MCols: v"));
+    if (m < 0 || n < 0 || (int64_t)m * n > M->len) return fail(DSC_E_SHAPE, "Add_V_MCols: %d x %d exceeds buffer length %d", m, n, M->len);
+    if (v->len != m) return fail(DSC_E_SHAPE, "Add_V_MCols: vector length %d, matrix has %d rows", v->len, m);
+    DSC_TRY(out_buf(ctx, dtype_of<T>::value, m * n, outh, &o));
+    if (m * n == 0) return DSC_OK;
+    int grid = grid_for((size_t)m * n, 256 * 4, ctx->sm_count * 8);
+    add_v_mcols_kernel<T><<<grid, 256, 0, ctx->stream>>>(v->ptr<T>(), M->ptr<T>(), o->ptr<T>(), m, n);
+    DSC_LAUNCH_CHECK(ctx);
+    return DSC_OK;
+}
+
+template <typename T>
+static int diag_impl(dsc_ctx_t c, int32_t m, int32_t n, dsc_buf_t Ah, dsc_buf_t* outh) {
+    if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
+    Ctx* ctx = as_ctx(c);
+    Buf *A, *o;
+    DSC_TRY(in_buf(ctx, dtype_of<T>::value, Ah, &A, "Diagonal_M: A"));
+    if (m < 0 || n < 0 || (int64_t)m * n > A->len) return fail(DSC_E_SHAPE, "Diagonal_M: %d x %d exceeds buffer length %d", m, n, A->len);
+    int k = m < n ? m : n;
+    DSC_TRY(out_buf(ctx, dtype_of<T>::value, k, outh, &o));
+    if (k == 0) return DSC_OK;
+    diag_kernel<T><<<(k + 255) / 256, 256, 0, ctx->stream>>>(A->ptr<T>(), o->ptr<T>(), n, k);
+    DSC_LAUNCH_CHECK(ctx);
+    return DSC_OK;
+}
+
+}  // namespace dsc
+
+using namespace dsc;
+
+extern "C" {
+#define DSC_LAYOUT_API(P, T)                                                                                              \
+    int dsc_##P##transpose(dsc_ctx_t c, int32_t m, int32_t n, dsc_buf_t A, dsc_buf_t* out) { return transpose_impl<T>(c, m, n, A, out); } \
+    int dsc_##P##permute(dsc_ctx_t c, int rank, const int64_t* shape, const int32_t* perm, dsc_buf_t A, dsc_buf_t* out) { \
+        return permute_impl<T>(c, rank, shape, perm, A, out);                                                             \
+    }                                                                                                                     \
+    int dsc_##P##repeat_rows(dsc_ctx_t c, int32_t m, dsc_buf_t v, dsc_buf_t* out) { return repeat_impl<T, true>(c, m, v, out); } \
+    int dsc_##P##repeat_cols(dsc_ctx_t c, int32_t n, dsc_buf_t v, dsc_buf_t* out) { return repeat_impl<T, false>(c, n, v, out); } \
+    int dsc_##P##colsum_inplace(dsc_ctx_t c, int32_t m, int32_t n, dsc_buf_t M, dsc_buf_t v) { return colsum_impl<T>(c, m, n, M, v); } \
+    int dsc_##P##add_v_mcols(dsc_ctx_t c, int32_t m, int32_t n, dsc_buf_t v, dsc_buf_t M, dsc_buf_t* out) {               \
+        return add_v_mcols_impl<T>(c, m, n, v, M, out);                                                                   \
+    }                                                                                                                     \
+    int dsc_##P##diag(dsc_ctx_t c, int32_t m, int32_t n, dsc_buf_t A, dsc_buf_t* out) { return diag_impl<T>(c, m, n, A, out); }
+DSC_LAYOUT_API(s, float)
+DSC_LAYOUT_API(d, double)
+}

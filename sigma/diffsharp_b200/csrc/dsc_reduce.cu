@@ -1,0 +1,307 @@
+// K7: deterministic full reductions (Sum_V/Sum_M, L1Norm_V, L2Norm_V, SupNorm_V, Mul_Dot_V_V,
+// MaxIndex_V, MinIndex_V — reference Backend.fs:81-88).
+//
+// One launch per reduction.  The element -> thread assignment and the combine tree are functions
+// of n only (fixed grid, fixed per-thread stride, warp-shuffle tree, shared-memory tree over warps,
+// and a last-block pass over the per-block partials in block order), so the result is bit-identical
+// from run to run.  HBM-bound: 128-bit loads, 4 independent accumulators per thread.
+#include <float.h>
+
+#include "dsc_internal.cuh"
+
+namespace dsc {
+
+constexpr int kRThreads = 256;
+constexpr int kRUnroll = 4;
+constexpr int kMaxPartials = 148 * 8;
+
+enum { R_SUM = 0, R_ASUM = 1, R_SUMSQ = 2, R_AMAX = 3, R_DOT = 4 };
+
+template <int KIND, typename T>
+__device__ __forceinline__ T r_load(T a, T b) {
+    if constexpr (KIND == R_SUM) return a;
+    else if constexpr (KIND == R_ASUM) return a < T(0) ? -a : a;
+    else if constexpr (KIND == R_SUMSQ) return a * a;
+    else if constexpr (KIND == R_AMAX) return a < T(0) ? -a : a;
+    else return a * b;
+}
+template <int KIND, typename T>
+__device__ __forceinline__ T r_comb(T x, T y) {
+    if constexpr (KIND == R_AMAX) return (x != x) ? x : ((y != y) ? y : (x > y ? x : y));  // NaN-propagating max
+    else return x + y;
+}
+
+template <typename T> struct RVec;
+template <> struct RVec<float> { using type = float4; static constexpr int N = 4; };
+template <> struct RVec<double> { using type = double2; static constexpr int N = 2; };
+__device__ __forceinline__ float rl(const float4& v, int i) { return (&v.x)[i]; }
+__device__ __forceinline__ double rl(const double2& v, int i) { return (&v.x)[i]; }
+
+template <int KIND, typename T>
+__device__ __forceinline__ T block_tree(T v, T* smem) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = r_comb<KIND>(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) smem[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = lane < (kRThreads / 32) ? smem[lane] : T(0);
+#pragma unroll
+        for (int o = (kRThreads / 64); o > 0; o >>= 1) v = r_comb<KIND>(v, __shfl_xor_sync(0xffffffffu, v, o));
+    }
+    __syncthreads();
+    return v;  // valid in thread 0
+}
+
+// scratch layout: [0] ticket (uint32), [64..) T result, [256..) partials
+template <int KIND, typename T, bool VEC>
+__global__ void __launch_bounds__(kRThreads) reduce_kernel(const T* __restrict__ a, const T* __restrict__ b, size_t n,
+                                                            unsigned int* ticket, T* partials, T* result) {
+    __shared__ T smem[kRThreads / 32];
+    __shared__ bool is_last;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    T acc[kRUnroll];
+#pragma unroll
+    for (int u = 0; u < kRUnroll; ++u) acc[u] = T(0);
+    if constexpr (VEC) {
+        using V = typename RVec<T>::type;
+        constexpr int W = RVec<T>::N;
+        const size_t nvec = n / W;
+        size_t i = tid;
+        for (; i + (kRUnroll - 1) * nthreads < nvec; i += kRUnroll * nthreads) {
+            V va[kRUnroll], vb[kRUnroll];
+#pragma unroll
+            for (int u = 0; u < kRUnroll; ++u) {
+                va[u] = *reinterpret_cast<const V*>(a + (i + u * nthreads) * W);
+                if constexpr (KIND == R_DOT) vb[u] = *reinterpret_cast<const V*>(b + (i + u * nthreads) * W);
+                else vb[u] = va[u];
+            }
+#pragma unroll
+            for (int u = 0; u < kRUnroll; ++u)
+#pragma unroll
+                for (int l = 0; l < W; ++l) acc[u] = r_comb<KIND>(acc[u], r_load<KIND>(rl(va[u], l), rl(vb[u], l)));
+        }
+        for (; i < nvec; i += nthreads) {
+            V va = *reinterpret_cast<const V*>(a + i * W), vb = va;
+            if constexpr (KIND == R_DOT) vb = *reinterpret_cast<const V*>(b + i * W);
+#pragma unroll
+            for (int l = 0; l < W; ++l) acc[0] = r_comb<KIND>(acc[0], r_load<KIND>(rl(va, l), rl(vb, l)));
+        }
+        for (size_t j = nvec * W + tid; j < n; j += nthreads)
+            acc[1] = r_comb<KIND>(acc[1], r_load<KIND>(a[j], KIND == R_DOT ? b[j] : a[j]));
+    } else {
+        for (size_t j = tid; j < n; j += nthreads)
+            acc[0] = r_comb<KIND>(acc[0], r_load<KIND>(a[j], KIND == R_DOT ? b[j] : a[j]));
+    }
+    T v = r_comb<KIND>(r_comb<KIND>(acc[0], acc[1]), r_comb<KIND>(acc[2], acc[3]));
+    v = block_tree<KIND>(v, smem);
+    if (gridDim.x == 1) {
+        if (threadIdx.x == 0) *result = v;
+        return;
+    }
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = v;
+        __threadfence();
+        unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // last block: fixed-order pass over the partials
+    T w = T(0);
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) w = r_comb<KIND>(w, partials[i]);
+    w = block_tree<KIND>(w, smem);
+    if (threadIdx.x == 0) {
+        *result = w;
+        *ticket = 0;
+    }
+}
+
+struct ArgPair {
+    double v;  // wide enough for both dtypes (exact for float)
+    int idx;
+};
+
+// better(x, y): does candidate x beat incumbent y?  first occurrence of the extreme value wins,
+// as in the reference's host twin (strict > / <, AD.Float32.fs:1629-1650).
+template <bool MAXI>
+__device__ __forceinline__ bool better(double xv, int xi, double yv, int yi) {
+    if (MAXI) return (xv > yv) || (xv == yv && xi < yi);
+    return (xv < yv) || (xv == yv && xi < yi);
+}
+
+template <typename T, bool MAXI>
+__global__ void __launch_bounds__(kRThreads) argext_kernel(const T* __restrict__ a, int n, unsigned int* ticket,
+                                                            ArgPair* partials, int* result) {
+    __shared__ double sv[kRThreads / 32];
+    __shared__ int si[kRThreads / 32];
+    __shared__ bool is_last;
+    const double init = MAXI ? -INFINITY : INFINITY;
+    double bv = init;
+    int bi = 0x7fffffff;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        double v = (double)a[j];
+        if (better<MAXI>(v, j, bv, bi)) { bv = v; bi = j; }
+    }
+    auto tree = [&](double& v, int& i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, v, o);
+            int oi = __shfl_xor_sync(0xffffffffu, i, o);
+            if (better<MAXI>(ov, oi, v, i)) { v = ov; i = oi; }
+        }
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (lane == 0) { sv[warp] = v; si[warp] = i; }
+        __syncthreads();
+        if (warp == 0) {
+            v = lane < (kRThreads / 32) ? sv[lane] : init;
+            i = lane < (kRThreads / 32) ? si[lane] : 0x7fffffff;
+#pragma unroll
+            for (int o = (kRThreads / 64); o > 0; o >>= 1) {
+                double ov = __shfl_xor_sync(0xffffffffu, v, o);
+                int oi = __shfl_xor_sync(0xffffffffu, i, o);
+                if (better<MAXI>(ov, oi, v, i)) { v = ov; i = oi; }
+            }
+        }
+        __syncthreads();
+    };
+    tree(bv, bi);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x].v = bv;
+        partials[blockIdx.x].idx = bi;
+        __threadfence();
+        unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    bv = init;
+    bi = 0x7fffffff;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x)
+        if (better<MAXI>(partials[i].v, partials[i].idx, bv, bi)) { bv = partials[i].v; bi = partials[i].idx; }
+    tree(bv, bi);
+    if (threadIdx.x == 0) {
+        // sequential twin: if every comparison is false (a[0] is NaN, or nothing beats a[0]) the answer is 0
+        T a0 = a[0];
+        if (a0 != a0 || bi == 0x7fffffff) bi = 0;
+        *result = bi;
+        *ticket = 0;
+    }
+}
+
+template <typename T>
+__global__ void sqrt1_kernel(T* p) { *p = sqrt(*p); }
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Launch a reduction leaving the scalar at `result` (device pointer).
+template <int KIND, typename T>
+static int launch_reduce(Ctx* ctx, const T* a, const T* b, size_t n, T* result) {
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(ctx->red_scratch);
+    T* partials = reinterpret_cast<T*>(reinterpret_cast<char*>(ctx->red_scratch) + 256);
+    bool vec = al16(a) && (KIND != R_DOT || al16(b));
+    size_t items = vec ? n / RVec<T>::N : n;
+    int grid = grid_for(items, kRThreads * kRUnroll * 2, kMaxPartials);
+    if (vec) reduce_kernel<KIND, T, true><<<grid, kRThreads, 0, ctx->stream>>>(a, b, n, ticket, partials, result);
+    else reduce_kernel<KIND, T, false><<<grid, kRThreads, 0, ctx->stream>>>(a, b, n, ticket, partials, result);
+    DSC_LAUNCH_CHECK(ctx);
+    return DSC_OK;
+}
+
+template <typename T>
+static T* result_slot(Ctx* ctx) { return reinterpret_cast<T*>(reinterpret_cast<char*>(ctx->red_scratch) + 64); }
+
+template <typename T>
+static int fetch_scalar(Ctx* ctx, const void* dev, T* out) {
+    if (ctx->capturing)
+        return fail(DSC_E_INVALID, "host-scalar reduction while capturing a graph: use the *_dev variant");
+    DSC_CUDA_CHECK(cudaMemcpyAsync(ctx->red_host, dev, sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    DSC_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    *out = *reinterpret_cast<T*>(ctx->red_host);
+    ctx->stats.memcpy_d2h_bytes += sizeof(T);
+    return DSC_OK;
+}
+
+template <int KIND, typename T>
+static int reduce_scalar(dsc_ctx_t c, dsc_buf_t xh, dsc_buf_t yh, T* out, const char* name) {
+    if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
+    if (!out) return fail(DSC_E_INVALID, "%s: null result pointer", name);
+    Ctx* ctx = as_ctx(c);
+    Buf *x, *y = nullptr;
+    DSC_TRY(in_buf(ctx, dtype_of<T>::value, xh, &x, name));
+    if (KIND == R_DOT) {
+        DSC_TRY(in_buf(ctx, dtype_of<T>::value, yh, &y, name));
+        if (x->len != y->len) return fail(DSC_E_SHAPE, "%s: lengths %d and %d", name, x->len, y->len);
+    }
+    if (x->len == 0) { *out = T(0); return DSC_OK; }
+    T* slot = result_slot<T>(ctx);
+    DSC_TRY((launch_reduce<KIND, T>(ctx, x->ptr<T>(), y ? y->ptr<T>() : nullptr, x->len, slot)));
+    DSC_TRY(fetch_scalar<T>(ctx, slot, out));
+    return DSC_OK;
+}
+
+template <int KIND, typename T>
+static int reduce_dev(dsc_ctx_t c, dsc_buf_t xh, dsc_buf_t yh, dsc_buf_t* outh, const char* name) {
+    if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
+    Ctx* ctx = as_ctx(c);
+    Buf *x, *y = nullptr, *o;
+    DSC_TRY(in_buf(ctx, dtype_of<T>::value, xh, &x, name));
+    if (KIND == R_DOT) {
+        DSC_TRY(in_buf(ctx, dtype_of<T>::value, yh, &y, name));
+        if (x->len != y->len) return fail(DSC_E_SHAPE, "%s: lengths %d and %d", name, x->len, y->len);
+    }
+    DSC_TRY(out_buf(ctx, dtype_of<T>::value, 1, outh, &o));
+    if (x->len == 0) {
+        DSC_CUDA_CHECK(cudaMemsetAsync(o->ptr<T>(), 0, sizeof(T), ctx->stream));
+        return DSC_OK;
+    }
+    return launch_reduce<KIND, T>(ctx, x->ptr<T>(), y ? y->ptr<T>() : nullptr, x->len, o->ptr<T>());
+}
+
+template <typename T, bool MAXI>
+static int argext(dsc_ctx_t c, dsc_buf_t xh, int32_t* out, const char* name) {
+    if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
+    if (!out) return fail(DSC_E_INVALID, "%s: null result pointer", name);
+    Ctx* ctx = as_ctx(c);
+    Buf* x;
+    DSC_TRY(in_buf(ctx, dtype_of<T>::value, xh, &x, name));
+    if (x->len == 0) return fail(DSC_E_SHAPE, "%s of an empty buffer", name);
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(ctx->red_scratch);
+    int* slot = reinterpret_cast<int*>(reinterpret_cast<char*>(ctx->red_scratch) + 64);
+    ArgPair* partials = reinterpret_cast<ArgPair*>(reinterpret_cast<char*>(ctx->red_scratch) + 256);
+    int grid = grid_for(x->len, kRThreads * 8, kMaxPartials);
+    argext_kernel<T, MAXI><<<grid, kRThreads, 0, ctx->stream>>>(x->ptr<T>(), x->len, ticket, partials, slot);
+    DSC_LAUNCH_CHECK(ctx);
+    return fetch_scalar<int32_t>(ctx, slot, out);
+}
+
+template <typename T>
+static int nrm2_impl(dsc_ctx_t c, dsc_buf_t xh, T* out) {
+    T ss = T(0);
+    DSC_TRY((reduce_scalar<R_SUMSQ, T>(c, xh, 0, &ss, "L2Norm_V")));
+    *out = (T)sqrt((double)ss);
+    if (sizeof(T) == 4) *out = sqrtf((float)ss);
+    return DSC_OK;
+}
+
+}  // namespace dsc
+
+using namespace dsc;
+
+extern "C" {
+#define DSC_RED_API(P, T)                                                                                           \
+    int dsc_##P##dot(dsc_ctx_t c, dsc_buf_t x, dsc_buf_t y, T* out) { return reduce_scalar<R_DOT, T>(c, x, y, out, "Mul_Dot_V_V"); } \
+    int dsc_##P##asum(dsc_ctx_t c, dsc_buf_t x, T* out) { return reduce_scalar<R_ASUM, T>(c, x, 0, out, "L1Norm_V"); }  \
+    int dsc_##P##nrm2(dsc_ctx_t c, dsc_buf_t x, T* out) { return nrm2_impl<T>(c, x, out); }                          \
+    int dsc_##P##amax(dsc_ctx_t c, dsc_buf_t x, T* out) { return reduce_scalar<R_AMAX, T>(c, x, 0, out, "SupNorm_V"); } \
+    int dsc_##P##sum(dsc_ctx_t c, dsc_buf_t x, T* out) { return reduce_scalar<R_SUM, T>(c, x, 0, out, "Sum_V"); }      \
+    int dsc_##P##argmax(dsc_ctx_t c, dsc_buf_t x, int32_t* out) { return argext<T, true>(c, x, out, "MaxIndex_V"); }   \
+    int dsc_##P##argmin(dsc_ctx_t c, dsc_buf_t x, int32_t* out) { return argext<T, false>(c, x, out, "MinIndex_V"); }  \
+    int dsc_##P##sum_dev(dsc_ctx_t c, dsc_buf_t x, dsc_buf_t* out) { return reduce_dev<R_SUM, T>(c, x, 0, out, "Sum_V"); } \
+    int dsc_##P##dot_dev(dsc_ctx_t c, dsc_buf_t x, dsc_buf_t y, dsc_buf_t* out) { return reduce_dev<R_DOT, T>(c, x, y, out, "Mul_Dot_V_V"); }
+DSC_RED_API(s, float)
+DSC_RED_API(d, double)
+}
