@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on BASELINE.json's config.
+
+metric  : "MLP grad steps/sec" on config 3 (784-1024-1024-10 tanh MLP, global batch 8192, float32,
+          batch rows sharded over N GPUs, NCCL all-reduce of the weight/bias adjoints), plus the
+          backend-op sweep (config 2, 4096x4096 f32/f64) as HBM GB/s and GEMM TFLOP/s vs peak.
+A "step" = one reverse-mode gradient of the summed-squared-error loss: the full Backend<'T> call
+sequence the unchanged AD layer issues (zero-adjoint fills, transposes, adjoint accumulations, loss
+reduction) on this rank's rows + ONE all-reduce of the adjoints.  Global batch is fixed => strong
+scaling.
+
+  value : device-timed, inputs resident in HBM, the step replayed as a CUDA graph of the captured
+          call sequence (every kernel of the eager sequence runs; the host tape walk does not).
+  eager : the same step driven op by op through the plugin interface (reported next to it).
+  e2e   : through the public plugin call (workloads.mlp_grad over CudaBackend) with HOST buffers:
+          every step uploads its X/Y rows from pinned host memory and reads the loss and all
+          adjoints back to pinned host memory.
+
+`--impl reference` times the CPU oracle (oracle/: the same call sequence over OpenBLAS — the
+reference's own F#/OpenBLAS stack cannot be built here) on the box's host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LAYERS = [784, 1024, 1024, 10]
+GLOBAL_BATCH = 8192
+# algorithmic GEMM work of one C3 step = fwd + dW + dH
+STEP_GFLOP = 78.35
+ALLREDUCE_MB = 7.45
+
+
+def load_peaks():
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback"}
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            peaks.update(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d["bf16_tflops"]),
+                         bf16_tflops_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+        except Exception:
+            pass
+    # TF32 / FP64 GEMM peaks are not in MEASURED_PEAKS.json; tools/measure_peaks.py records cuBLAS numbers
+    q = os.path.join(ROOT, "profiles", "gemm_peaks.json")
+    if os.path.exists(q):
+        try:
+            d = json.load(open(q))
+            peaks["tf32_tflops"] = float(d["tf32_tflops"])
+            peaks["fp64_tflops"] = float(d["fp64_tflops"])
+            peaks["gemm_source"] = "measured cuBLAS (profiles/gemm_peaks.json)"
+        except Exception:
+            pass
+    if "tf32_tflops" not in peaks:
+        peaks["tf32_tflops"] = peaks["bf16_tflops"] / 2.0   # tensor pipe: TF32 = 1/2 bf16 rate
+        peaks["fp64_tflops"] = 40.0                         # B200 datasheet
+        peaks["gemm_source"] = "derived (bf16/2; datasheet fp64)"
+    return peaks
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.samples, self._stop = device, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def pinned_array(lib, check, shape, dtype):
+    n = int(np.prod(shape))
+    p = C.c_void_p()
+    check(lib.dsc_host_alloc_pinned(n * np.dtype(dtype).itemsize, C.byref(p)))
+    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape), p
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm: the oracle's OpenBLAS path executing the same call sequence, all host threads."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from oracle.backend import OracleBackend, get_num_threads, openblas_info, set_num_threads
+    from sigma.diffsharp_b200 import workloads as wl
+    from sigma.diffsharp_b200.config import DictBackendProvider, GlobalConfig
+    cores = os.cpu_count() or 1
+    set_num_threads(cores)
+    GlobalConfig.BackendProvider = DictBackendProvider(OracleBackend(np.float32), OracleBackend(np.float64))
+    sample_rows = GLOBAL_BATCH // 8  # bounded sample: 1/8 of the batch rows per timed step
+    X, Y, Ws, bs = wl.mlp_inputs(LAYERS, GLOBAL_BATCH, row_range=(0, sample_rows))
+    dX, dY = wl.to_DM(X), wl.to_DM(Y)
+    dWs, dbs = [wl.to_DM(w) for w in Ws], [wl.to_DV(b) for b in bs]
+    for _ in range(max(1, min(args.warmup, 2))):
+        wl.mlp_grad(dX, dY, dWs, dbs)
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        wl.mlp_grad(dX, dY, dWs, dbs)
+        times.append(time.perf_counter() - t0)
+    t_sample = sum(times) / len(times)
+    t_step = t_sample * (GLOBAL_BATCH / sample_rows)  # every cost of the step is linear in the batch rows
+    value = 1.0 / t_step
+    sample = (f"{sample_rows} of {GLOBAL_BATCH} batch rows per timed step, scaled x{GLOBAL_BATCH // sample_rows}; "
+              f"{openblas_info()}; threads={get_num_threads()}")
+    line = {
+        "impl": "reference", "metric": "MLP grad steps/sec", "value": value, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C3: reverse-mode grad of 784-1024-1024-10 tanh MLP loss, global batch 8192, float32"},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def time_kernel(ctx, fn, iters=10, flush=True):
+    """Average device time (ms) of fn() over `iters` launches, L2 flushed before every launch, CUDA
+    events on the launching stream."""
+    fn()
+    ctx.sync()
+    e0, e1 = ctx.event(), ctx.event()
+    tot = 0.0
+    for _ in range(iters):
+        if flush:
+            ctx.flush_l2()
+        ctx.record(e0)
+        fn()
+        ctx.record(e1)
+        tot += ctx.elapsed_ms(e0, e1)
+    ctx.event_destroy(e0)
+    ctx.event_destroy(e1)
+    return tot / iters
+
+
+def op_sweep(provider, peaks, n=4096):
+    """config 2: Mul_M_M, Mul_Had_M_M, Map_F_M tanh/exp, Sum_M, Transpose_M at 4096x4096, f32 and f64."""
+    from sigma.diffsharp_b200.backend import CudaBackend, MapOp
+    from sigma.diffsharp_b200.buffers import ShapedDataBufferView
+    out = {}
+    ctx = provider.ctx
+    for dtype, name in ((np.float32, "f32"), (np.float64, "f64")):
+        b = CudaBackend(dtype, ctx=ctx, fuse=False)
+        es = np.dtype(dtype).itemsize
+        rng = np.random.default_rng(2)
+        A = ShapedDataBufferView(b.CreateDataBuffer((rng.random(n * n) * 2 - 1).astype(dtype)), n, n)
+        Bm = ShapedDataBufferView(b.CreateDataBuffer((rng.random(n * n) * 2 - 1).astype(dtype)), n, n)
+        N = n * n
+        cases = {
+            "Mul_Had_M_M": (lambda: b.Mul_Had_M_M(A, Bm), 3 * N * es),
+            "Map_F_M_tanh": (lambda: b.Map_F_M(MapOp.Tanh, None, A), 2 * N * es),
+            "Map_F_M_exp": (lambda: b.Map_F_M(MapOp.Exp, None, A), 2 * N * es),
+            "Sum_M": (lambda: b.Sum_M(A.DataBuffer), N * es),
+            "Transpose_M": (lambda: b.Transpose_M(A), 2 * N * es),
+        }
+        for k, (fn, nbytes) in cases.items():
+            ms = time_kernel(ctx, fn, iters=10)
+            gbs = nbytes / ms / 1e6
+            out[f"{k}_{name}"] = {"ms": round(ms, 5), "GB/s": round(gbs, 1), "frac_hbm": round(gbs / peaks["hbm_gbs"], 3)}
+        ms = time_kernel(ctx, lambda: b.Mul_M_M(A, Bm), iters=5)
+        tf = 2.0 * n ** 3 / ms / 1e9
+        peak = peaks["tf32_tflops"] / 3.0 if dtype == np.float32 else peaks["fp64_tflops"]
+        out[f"Mul_M_M_{name}"] = {"ms": round(ms, 4), "TFLOP/s": round(tf, 2), "peak": round(peak, 1), "frac": round(tf / peak, 3),
+                                  "roofline": "3xTF32 = TF32 peak / 3" if dtype == np.float32 else "FP64 tensor"}
+    return out
+
+
+def run_ours(args):
+    from sigma.diffsharp_b200 import _lib, dist as D, workloads as wl
+    from sigma.diffsharp_b200._lib import check, lib
+    from sigma.diffsharp_b200.buffers import CudaDataBuffer, ShapedDataBufferView
+    from sigma.diffsharp_b200.config import CudaBackendProvider, GlobalConfig
+    from sigma.diffsharp_b200.ad import DNDArray
+
+    rank, world = D.init_process_group()
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    peaks = load_peaks()
+    provider = CudaBackendProvider(device=local)
+    GlobalConfig.BackendProvider = provider
+    ctx = provider.ctx
+    backend = provider.GetBackend(np.float32(0)).BackendHandle
+    comm = D.NcclComm(ctx)
+
+    r0, r1 = D.shard_range(GLOBAL_BATCH, rank, world)
+    X, Y, Ws, bs = wl.mlp_inputs(LAYERS, GLOBAL_BATCH, row_range=(r0, r1))
+    rows = r1 - r0
+    dX, dY = wl.to_DM(X), wl.to_DM(Y)
+    dWs, dbs = [wl.to_DM(w) for w in Ws], [wl.to_DV(b) for b in bs]
+
+    def eager_step():
+        L, dW, db = D.sharded_mlp_grad(comm, dX, dY, dWs, dbs)
+        comm.join()
+        return L, dW, db
+
+    # ---- warm-up (also sizes the GEMM workspace and the pool before capture) ----
+    for _ in range(max(args.warmup, 3)):
+        eager_step()
+    ctx.sync()
+
+    # ---- eager timing: the plugin interface driven op by op ----
+    s0 = ctx.stats()
+    e0, e1 = ctx.event(), ctx.event()
+    D.barrier(); ctx.sync()
+    ctx.record(e0)
+    for _ in range(args.steps):
+        eager_step()
+    ctx.record(e1)
+    ctx.sync(); D.barrier()
+    eager_ms = D.max_over_ranks(ctx.elapsed_ms(e0, e1)) / args.steps
+    launches_per_step = (ctx.stats()["kernel_launches"] - s0["kernel_launches"]) // args.steps
+
+    # ---- capture the step's call sequence once, replay it as a CUDA graph ----
+    backend.capture_scalars = []
+    ctx.graph_begin()
+    try:
+        _, gW, gb = D.sharded_mlp_grad(comm, dX, dY, dWs, dbs)
+    finally:
+        graph = ctx.graph_end()
+        loss_bufs, backend.capture_scalars = backend.capture_scalars, None
+    for _ in range(max(args.warmup, 3)):
+        ctx.graph_launch(graph)
+    ctx.sync()
+    sampler = ClockSampler(local)
+    sampler.start()
+    D.barrier(); ctx.sync()
+    ctx.record(e0)
+    for _ in range(args.steps):
+        ctx.graph_launch(graph)
+    ctx.record(e1)
+    ctx.sync(); D.barrier()
+    graph_ms = D.max_over_ranks(ctx.elapsed_ms(e0, e1)) / args.steps
+    clocks = sampler.stop()
+    loss_graph = float(loss_bufs[0].SubData[0])
+
+    # ---- e2e: host buffers in, loss + adjoints out, through the public plugin call ----
+    hX, _pX = pinned_array(lib, check, X.shape, np.float32)
+    hY, _pY = pinned_array(lib, check, Y.shape, np.float32)
+    hX[...] = X
+    hY[...] = Y
+    n_params = sum(w.size for w in Ws) + sum(b.size for b in bs)
+    hG, _pG = pinned_array(lib, check, (n_params,), np.float32)
+    bX = CudaDataBuffer.empty(ctx, np.float32, X.size)
+    bY = CudaDataBuffer.empty(ctx, np.float32, Y.size)
+    eX, eY = DNDArray(ShapedDataBufferView(bX, *X.shape)), DNDArray(ShapedDataBufferView(bY, *Y.shape))
+
+    def e2e_step():
+        check(lib.dsc_buf_upload_async(bX.handle, 0, hX.ctypes.data, X.size))
+        check(lib.dsc_buf_upload_async(bY.handle, 0, hY.ctypes.data, Y.size))
+        L, dW, db = D.sharded_mlp_grad(comm, eX, eY, dWs, dbs)   # Sum_M inside returns the loss to the host
+        comm.join()
+        off = 0
+        for a in [w.Buffer.DataBuffer for w in dW] + [v.Buffer for v in db]:
+            check(lib.dsc_buf_download_async(a.handle, 0, hG.ctypes.data + 4 * off, a.Length))
+            off += a.Length
+        ctx.sync()
+        return float(L)
+
+    for _ in range(3):
+        e2e_step()
+    D.barrier(); ctx.sync()
+    ctx.record(e0)
+    for _ in range(args.steps):
+        loss_e2e = e2e_step()
+    ctx.record(e1)
+    ctx.sync(); D.barrier()
+    e2e_ms = D.max_over_ranks(ctx.elapsed_ms(e0, e1)) / args.steps
+    h2d = (X.size + Y.size) * 4
+    d2h = n_params * 4 + 4
+
+    # ---- roofline of the dominant kernel: the f32 GEMM of the widest layer, as launched in the step ----
+    from sigma.diffsharp_b200.backend import CudaBackend
+    rb = CudaBackend(np.float32, ctx=ctx, fuse=False)
+    rng = np.random.default_rng(0)
+    Am = ShapedDataBufferView(rb.CreateDataBuffer((rng.random(rows * 1024) * 2 - 1).astype(np.float32)), rows, 1024)
+    Bm = ShapedDataBufferView(rb.CreateDataBuffer((rng.random(1024 * 1024) * 2 - 1).astype(np.float32)), 1024, 1024)
+    gemm_ms = time_kernel(ctx, lambda: rb.Mul_M_M(Am, Bm), iters=20, flush=False)
+    gemm_flop = 2.0 * rows * 1024 * 1024
+    achieved = gemm_flop / gemm_ms / 1e9
+    peak3 = peaks["tf32_tflops"] / 3.0
+    st = ctx.stats()
+    roofline = {"bound": "tensor", "achieved": round(achieved, 2), "peak": round(peak3, 2), "unit": "TFLOP/s",
+                "frac": round(achieved / peak3, 4), "traffic": None,
+                "kernel": f"Mul_M_M f32 {rows}x1024x1024 (hidden-layer GEMM of the step); includes the hi/lo operand split pre-pass",
+                "peak_source": f"3xTF32 roofline = TF32 GEMM peak / 3; TF32 peak {peaks['gemm_source']}",
+                "gemm_path": {"tcgen05": st["gemm_tcgen05"], "simt": st["gemm_simt"], "dmma": st["gemm_dmma"]}}
+
+    line = {
+        "metric": "MLP grad steps/sec", "value": round(1e3 / graph_ms, 3), "unit": "steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(graph_ms, 4), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C3: reverse-mode grad of 784-1024-1024-10 tanh MLP loss, global batch 8192, float32",
+                   "global_batch": GLOBAL_BATCH, "rows_per_gpu": rows, "parallelism": f"batch-row shards x{world} + NCCL all-reduce of adjoints ({ALLREDUCE_MB} MB)",
+                   "mode": "CUDA-graph replay of the captured Backend<'T> call sequence",
+                   "l2": f"no flush between steps: per-rank working set {st['pool_bytes_reserved'] / 1e6:.0f} MB streams through the 126 MB L2"},
+        "eager": {"value": round(1e3 / eager_ms, 3), "unit": "steps/s", "ms_per_step": round(eager_ms, 4),
+                  "note": "same step driven op by op from Python through the C ABI (host-bound)"},
+        "e2e": {"value": round(1e3 / e2e_ms, 3), "unit": "steps/s", "ms_per_step": round(e2e_ms, 4),
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "launches_per_step": int(launches_per_step),
+        "step_gflop": STEP_GFLOP, "step_tflops": round(STEP_GFLOP / world / graph_ms, 2),
+        "loss": loss_graph, "loss_e2e": loss_e2e,
+        "clocks": clocks, "roofline": roofline, "peaks": peaks,
+    }
+    if world == 1 and rank == 0 and not args.no_sweep:
+        line["op_sweep"] = op_sweep(provider, peaks)
+    if world == 1 and rank == 0 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    comm.close()
+
+
+def cpu_baseline():
+    """The oracle (port of the reference's call sequence over OpenBLAS) on the host cores, bounded sample."""
+    from oracle.backend import OracleBackend, get_num_threads, openblas_info, set_num_threads
+    from sigma.diffsharp_b200 import workloads as wl
+    from sigma.diffsharp_b200.config import DictBackendProvider, GlobalConfig
+    cores = os.cpu_count() or 1
+    set_num_threads(cores)
+    old = GlobalConfig.BackendProvider
+    GlobalConfig.BackendProvider = DictBackendProvider(OracleBackend(np.float32), OracleBackend(np.float64))
+    try:
+        sample_rows = GLOBAL_BATCH // 8
+        X, Y, Ws, bs = wl.mlp_inputs(LAYERS, GLOBAL_BATCH, row_range=(0, sample_rows))
+        dX, dY = wl.to_DM(X), wl.to_DM(Y)
+        dWs, dbs = [wl.to_DM(w) for w in Ws], [wl.to_DV(b) for b in bs]
+        wl.mlp_grad(dX, dY, dWs, dbs)
+        times = []
+        t_end = time.perf_counter() + 15.0
+        while len(times) < 3 or (time.perf_counter() < t_end and len(times) < 20):
+            t0 = time.perf_counter()
+            wl.mlp_grad(dX, dY, dWs, dbs)
+            times.append(time.perf_counter() - t0)
+        t_step = statistics.median(times) * (GLOBAL_BATCH / sample_rows)
+        return {"value": round(1.0 / t_step, 4), "unit": "steps/s", "cores": get_num_threads(), "kind": "port",
+                "sample": f"{len(times)} timed steps of {sample_rows}/{GLOBAL_BATCH} batch rows, scaled x8 (costs are linear in rows); {openblas_info()}"}
+    finally:
+        GlobalConfig.BackendProvider = old
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-sweep", action="store_true", help="skip the config-2 op sweep")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

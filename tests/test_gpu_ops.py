@@ -1,0 +1,197 @@
+"""Parity of every Backend<'T> member: CUDA path (through the C ABI) vs the CPU oracle on the same
+seeded inputs.  Tolerances (north_star): bit-exact for Transpose / reshape / indexing / broadcast
+copies; relative error <= 1e-5 (float32) and <= 1e-12 (float64) elsewhere, measured norm-wise
+(max |gpu - ref| / max |ref|); GEMM-class ops against the backward-error bound rtol * (|A| |B|)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+import make_golden as mg  # noqa: E402
+from _util import rel_err  # noqa: E402
+
+from oracle.backend import OracleBackend  # noqa: E402
+from sigma.diffsharp_b200 import _lib  # noqa: E402
+from sigma.diffsharp_b200.backend import MapOp  # noqa: E402
+from sigma.diffsharp_b200.buffers import CudaDataBuffer, NativeDataBuffer, ShapedDataBufferView  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+RTOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-12}
+EXACT = ("argmax", "argmin", "transpose", "repeat_rows", "repeat_cols", "diag", "permute")
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden.npz"))
+
+
+def backend(provider, dtype):
+    return provider.GetBackend(np.dtype(dtype).type(0)).BackendHandle
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_every_op_against_oracle_and_goldens(cuda_provider, dtype):
+    b = backend(cuda_provider, dtype)
+    inp = mg.op_inputs(dtype)
+    got = mg.run_ops(b, inp)
+    ref = mg.run_ops(OracleBackend(dtype), inp)
+    name = "f32" if dtype == np.float32 else "f64"
+    for k in ref:
+        if k in EXACT:
+            assert np.array_equal(got[k], ref[k]), k
+            assert np.array_equal(got[k], GOLD[f"{name}_{k}"]), k
+        else:
+            scale = 100 if k in ("solve", "inverse", "det") else 1  # conditioning of the 6x6 solve
+            assert rel_err(got[k], ref[k]) <= RTOL[np.dtype(dtype)] * scale, k
+            assert rel_err(got[k], GOLD[f"{name}_{k}"]) <= RTOL[np.dtype(dtype)] * scale, k
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [1, 3, 31, 1000, 4097, 1 << 20])
+def test_elementwise_sizes_and_misaligned_views(cuda_provider, dtype, n):
+    b, o = backend(cuda_provider, dtype), OracleBackend(dtype)
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n + 3).astype(dtype)
+    y = rng.standard_normal(n + 3).astype(dtype)
+    for off in (0, 1, 3):  # views at odd offsets are not 16-byte aligned: scalar path
+        dx = b.CreateDataBuffer(x).GetValues(off, n)
+        dy = b.CreateDataBuffer(y).GetValues(off, n)
+        hx, hy = NativeDataBuffer(x, off, n), NativeDataBuffer(y, off, n)
+        for op in (MapOp.Tanh, MapOp.Exp, MapOp.Cosh, MapOp.Sigmoid, MapOp.Abs, MapOp.Sign, MapOp.ReL):
+            assert rel_err(b.Map_F_V(op, None, dx).SubData, o.Map_F_V(op, None, hx).SubData) <= RTOL[np.dtype(dtype)], (op, off)
+        assert np.array_equal(b.Add_V_V(dx, dy).SubData, o.Add_V_V(hx, hy).SubData)
+        assert np.array_equal(b.Sub_V_V(dx, dy).SubData, o.Sub_V_V(hx, hy).SubData)
+        assert np.array_equal(b.Map2_F_V_V(MapOp.Mul, None, dx, dy).SubData, o.Map2_F_V_V(MapOp.Mul, None, hx, hy).SubData)
+        assert np.array_equal(b.Mul_S_V(dtype(0.3), dx).SubData, o.Mul_S_V(dtype(0.3), hx).SubData)
+        # reductions: compare both to an exact float64 sum
+        exact = float(np.sum(x[off:off + n].astype(np.float64)))
+        bound = RTOL[np.dtype(dtype)] * float(np.sum(np.abs(x[off:off + n].astype(np.float64))))
+        assert abs(float(b.Sum_V(dx)) - exact) <= bound
+        assert abs(float(b.Mul_Dot_V_V(dx, dy)) - float(x[off:off + n].astype(np.float64) @ y[off:off + n].astype(np.float64))) <= RTOL[np.dtype(dtype)] * float(np.abs(x[off:off + n].astype(np.float64)) @ np.abs(y[off:off + n].astype(np.float64)))
+        assert abs(float(b.L2Norm_V(dx)) - float(np.linalg.norm(x[off:off + n].astype(np.float64)))) <= RTOL[np.dtype(dtype)] * float(np.linalg.norm(x[off:off + n].astype(np.float64)))
+        assert float(b.SupNorm_V(dx)) == float(np.abs(x[off:off + n]).max())
+        assert b.MaxIndex_V(dx) == int(np.argmax(x[off:off + n])) and b.MinIndex_V(dx) == int(np.argmin(x[off:off + n]))
+
+
+def test_reductions_are_deterministic(cuda_provider):
+    b = backend(cuda_provider, np.float32)
+    x = b.CreateDataBuffer(np.random.default_rng(0).standard_normal(3_000_001).astype(np.float32))
+    vals = {float(b.Sum_V(x)) for _ in range(5)}
+    assert len(vals) == 1
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_edge_semantics_match_oracle(cuda_provider, dtype):
+    b, o = backend(cuda_provider, dtype), OracleBackend(dtype)
+    sp = np.array([np.nan, np.inf, -np.inf, 0.0, -0.0, 0.5, 1.5, 2.5, -0.5, -1.5, 1e-40, -3.0], dtype)
+    for op in (MapOp.Sign, MapOp.Round, MapOp.ReL, MapOp.Abs, MapOp.Floor, MapOp.Ceiling):
+        g = b.Map_F_V(op, None, b.CreateDataBuffer(sp)).SubData
+        r = o.Map_F_V(op, None, NativeDataBuffer(sp)).SubData
+        assert np.array_equal(g, r, equal_nan=True), op
+    # empty operands: foreign zero-length host buffers reach the backend
+    x = b.CreateDataBuffer(np.array([1, 2, 3], dtype))
+    empty = NativeDataBuffer(np.empty(0, dtype))
+    assert np.array_equal(b.Add_V_V(x, empty).SubData, [1, 2, 3])
+    assert np.array_equal(b.Add_V_V(empty, x).SubData, [1, 2, 3])
+    assert np.array_equal(b.Sub_V_V(empty, x).SubData, [-1, -2, -3])
+    m = ShapedDataBufferView(b.CreateDataBuffer(np.ones(6, dtype)), 2, 3)
+    z = ShapedDataBufferView(empty, 0, 0)
+    assert np.array_equal(b.Add_M_M_InPlace(m, z).DataBuffer.SubData, np.ones(6))
+    assert b.Sum_V(empty) == 0 and b.Mul_Dot_V_V(empty, empty) == 0
+    # foreign (host) buffers are uploaded on first touch (App. D-2)
+    host = NativeDataBuffer(np.array([4, 5, 6], dtype))
+    assert np.array_equal(b.Add_V_V(x, host).SubData, [5, 7, 9])
+    # first occurrence; a[0] = NaN pins index 0 like the sequential twin
+    assert b.MaxIndex_V(b.CreateDataBuffer(np.array([1, 5, 5, 2], dtype))) == 1
+    assert b.MaxIndex_V(b.CreateDataBuffer(np.array([np.nan, 5], dtype))) == 0
+    # singular -> None, closures never executed
+    zz = ShapedDataBufferView(b.CreateDataBuffer(np.zeros(4, dtype)), 2, 2)
+    assert b.Solve_M_V(zz, b.CreateDataBuffer(np.ones(2, dtype))) is None and b.Inverse_M(zz) is None
+    with pytest.raises(_lib.NotSupportedError):
+        b.Map_F_V(MapOp.Mul, lambda v: v * 2, x)
+    with pytest.raises(_lib.NotSupportedError):
+        b.Map_F_V(99, lambda v: v, x)
+    with pytest.raises(_lib.InvalidArgError):
+        b.Add_V_V(x, b.CreateDataBuffer(np.ones(2, dtype)))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(1, 1), (3, 5), (33, 65), (64, 64), (100, 257), (1024, 768), (10, 8192)])
+def test_transpose_bit_exact_and_involutive(cuda_provider_nofuse, dtype, shape):
+    b = backend(cuda_provider_nofuse, dtype)
+    a = np.random.default_rng(1).standard_normal(shape).astype(dtype)
+    v = ShapedDataBufferView(b.CreateDataBuffer(a.reshape(-1)), *shape)
+    t = b.Transpose_M(v)
+    assert t.Shape == (shape[1], shape[0])
+    assert np.array_equal(t.to_numpy(), a.T)
+    assert np.array_equal(b.Transpose_M(t).to_numpy(), a)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("m,k,n", [(1, 1, 1), (5, 7, 3), (128, 784, 300), (128, 300, 10), (300, 128, 10), (257, 129, 65),
+                                   (512, 512, 512), (1024, 96, 2048), (64, 4096, 64)])
+def test_gemm_all_transposes_against_openblas(cuda_provider, dtype, m, k, n):
+    """Mul_M_M and the transposed-operand forms of dsc_?gemm (what Transpose_M + Mul_M_M computes)."""
+    import ctypes as C
+    b, o = backend(cuda_provider, dtype), OracleBackend(dtype)
+    rng = np.random.default_rng(m * 1000 + n)
+    A = (rng.random((m, k)) * 2 - 1).astype(dtype)
+    B = (rng.random((k, n)) * 2 - 1).astype(dtype)
+    bias = rng.standard_normal(m).astype(dtype)
+    bound = RTOL[np.dtype(dtype)] * (np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64))
+    for ta in (0, 1):
+        for tb in (0, 1):
+            As = np.ascontiguousarray(A.T if ta else A)
+            Bs = np.ascontiguousarray(B.T if tb else B)
+            ref = o.gemm(ta, tb, m, n, k, As.reshape(-1), Bs.reshape(-1), bias).reshape(m, n).astype(np.float64)
+            dA, dB, dbias = b.CreateDataBuffer(As.reshape(-1)), b.CreateDataBuffer(Bs.reshape(-1)), b.CreateDataBuffer(bias)
+            out = b._out(b._f["gemm"], m * n, ta, tb, m, n, k, dA.handle, dB.handle, dbias.handle)
+            got = out.SubData.reshape(m, n).astype(np.float64)
+            assert np.all(np.abs(got - ref) <= bound + 1e-30), (ta, tb, float(np.abs(got - ref).max()), float(bound.min()))
+            exact = A.astype(np.float64) @ B.astype(np.float64) + bias.astype(np.float64)[:, None]
+            assert np.all(np.abs(got - exact) <= bound + RTOL[np.dtype(dtype)] * np.abs(bias).max())
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_gemv_ger_colsum_larger(cuda_provider, dtype):
+    b, o = backend(cuda_provider, dtype), OracleBackend(dtype)
+    rng = np.random.default_rng(9)
+    for m, n in [(1, 1), (7, 13), (1000, 10), (10, 1000), (2048, 1024), (513, 1027)]:
+        A = rng.standard_normal((m, n)).astype(dtype)
+        x, y = rng.standard_normal(n).astype(dtype), rng.standard_normal(m).astype(dtype)
+        dv = ShapedDataBufferView(b.CreateDataBuffer(A.reshape(-1)), m, n)
+        hv = ShapedDataBufferView(NativeDataBuffer(A.reshape(-1)), m, n)
+        tol = RTOL[np.dtype(dtype)]
+        assert rel_err(b.Mul_M_V(dv, b.CreateDataBuffer(x)).SubData, o.Mul_M_V(hv, NativeDataBuffer(x)).SubData) <= tol
+        assert rel_err(b.Mul_V_M(b.CreateDataBuffer(y), dv).SubData, o.Mul_V_M(NativeDataBuffer(y), hv).SubData) <= tol
+        assert np.array_equal(b.Mul_Out_V_V(b.CreateDataBuffer(y), b.CreateDataBuffer(x)).to_numpy(), np.outer(y, x).astype(dtype))
+        acc_d, acc_h = b.CreateDataBuffer(x), NativeDataBuffer(x.copy())
+        b.Add_M_Colwise_V_InPlace(dv, acc_d)
+        o.Add_M_Colwise_V_InPlace(hv, acc_h)
+        exact = x.astype(np.float64) + A.astype(np.float64).sum(0)
+        bound = tol * (np.abs(x).astype(np.float64) + np.abs(A).astype(np.float64).sum(0))
+        assert np.all(np.abs(acc_d.SubData.astype(np.float64) - exact) <= bound)
+        assert np.array_equal(b.RepeatReshapeCopy_V_MRows(m, b.CreateDataBuffer(x)).to_numpy(), np.tile(x, (m, 1)))
+        assert np.array_equal(b.RepeatReshapeCopy_V_MCols(n, b.CreateDataBuffer(y)).to_numpy(), np.tile(y[:, None], (1, n)))
+
+
+def test_buffer_interface(cuda_provider):
+    """ISigmaDiffDataBuffer members on the device buffer (Util.fs:133-141)."""
+    b = backend(cuda_provider, np.float32)
+    a = np.arange(24, dtype=np.float32)
+    buf = b.CreateDataBuffer(a)
+    assert isinstance(buf, CudaDataBuffer) and buf.Length == 24 and buf.Offset == 0
+    v = buf.GetValues(6, 5)                 # view: same storage
+    assert v.Offset == 6 and np.array_equal(v.SubData, a[6:11])
+    b.Add_V_V_InPlace(b.CreateDataBuffer(np.ones(5, np.float32)), 0, buf, 6, 5)
+    assert np.array_equal(v.SubData, a[6:11] + 1)   # the view sees the in-place update
+    assert np.array_equal(v.Data[v.Offset:v.Offset + v.Length], a[6:11] + 1)
+    d = buf.DeepCopy()
+    b.Add_V_V_InPlace(b.CreateDataBuffer(np.ones(5, np.float32)), 0, buf, 0, 5)
+    assert np.array_equal(d.SubData[:5], a[:5])      # deep copy is detached
+    s = ShapedDataBufferView(b.CreateDataBuffer(a), 4, 6).GetSlice(1, 2, 2, 4)   # GetStackedValues
+    assert s.Shape == (2, 3) and np.array_equal(s.to_numpy(), a.reshape(4, 6)[1:3, 2:5])
+    z = b.CreateDataBuffer(b.CreateZeroArray(1000))
+    assert np.array_equal(z.SubData, np.zeros(1000, np.float32))
+    w = b.CreateDataBuffer(b.CreateValueArray(1000, 2.5))
+    assert np.array_equal(w.SubData, np.full(1000, 2.5, np.float32))
+    st = b.ctx.stats()
+    assert st["kernel_launches"] > 0 and st["pool_hits"] + st["pool_misses"] > 0

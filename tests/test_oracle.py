@@ -1,0 +1,123 @@
+"""The CPU oracle (oracle/) against the reference's own constants, against independent float64 NumPy
+formulas, and against the frozen fixtures in tests/golden/golden.npz.  PARITY UNPINNED: the reference
+holds no Backend<'T> known-answer vectors beyond Script.fsx."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+import make_golden as mg  # noqa: E402
+
+from oracle.backend import OracleBackend  # noqa: E402
+from sigma.diffsharp_b200 import ad  # noqa: E402
+from sigma.diffsharp_b200.backend import MapOp  # noqa: E402
+from sigma.diffsharp_b200.buffers import NativeDataBuffer, ShapedDataBufferView  # noqa: E402
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden.npz"))
+TOL = {np.dtype(np.float32): 2e-6, np.dtype(np.float64): 1e-13}
+
+
+def test_script_fsx_repeat_reshape_copy_rows():
+    """tests/DiffSharp.Tests/Script.fsx:7-16: r[i,j] = v[j], m = 2 — the only Backend op the reference pins."""
+    v32 = GOLD["script_fsx_v"].astype(np.float32)
+    m = int(GOLD["script_fsx_m"][0])
+    r = OracleBackend(np.float32).RepeatReshapeCopy_V_MRows(m, NativeDataBuffer(v32))
+    expected = np.zeros((m, v32.size), np.float32)
+    for i in range(m):
+        for j in range(v32.size):
+            expected[i, j] = v32[j]
+    assert r.Shape == (2, 4)
+    assert np.array_equal(r.to_numpy(), expected)
+
+
+@pytest.mark.parametrize("mode", ["forward", "reverse"])
+def test_fixedpoint_reference_property(mode):
+    """tests/DiffSharp.Tests/AD.Float32.fs:47-57 with the reference's =~ (absolute eps 1e-4, Tests.fs:46-47)."""
+    g = lambda a, b: (a + b / a) / ad.D(2, np.float32)  # noqa: E731
+    f = lambda b: ad.DNumber.FixedPoint(g, ad.D(1.2, np.float32), b)  # noqa: E731
+    fn = ad.jacobianv_ if mode == "forward" else ad.jacobianTv_
+    p, t = fn(f, ad.D(25, np.float32), ad.D(1, np.float32))
+    exp_p, exp_t = GOLD["fixedpoint_expected"]
+    assert abs(float(p) - exp_p) < 1e-4 and abs(float(t) - exp_t) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_oracle_matches_frozen_goldens(dtype):
+    name = "f32" if dtype == np.float32 else "f64"
+    got = mg.run_ops(OracleBackend(dtype), mg.op_inputs(dtype))
+    for k, v in got.items():
+        ref = GOLD[f"{name}_{k}"]
+        assert v.shape == ref.shape, k
+        if k in ("argmax", "argmin", "transpose", "repeat_rows", "repeat_cols", "diag", "permute"):
+            assert np.array_equal(v, ref), k
+        else:
+            np.testing.assert_allclose(v, ref, rtol=50 * TOL[np.dtype(dtype)], atol=50 * TOL[np.dtype(dtype)], err_msg=k)
+
+
+NP_UNARY = {
+    MapOp.Log: np.log, MapOp.Log10: np.log10, MapOp.Exp: np.exp, MapOp.Sin: np.sin, MapOp.Cos: np.cos, MapOp.Tan: np.tan,
+    MapOp.Sqrt: np.sqrt, MapOp.Sinh: np.sinh, MapOp.Cosh: np.cosh, MapOp.Tanh: np.tanh, MapOp.Asin: np.arcsin,
+    MapOp.Acos: np.arccos, MapOp.Atan: np.arctan, MapOp.Abs: np.abs, MapOp.Sign: np.sign, MapOp.Floor: np.floor,
+    MapOp.Ceiling: np.ceil, MapOp.Round: np.rint, MapOp.ReL: lambda v: np.maximum(v, 0),
+    MapOp.Sigmoid: lambda v: 1 / (1 + np.exp(-v)),
+}
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_oracle_against_independent_float64_formulas(dtype):
+    """Every op of the oracle against a float64 NumPy formula written independently of oracle_backend.c."""
+    inp = mg.op_inputs(dtype)
+    got = mg.run_ops(OracleBackend(dtype), inp)
+    f = {k: v.astype(np.float64) for k, v in inp.items()}
+    tol = TOL[np.dtype(dtype)]
+    chk = lambda k, ref, scale=1.0: np.testing.assert_allclose(got[k].astype(np.float64).reshape(-1), np.asarray(ref).reshape(-1), rtol=40 * tol * scale, atol=40 * tol * scale, err_msg=k)  # noqa: E731
+    for op, fn in NP_UNARY.items():
+        src = f["pos"] if op in (MapOp.Log, MapOp.Log10, MapOp.Sqrt) else f["unit"] if op in (MapOp.Asin, MapOp.Acos) else f["x"]
+        chk(f"map_{op.name}", fn(src))
+    s, pos, yb = 1.75, f["pos"], np.abs(f["y"]) + 0.5
+    chk("map_s_Div", s / pos); chk("map_s_Pow_Ab", pos ** s); chk("map_s_Pow_Ba", s ** pos)
+    chk("map_s_Atan2_Ab", np.arctan2(pos, s)); chk("map_s_Atan2_Ba", np.arctan2(s, pos))
+    chk("map2_Mul", pos * yb); chk("map2_Div", pos / yb); chk("map2_Pow_Ab", pos ** yb); chk("map2_Atan2_Ab", np.arctan2(pos, yb))
+    x, y = f["x"], f["y"]
+    chk("add", x + y); chk("sub", x - y); chk("add_s", x + s); chk("sub_s_v", s - x); chk("sub_v_s", x - s); chk("mul_s", s * x)
+    chk("dot", x @ y, 10); chk("l1", np.abs(x).sum(), 10); chk("l2", np.sqrt((x * x).sum()), 10); chk("sup", np.abs(x).max())
+    chk("sum", x.sum(), 20)
+    assert got["argmax"][0] == np.argmax(x) and got["argmin"][0] == np.argmin(x)
+    A, B, S = f["A"], f["B"], f["S"]
+    chk("gemm", A @ B, 10); chk("gemm_bias", A @ B + f["vm"][:, None], 10); chk("gemv", A @ f["vk"], 10)
+    chk("gemv_add", A @ f["vk"] + f["vm"], 10); chk("gemv_t", f["vm"] @ A, 10); chk("ger", np.outer(f["vm"], f["vk"]))
+    chk("had", A * A); chk("transpose", A.T); chk("repeat_rows", np.tile(f["vk"], (3, 1))); chk("repeat_cols", np.tile(f["vk"][:, None], (1, 3)))
+    chk("add_v_mcols", A + f["vm"][:, None]); chk("colsum", f["vk"] + A.sum(0), 10); chk("diag", np.diag(A))
+    chk("solve", np.linalg.solve(S, f["v6"]), 100); chk("inverse", np.linalg.inv(S), 100); chk("det", np.linalg.det(S), 100)
+    chk("permute", np.arange(24.0).reshape(2, 3, 4).transpose(2, 0, 1))
+
+
+def test_oracle_edge_semantics():
+    b = OracleBackend(np.float32)
+    nb = lambda a: NativeDataBuffer(np.asarray(a, np.float32))  # noqa: E731
+    # Sign(NaN) = 0 (Util.fs:88-91), Round is half-to-even, ReLU propagates NaN
+    assert np.array_equal(b.Map_F_V(MapOp.Sign, None, nb([np.nan, -2, 0, 3])).SubData, [0, -1, 0, 1])
+    assert np.array_equal(b.Map_F_V(MapOp.Round, None, nb([0.5, 1.5, 2.5, -0.5])).SubData, [0, 2, 2, -0])
+    r = b.Map_F_V(MapOp.ReL, None, nb([np.nan, -1, 2])).SubData
+    assert np.isnan(r[0]) and r[1] == 0 and r[2] == 2
+    # empty operand = additive identity (App. D-1)
+    assert np.array_equal(b.Add_V_V(nb([1, 2]), nb([])).SubData, [1, 2])
+    assert np.array_equal(b.Sub_V_V(nb([]), nb([1, 2])).SubData, [-1, -2])
+    # first occurrence wins; a[0] = NaN pins index 0
+    assert b.MaxIndex_V(nb([1, 5, 5, 2])) == 1 and b.MinIndex_V(nb([3, 1, 1])) == 1
+    assert b.MaxIndex_V(nb([np.nan, 5])) == 0
+    # singular -> None
+    z = ShapedDataBufferView(nb(np.zeros(4)), 2, 2)
+    assert b.Solve_M_V(z, nb([1, 1])) is None and b.Inverse_M(z) is None
+    with pytest.raises(NotImplementedError):
+        b.Map_F_V(MapOp.Mul, None, nb([1]))  # not a unary op-code: closures are never executed
+
+
+def test_config_goldens_reproduce(oracle_provider, use_provider):
+    use_provider(oracle_provider)
+    g = mg.config_goldens()
+    for k, v in g.items():
+        tol = 5e-5 if k.startswith("c1") else 1e-12
+        np.testing.assert_allclose(v, GOLD[k], rtol=tol, atol=tol * np.abs(GOLD[k]).max(), err_msg=k)
