@@ -1,4 +1,555 @@
+// K1: float32 GEMM on the 5th-generation tensor cores — tcgen05.mma kind::tf32 with the accumulator
+// in TMEM, operands staged in shared memory by TMA, and a 3xTF32 operand split so that the result
+// stays float32-class (north_star: <= 1e-5 relative to OpenBLAS sgemm).
+//
+//   C(m x n) = op(A) op(B) [+ bias[i]]        Mul_M_M / Mul_M_M_Add_V_MCols (Backend.fs:119,121)
+//
+// Two launches per GEMM:
+//  (1) split pre-pass (HBM-bound): every operand is rounded to TF32 (hi = rna_tf32(x)) and its
+//      residual again (lo = rna_tf32(x - hi), x - hi is exact in fp32), and written as two K-MAJOR
+//      planes [rows x Kp] (Kp = K rounded up to 32, zero padded).  The pre-pass also normalises the
+//      layout: an operand whose K index is not contiguous (B of an NN product, A of a TN product) is
+//      transposed through shared memory on the way, so the tensor-core kernel only ever sees K-major
+//      SWIZZLE_128B tiles.  A lazily transposed operand (Transpose_M feeding Mul_M_M,
+//      AD.Float32.fs:4127-4143) therefore costs nothing extra.
+//  (2) persistent warp-specialised kernel, one CTA per SM, 192 threads:
+//        warp 0    TMA producer: 4 tile loads per k-block (A_hi, A_lo, B_hi, B_lo) into a
+//                  STAGES-deep shared-memory ring, completion on a `full` mbarrier (expect_tx)
+//        warp 1    allocates TMEM and issues tcgen05.mma from one thread: per 8-wide k-slice
+//                  D += A_lo*B_hi; D += A_hi*B_lo; D += A_hi*B_hi  (128 x BN fp32 accumulator in
+//                  TMEM); tcgen05.commit releases the smem stage (`empty`) and, after the last
+//                  k-block, publishes the accumulator (`tmem_full`)
+//        warps 2-5 epilogue: tcgen05.ld the accumulator (each warp owns the 32 TMEM lanes of its
+//                  quadrant), add the bias, predicated float4 stores to C, then hand the
+//                  accumulator stage back (`tmem_empty`).  Two accumulator stages (2 x BN TMEM
+//                  columns) let the epilogue of tile i overlap the main loop of tile i+1.
+// The a_lo*b_lo term (<= 2^-22 relative) is dropped: that is the "3x" in 3xTF32.
+//
+// Accuracy of long reductions.  The tensor core's fp32 accumulator TRUNCATES on every accumulate
+// (measured on B200: same-sign data, K = 8192, one TMEM accumulator => 9.1e-5 relative error,
+// = 3 MMAs x K/16 x 2^-24).  The K loop is therefore cut into chunks of kChunkKb k-blocks (256
+// elements): each chunk accumulates from zero in TMEM (truncation bias <= 2.8e-6 of the chunk), and
+// the epilogue warps add the chunk results in registers with IEEE round-to-nearest fp32 adds.
+// The two TMEM accumulator stages alternate per chunk, so draining chunk c overlaps the MMAs of
+// chunk c+1.
+//
+// Split-K.  When the output has fewer tiles than SMs (weight-adjoint GEMMs: small m x n, K = batch),
+// the chunks of one tile are dealt to `splits` CTAs; each writes an fp32 partial tile and a second
+// kernel adds the partials in split order (deterministic) and applies the bias.
+#include <cuda.h>
+
 #include "dsc_internal.cuh"
+
 namespace dsc {
-int gemm_tf32x3_tcgen05(Ctx*, int, int, int, int, int, const float*, const float*, const float*, float*) { return 1; }
+namespace tf32x3 {
+
+constexpr int BM = 128;
+constexpr int BK = 32;  // floats: 128 bytes = one SWIZZLE_128B row
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;  // warp0 TMA, warp1 MMA, 8 epilogue warps
+constexpr int kChunkKb = 8;                   // k-blocks per accumulation chunk (256 K-elements)
+constexpr int kAPlaneBytes = BM * BK * 4;
+
+template <int BN>
+struct Cfg {
+    static constexpr int kBPlaneBytes = BN * BK * 4;
+    static constexpr int kStageBytes = 2 * kAPlaneBytes + 2 * kBPlaneBytes;
+    static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
+    static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator stages; power of two
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// ---- PTX helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by ONE thread for the whole CTA
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives columns [c, c+32) of TMEM lane base+i
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor for a K-major SWIZZLE_128B tile (rows of 128 B, 8-row groups of
+// 1024 B): start address >> 4 in bits [0,14), LBO (unused for swizzled K-major) = 1 in [16,30),
+// SBO = 1024 B >> 4 in [32,46), descriptor version 1 in [46,48), layout SWIZZLE_128B (=2) in [61,64).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// Instruction descriptor, kind::tf32: D = F32 (bits 4-5 = 1), A/B = TF32 (bits 7-9, 10-12 = 2), both
+// K-major (bits 15,16 = 0), N >> 3 in bits [17,23), M >> 4 in bits [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct Params {
+    int m, n, num_kb;          // problem rows/cols, number of 32-wide k-blocks
+    int tiles_m, tiles_n;
+    int splits, kb_per_split;  // split-K: k-blocks [s*kb_per_split, (s+1)*kb_per_split) belong to split s
+    float* C;                  // splits == 1: the result; splits > 1: partial planes [splits][m][n]
+    const float* bias;         // applied here only when splits == 1
+    int vec4;                  // output rows are 16-byte aligned and n % 4 == 0
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
+                   const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, const Params p) {
+    using cfg = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = smem_base + cfg::kStages * cfg::kStageBytes;
+    // barrier slots (8 bytes each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then the TMEM base
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (cfg::kStages + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * cfg::kStages + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * cfg::kStages + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * cfg::kStages + 4);
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + cfg::kStages * cfg::kStageBytes + 8 * (2 * cfg::kStages + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < cfg::kStages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), kEpiWarps);  // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)cfg::kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int num_units = num_tiles * p.splits;  // unit u = (split u / num_tiles, tile u % num_tiles)
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+                const int tile = u % num_tiles, split = u / num_tiles;
+                const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    const uint32_t st = smem_base + s * cfg::kStageBytes;
+                    mbar_expect_tx(full_bar(s), cfg::kStageBytes);
+                    tma_load_2d(st, &map_ahi, full_bar(s), kb * BK, m0);
+                    tma_load_2d(st + kAPlaneBytes, &map_alo, full_bar(s), kb * BK, m0);
+                    tma_load_2d(st + 2 * kAPlaneBytes, &map_bhi, full_bar(s), kb * BK, n0);
+                    tma_load_2d(st + 2 * kAPlaneBytes + cfg::kBPlaneBytes, &map_blo, full_bar(s), kb * BK, n0);
+                    if (++s == cfg::kStages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+            int s = 0, as = 0;
+            uint32_t ph = 0, aph = 0;
+            for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+                const int split = u / num_tiles;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+                for (int c0 = kb0; c0 < kb1; c0 += kChunkKb) {
+                    const int c1 = min(kb1, c0 + kChunkKb);
+                    mbar_wait(tempty_bar(as), aph ^ 1u);  // the epilogue has drained this accumulator stage
+                    tcgen05_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                    for (int kb = c0; kb < c1; ++kb) {
+                        mbar_wait(full_bar(s), ph);        // TMA bytes have landed
+                        tcgen05_fence_after();
+                        const uint32_t st = smem_base + s * cfg::kStageBytes;
+                        const uint64_t ahi = make_kmajor_sw128_desc(st);
+                        const uint64_t alo = make_kmajor_sw128_desc(st + kAPlaneBytes);
+                        const uint64_t bhi = make_kmajor_sw128_desc(st + 2 * kAPlaneBytes);
+                        const uint64_t blo = make_kmajor_sw128_desc(st + 2 * kAPlaneBytes + cfg::kBPlaneBytes);
+#pragma unroll
+                        for (int k = 0; k < BK / 8; ++k) {
+                            // advance 8 floats = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+                            const uint64_t adv = (uint64_t)(k * 2);
+                            umma_tf32(d_tmem, alo + adv, bhi + adv, idesc, (uint32_t)((kb != c0) | (k != 0)));
+                            umma_tf32(d_tmem, ahi + adv, blo + adv, idesc, 1u);
+                            umma_tf32(d_tmem, ahi + adv, bhi + adv, idesc, 1u);
+                        }
+                        tcgen05_commit(empty_bar(s));      // smem stage is free once these MMAs retire
+                        if (++s == cfg::kStages) { s = 0; ph ^= 1u; }
+                    }
+                    tcgen05_commit(tfull_bar(as));         // chunk accumulator complete
+                    if (++as == 2) { as = 0; aph ^= 1u; }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue warps 2..9 =====================
+        // warp w may touch the TMEM lanes of quadrant (w & 3); the two warps of a quadrant split the
+        // BN columns in halves.  Each thread owns ONE output row and HALF = BN/2 consecutive columns,
+        // and keeps their running sum over the K chunks in registers.
+        constexpr int HALF = BN / 2;
+        const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
+        int as = 0;
+        uint32_t aph = 0;
+        for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+            const int tile = u % num_tiles, split = u / num_tiles;
+            const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
+            const int kb0 = split * p.kb_per_split;
+            const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+            float acc[HALF];
+#pragma unroll
+            for (int j = 0; j < HALF; ++j) acc[j] = 0.f;
+            for (int c0 = kb0; c0 < kb1; c0 += kChunkKb) {
+                mbar_wait(tfull_bar(as), aph);
+                tcgen05_fence_after();
+#pragma unroll
+                for (int c = 0; c < HALF; c += 32) {
+                    uint32_t r[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + half * HALF + c);
+                    tmem_ld_32x32(taddr, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c + j] += __uint_as_float(r[j]);  // IEEE RN adds across chunks
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(as));
+                if (++as == 2) { as = 0; aph ^= 1u; }
+            }
+            const int row = m0 + quad * 32 + lane;
+            if (row < p.m) {
+                const float bv = (p.bias != nullptr) ? p.bias[row] : 0.f;
+                float* crow = p.C + (size_t)split * p.m * p.n + (size_t)row * p.n;
+                const int col0 = n0 + half * HALF;
+#pragma unroll
+                for (int c = 0; c < HALF; c += 4) {
+                    const int col = col0 + c;
+                    if (p.vec4 && col + 4 <= p.n) {
+                        *reinterpret_cast<float4*>(crow + col) = make_float4(acc[c] + bv, acc[c + 1] + bv, acc[c + 2] + bv, acc[c + 3] + bv);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (col + j < p.n) crow[col + j] = acc[c + j] + bv;
+                    }
+                }
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)cfg::kTmemCols) : "memory");
+    }
+}
+
+// C = sum_s P[s] (+ bias[row]) in split order (deterministic)
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ P, const float* __restrict__ bias, float* __restrict__ C,
+                                                             int m, int n, int splits, int vec4) {
+    const size_t total = (size_t)m * n;
+    if (vec4) {
+        const size_t nv = total / 4;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x * blockDim.x) {
+            float4 a = reinterpret_cast<const float4*>(P)[i];
+            for (int s = 1; s < splits; ++s) {
+                const float4 b = reinterpret_cast<const float4*>(P + (size_t)s * total)[i];
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            if (bias) {
+                const float bv = bias[(i * 4) / n];
+                a.x += bv; a.y += bv; a.z += bv; a.w += bv;
+            }
+            reinterpret_cast<float4*>(C)[i] = a;
+        }
+    } else {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+            float a = P[i];
+            for (int s = 1; s < splits; ++s) a += P[(size_t)s * total + i];
+            if (bias) a += bias[i / n];
+            C[i] = a;
+        }
+    }
+}
+
+// ---- split pre-pass ---------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    float h = tf32_rna(x);
+    if (!isfinite(h)) h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);  // rounding overflowed: truncate instead
+    hi = h;
+    const float res = x - h;  // exact in fp32
+    lo = isfinite(res) ? tf32_rna(res) : 0.f;
+}
+
+// src is [rows x k] row-major (K contiguous).  out planes are [rows x kp], zero padded in k.
+__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo,
+                                                          int rows, int k, int kp, int vec_in) {
+    const size_t total = (size_t)rows * (kp / 4);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / (kp / 4)), c = (int)(i % (kp / 4)) * 4;
+        float x[4] = {0.f, 0.f, 0.f, 0.f};
+        if (vec_in && c + 4 <= k) {
+            const float4 v = *reinterpret_cast<const float4*>(src + (size_t)r * k + c);
+            x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (c + j < k) x[j] = src[(size_t)r * k + c + j];
+        }
+        float4 h, l;
+        split_tf32(x[0], h.x, l.x); split_tf32(x[1], h.y, l.y); split_tf32(x[2], h.z, l.z); split_tf32(x[3], h.w, l.w);
+        *reinterpret_cast<float4*>(hi + (size_t)r * kp + c) = h;
+        *reinterpret_cast<float4*>(lo + (size_t)r * kp + c) = l;
+    }
+}
+
+// src is [k x rows] row-major (the K index is the slow one): transpose through shared memory.
+__global__ void __launch_bounds__(256) split_transpose_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo,
+                                                               int rows, int k, int kp) {
+    __shared__ float tile[32][33];
+    const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const int kk = k0 + j, rr = r0 + tx;
+        tile[j][tx] = (kk < k && rr < rows) ? src[(size_t)kk * rows + rr] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const int rr = r0 + j, kk = k0 + tx;
+        if (rr < rows && kk < kp) {
+            float h, l;
+            split_tf32(tile[tx][j], h, l);
+            hi[(size_t)rr * kp + kk] = h;
+            lo[(size_t)rr * kp + kk] = l;
+        }
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int load_encode() {
+    if (g_encode) return DSC_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        return fail(DSC_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    }
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    return DSC_OK;
+}
+
+// plane is [rows x kp] fp32, K-major; box = 32 floats (128 B) x box_rows, SWIZZLE_128B, OOB rows read as zero
+static int make_map(CUtensorMap* map, const float* plane, int rows, int kp, int box_rows) {
+    cuuint64_t dims[2] = {(cuuint64_t)kp, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kp * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(plane), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DSC_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %d x %d plane, box rows %d", (int)r, rows, kp, box_rows);
+    return DSC_OK;
+}
+
+template <int BN>
+static int launch(Ctx* ctx, const CUtensorMap* maps, const Params& p) {
+    using cfg = Cfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DSC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::kSmemBytes));
+        attr_set = true;
+    }
+    const int units = p.tiles_m * p.tiles_n * p.splits;
+    const int grid = units < ctx->sm_count ? units : ctx->sm_count;
+    gemm_tf32x3_kernel<BN><<<grid, kThreads, cfg::kSmemBytes, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+    DSC_LAUNCH_CHECK(ctx);
+    return DSC_OK;
+}
+
+static int split_operand(Ctx* ctx, const float* src, bool k_contiguous, int rows, int k, int kp, float* hi, float* lo) {
+    if (k_contiguous) {
+        const int vec_in = ((k % 4) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+        const int grid = grid_for((size_t)rows * (kp / 4), 256 * 4, ctx->sm_count * 8);
+        split_rows_kernel<<<grid, 256, 0, ctx->stream>>>(src, hi, lo, rows, k, kp, vec_in);
+    } else {
+        dim3 grid((rows + 31) / 32, kp / 32);
+        split_transpose_kernel<<<grid, 256, 0, ctx->stream>>>(src, hi, lo, rows, k, kp);
+    }
+    DSC_LAUNCH_CHECK(ctx);
+    return DSC_OK;
+}
+
+}  // namespace tf32x3
+
+int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const float* A, const float* B, const float* bias, float* C) {
+    using namespace tf32x3;
+    // Eligibility: enough rows/cols to fill 128-row tiles and enough depth to amortise the pre-pass.
+    // Skinny / tiny products stay on the CUDA-core kernel (they are bandwidth- or latency-bound).
+    if (m < 128 || n < 32 || k < 32) return 1;
+    DSC_TRY(load_encode());
+    const int kp = (k + BK - 1) / BK * BK;
+
+    // ---- plan: tile width, split-K, workspace (all decided before anything is launched) ----
+    // tile width: shared-memory traffic per output column block is ~ (BM + BN) rows per k-block
+    int bn = 256;
+    {
+        long best = -1;
+        const int cands[3] = {64, 128, 256};
+        for (int c : cands) {
+            const long tn = (n + c - 1) / c;
+            const long cost = tn * (BM + c);
+            if (best < 0 || cost < best) { best = cost; bn = c; }
+        }
+    }
+    Params p;
+    p.m = m; p.n = n; p.num_kb = kp / BK;
+    p.tiles_m = (m + BM - 1) / BM;
+    p.tiles_n = (n + bn - 1) / bn;
+    const int tiles = p.tiles_m * p.tiles_n;
+    const int chunks = (p.num_kb + kChunkKb - 1) / kChunkKb;
+    int splits = 1;
+    if (tiles * 2 <= ctx->sm_count && chunks >= 4) {  // every split keeps >= 2 chunks of K
+        splits = ctx->sm_count / tiles;
+        if (splits > chunks / 2) splits = chunks / 2;
+        if (splits > 16) splits = 16;
+        if (splits < 1) splits = 1;
+    }
+    const int chunks_per_split = (chunks + splits - 1) / splits;
+    splits = (chunks + chunks_per_split - 1) / chunks_per_split;
+    p.splits = splits;
+    p.kb_per_split = chunks_per_split * kChunkKb;
+
+    const size_t plane_a = (size_t)m * kp, plane_b = (size_t)n * kp;
+    const size_t planes_bytes = ((2 * plane_a + 2 * plane_b) * sizeof(float) + 1023) & ~size_t(1023);
+    const size_t partial_bytes = splits > 1 ? (size_t)splits * m * n * sizeof(float) : 0;
+    DSC_TRY(ensure_gemm_ws(ctx, planes_bytes + partial_bytes + 2048));
+    char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ctx->gemm_ws) + 1023) & ~uintptr_t(1023));
+    float* ws = reinterpret_cast<float*>(base);
+    float *ahi = ws, *alo = ws + plane_a, *bhi = ws + 2 * plane_a, *blo = ws + 2 * plane_a + plane_b;
+    float* partial = splits > 1 ? reinterpret_cast<float*>(base + planes_bytes) : nullptr;
+
+    // ---- (1) split pre-pass ----
+    // op(A)(m x k): stored m x k (K contiguous) unless ta; op(B)(k x n): stored k x n (K NOT contiguous) unless tb
+    DSC_TRY(split_operand(ctx, A, !ta, m, k, kp, ahi, alo));
+    DSC_TRY(split_operand(ctx, B, tb != 0, n, k, kp, bhi, blo));
+
+    // ---- (2) tensor-core kernel ----
+    p.C = splits > 1 ? partial : C;
+    p.bias = splits > 1 ? nullptr : bias;
+    p.vec4 = ((n % 4) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    CUtensorMap maps[4];
+    DSC_TRY(make_map(&maps[0], ahi, m, kp, BM));
+    DSC_TRY(make_map(&maps[1], alo, m, kp, BM));
+    DSC_TRY(make_map(&maps[2], bhi, n, kp, bn));
+    DSC_TRY(make_map(&maps[3], blo, n, kp, bn));
+    int s;
+    if (bn == 256) s = launch<256>(ctx, maps, p);
+    else if (bn == 128) s = launch<128>(ctx, maps, p);
+    else s = launch<64>(ctx, maps, p);
+    if (s != DSC_OK) return s;
+
+    // ---- (3) split-K reduction in split order ----
+    if (splits > 1) {
+        const int v4 = ((n % 4) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+        const int grid = grid_for((size_t)m * n / (v4 ? 4 : 1), 256 * 2, ctx->sm_count * 8);
+        splitk_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(partial, bias, C, m, n, splits, v4);
+        DSC_LAUNCH_CHECK(ctx);
+    }
+    ctx->stats.gemm_tcgen05++;
+    return DSC_OK;
+}
+
+}  // namespace dsc
