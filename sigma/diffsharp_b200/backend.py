@@ -17,6 +17,10 @@ eager sequence and switchable off with ``CudaBackend(fuse=False)``:
     materialises it.
   * the tanh adjoint chain Map(Cosh) -> Map_F_S(1, Div) -> Had -> Had (AD.Float32.fs:4238-4240) is
     recognised and issued as one fused kernel with the same sequence of roundings.
+  * zero adjoints are lazy: ``CreateDataBuffer(CreateZeroArray n)`` (two per tape node,
+    AD.Float32.fs:1834-1835,3746) allocates nothing; the first ``Add_M_M_InPlace``/``Add_V_V`` into
+    a known-zero buffer is a copy of the addend (0 + v = v; only the sign of a zero can differ), any
+    other use materialises the zeros with a memset.
 """
 from __future__ import annotations
 
@@ -179,7 +183,10 @@ class CudaBackend(Backend):
 
     def _materialize(self, lb: LazyCudaBuffer):
         lz = lb._lazy
-        if lz.kind == "T":
+        if lz.kind == "Z":
+            h = _lib.buf_t()
+            check(lib.dsc_buf_alloc_fill(self._h, self._code, lb._length, 0.0, C.byref(h)))
+        elif lz.kind == "T":
             src, m, n = lz.args
             h = _lib.buf_t()
             check(self._f["transpose"](self._h, m, n, src.handle, C.byref(h)))
@@ -198,6 +205,8 @@ class CudaBackend(Backend):
         if isinstance(a, ConstArray) and a._arr is None:
             if a.value is None:
                 return CudaDataBuffer.empty(self.ctx, self.dtype, a.n)
+            if self.fuse and a.value == 0.0 and a.n > 0:
+                return LazyCudaBuffer(self, a.n, _Lazy("Z"))
             return CudaDataBuffer.filled(self.ctx, self.dtype, a.n, a.value)
         if isinstance(a, ConstArray):
             a = a._arr
@@ -240,8 +249,22 @@ class CudaBackend(Backend):
     def MinIndex_V(self, a): return self._index_red("argmin", a)
 
     # ---- Vector valued (Backend.fs:90-109) ----------------------------------------------------
+    def _is_zero(self, b):
+        lz = self._lz(b)
+        return lz is not None and lz.kind == "Z"
+
+    def _copy_of(self, src: CudaDataBuffer) -> CudaDataBuffer:
+        h = _lib.buf_t()
+        check(lib.dsc_buf_copy(src.handle, C.byref(h)))
+        return CudaDataBuffer(self.ctx, self.dtype, h.value, src.Length)
+
     def _map2(self, op, a, b):
         da, db = self._dev(a), self._dev(b)
+        if op in (MapOp.Add, MapOp.Sub) and da.Length == db.Length:
+            if self._is_zero(db):      # x +/- 0 = x
+                return LazyCudaBuffer(self, da.Length, _Lazy("Z")) if self._is_zero(da) else self._copy_of(da)
+            if op == MapOp.Add and self._is_zero(da):  # 0 + x = x
+                return self._copy_of(db)
         return self._out(self._f["map2"], max(da.Length, db.Length), int(op), da.handle, db.handle)
 
     def _scalar_op(self, kind, s, v):
@@ -319,6 +342,17 @@ class CudaBackend(Backend):
 
     def Add_M_M_InPlace(self, a, b):
         da, db = self._dev(a.DataBuffer), self._dev(b.DataBuffer)
+        if self._is_zero(da):
+            # first accumulation into a known-zero adjoint (AD.Float32.fs:4118 after :3746)
+            if db.Length == 0 or self._is_zero(db):
+                return a
+            if db.Length != da.Length:
+                raise _lib.InvalidArgError(_lib.DSC_E_SHAPE, "Matrices must have same shape.")
+            h = _lib.buf_t()
+            check(lib.dsc_buf_copy(db.handle, C.byref(h)))
+            da._h, da._lazy = h.value, None
+            da._finalizer = weakref.finalize(da, lib.dsc_buf_free, h.value)
+            return a
         self._touch(da)
         check(self._f["add_inplace"](self._h, da.handle, db.handle))
         return a

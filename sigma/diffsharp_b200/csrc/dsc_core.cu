@@ -155,7 +155,8 @@ int in_buf(Ctx* ctx, int dtype, dsc_buf_t h, Buf** res, const char* what) {
 
 int ensure_red_scratch(Ctx* ctx, size_t bytes) {
     if (ctx->red_scratch_bytes >= bytes) return DSC_OK;
-    if (ctx->capturing) return fail(DSC_E_INVALID, "reduction scratch cannot grow while capturing");
+    if (ctx->capturing || ctx->live_graphs > 0)
+        return fail(DSC_E_INVALID, "reduction scratch cannot grow while a CUDA graph is being captured or is alive (run the step once eagerly first)");
     if (ctx->red_scratch) cudaFree(ctx->red_scratch);
     ctx->red_scratch = nullptr;
     ctx->red_scratch_bytes = 0;
@@ -167,7 +168,8 @@ int ensure_red_scratch(Ctx* ctx, size_t bytes) {
 
 int ensure_gemm_ws(Ctx* ctx, size_t bytes) {
     if (ctx->gemm_ws_bytes >= bytes) return DSC_OK;
-    if (ctx->capturing) return fail(DSC_E_INVALID, "GEMM workspace cannot grow while capturing (run the step once eagerly first)");
+    if (ctx->capturing || ctx->live_graphs > 0)
+        return fail(DSC_E_INVALID, "GEMM workspace cannot grow while a CUDA graph is being captured or is alive (run the step once eagerly first)");
     if (ctx->gemm_ws) {
         DSC_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         cudaFree(ctx->gemm_ws);
@@ -268,7 +270,7 @@ int dsc_create(int device, uint32_t flags, dsc_ctx_t* out) {
     DSC_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming));
     DSC_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
     DSC_CUDA_CHECK(cudaMallocHost(&ctx->red_host, 256));
-    int s = ensure_red_scratch(ctx, 1u << 20);
+    int s = ensure_red_scratch(ctx, 32u << 20);
     if (s != DSC_OK) return s;
     *out = reinterpret_cast<dsc_ctx_t>(ctx);
     return DSC_OK;
@@ -435,6 +437,7 @@ int dsc_graph_end(dsc_ctx_t c, dsc_graph_t* out) {
         delete g;
         return fail(DSC_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
     }
+    ctx->live_graphs++;
     *out = reinterpret_cast<dsc_graph_t>(g);
     return DSC_OK;
 }
@@ -454,6 +457,7 @@ int dsc_graph_destroy(dsc_ctx_t c, dsc_graph_t gh) {
     cudaStreamSynchronize(ctx->stream);
     cudaGraphExecDestroy(g->exec);
     cudaGraphDestroy(g->graph);
+    ctx->live_graphs--;
     for (Block* b : g->blocks) {
         if (b->refs <= 0) {
             cudaFree(b->ptr);

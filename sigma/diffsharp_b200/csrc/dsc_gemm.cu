@@ -100,6 +100,10 @@ static int gemm_simt(Ctx* ctx, int ta, int tb, int m, int n, int k, const T* A, 
 template <>
 int gemm_impl<float>(Ctx* ctx, int ta, int tb, int m, int n, int k, Buf* A, Buf* B, Buf* bias, Buf* C) {
     const float* bp = bias ? bias->ptr<float>() : nullptr;
+    {
+        int s = gemm_skinny<float>(ctx, ta, tb, m, n, k, A->ptr<float>(), B->ptr<float>(), bp, C->ptr<float>());
+        if (s <= 0) return s;
+    }
     if (!(ctx->flags & DSC_FLAG_GEMM_FP32_SIMT)) {
         int s = gemm_tf32x3_tcgen05(ctx, ta, tb, m, n, k, A->ptr<float>(), B->ptr<float>(), bp, C->ptr<float>());
         if (s <= 0) return s;  // handled (0) or failed (<0); 1 = not eligible
@@ -110,6 +114,10 @@ int gemm_impl<float>(Ctx* ctx, int ta, int tb, int m, int n, int k, Buf* A, Buf*
 template <>
 int gemm_impl<double>(Ctx* ctx, int ta, int tb, int m, int n, int k, Buf* A, Buf* B, Buf* bias, Buf* C) {
     const double* bp = bias ? bias->ptr<double>() : nullptr;
+    {
+        int s = gemm_skinny<double>(ctx, ta, tb, m, n, k, A->ptr<double>(), B->ptr<double>(), bp, C->ptr<double>());
+        if (s <= 0) return s;
+    }
     if (!(ctx->flags & DSC_FLAG_GEMM_F64_SIMT)) {
         int s = gemm_f64_dmma(ctx, ta, tb, m, n, k, A->ptr<double>(), B->ptr<double>(), bp, C->ptr<double>());
         if (s <= 0) return s;

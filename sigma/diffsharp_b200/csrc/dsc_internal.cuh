@@ -70,6 +70,7 @@ struct Ctx {
     // capture state
     bool capturing = false;
     int next_arena = 1;
+    int live_graphs = 0;          // scratch / workspace may not be reallocated while a captured graph references them
     int cur_arena = 0;
     Pool arena_pool;              // private pool of the graph being captured
     std::vector<Block*> arena_blocks;
@@ -168,5 +169,8 @@ int gemm_tf32x3_tcgen05(Ctx*, int ta, int tb, int m, int n, int k, const float* 
                         const float* bias, float* C);
 int gemm_f64_dmma(Ctx*, int ta, int tb, int m, int n, int k, const double* A, const double* B,
                   const double* bias, double* C);
+// n <= 16 products on CUDA cores (dsc_gemm_skinny.cu); same return convention
+template <typename T>
+int gemm_skinny(Ctx*, int ta, int tb, int m, int n, int k, const T* A, const T* B, const T* bias, T* C);
 
 }  // namespace dsc
