@@ -366,48 +366,65 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     lo = isfinite(res) ? tf32_rna(res) : 0.f;
 }
 
-// src is [rows x k] row-major (K contiguous).  out planes are [rows x kp], zero padded in k.
-__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo,
-                                                          int rows, int k, int kp, int vec_in) {
-    const size_t total = (size_t)rows * (kp / 4);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int r = (int)(i / (kp / 4)), c = (int)(i % (kp / 4)) * 4;
-        float x[4] = {0.f, 0.f, 0.f, 0.f};
-        if (vec_in && c + 4 <= k) {
-            const float4 v = *reinterpret_cast<const float4*>(src + (size_t)r * k + c);
-            x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (c + j < k) x[j] = src[(size_t)r * k + c + j];
-        }
-        float4 h, l;
-        split_tf32(x[0], h.x, l.x); split_tf32(x[1], h.y, l.y); split_tf32(x[2], h.z, l.z); split_tf32(x[3], h.w, l.w);
-        *reinterpret_cast<float4*>(hi + (size_t)r * kp + c) = h;
-        *reinterpret_cast<float4*>(lo + (size_t)r * kp + c) = l;
-    }
-}
+struct SplitJob {
+    const float* src;
+    float* hi;
+    float* lo;
+    int rows, k_contig;   // k_contig: src is [rows x k] (K contiguous); else src is [k x rows]
+    int blocks;           // CTAs assigned to this operand
+};
 
-// src is [k x rows] row-major (the K index is the slow one): transpose through shared memory.
-__global__ void __launch_bounds__(256) split_transpose_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo,
-                                                               int rows, int k, int kp) {
+// One launch splits BOTH operands of a GEMM (blockIdx.x < jobs[0].blocks -> operand A, else B).
+//  K-contiguous source  [rows x k] : each CTA converts 256 x 4 consecutive output float4 groups
+//  K-strided source     [k x rows] : each CTA transposes one 32 x 32 tile through shared memory
+// Output planes are [rows x kp] with kp = K rounded up to 32, zero padded.
+__global__ void __launch_bounds__(256) split_pair_kernel(const SplitJob ja, const SplitJob jb, int k, int kp) {
     __shared__ float tile[32][33];
-    const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const bool second = blockIdx.x >= (unsigned)ja.blocks;
+    const SplitJob& j = second ? jb : ja;
+    const int bid = second ? blockIdx.x - ja.blocks : blockIdx.x;
+    if (j.k_contig) {
+        const int vec_in = ((k % 4) == 0) && ((reinterpret_cast<uintptr_t>(j.src) & 15) == 0);
+        const int kq = kp / 4;
+        const size_t total = (size_t)j.rows * kq;
 #pragma unroll
-    for (int j = ty; j < 32; j += 8) {
-        const int kk = k0 + j, rr = r0 + tx;
-        tile[j][tx] = (kk < k && rr < rows) ? src[(size_t)kk * rows + rr] : 0.f;
-    }
-    __syncthreads();
+        for (int u = 0; u < 4; ++u) {
+            const size_t i = (size_t)bid * 1024 + u * 256 + threadIdx.x;
+            if (i >= total) break;
+            const int r = (int)(i / kq), c = (int)(i % kq) * 4;
+            float x[4] = {0.f, 0.f, 0.f, 0.f};
+            if (vec_in && c + 4 <= k) {
+                const float4 v = *reinterpret_cast<const float4*>(j.src + (size_t)r * k + c);
+                x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+            } else {
 #pragma unroll
-    for (int j = ty; j < 32; j += 8) {
-        const int rr = r0 + j, kk = k0 + tx;
-        if (rr < rows && kk < kp) {
-            float h, l;
-            split_tf32(tile[tx][j], h, l);
-            hi[(size_t)rr * kp + kk] = h;
-            lo[(size_t)rr * kp + kk] = l;
+                for (int e = 0; e < 4; ++e)
+                    if (c + e < k) x[e] = j.src[(size_t)r * k + c + e];
+            }
+            float4 h, l;
+            split_tf32(x[0], h.x, l.x); split_tf32(x[1], h.y, l.y); split_tf32(x[2], h.z, l.z); split_tf32(x[3], h.w, l.w);
+            *reinterpret_cast<float4*>(j.hi + (size_t)r * kp + c) = h;
+            *reinterpret_cast<float4*>(j.lo + (size_t)r * kp + c) = l;
+        }
+    } else {
+        const int tiles_r = (j.rows + 31) / 32;
+        const int r0 = (bid % tiles_r) * 32, k0 = (bid / tiles_r) * 32;
+        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+        for (int e = ty; e < 32; e += 8) {
+            const int kk = k0 + e, rr = r0 + tx;
+            tile[e][tx] = (kk < k && rr < j.rows) ? j.src[(size_t)kk * j.rows + rr] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = ty; e < 32; e += 8) {
+            const int rr = r0 + e, kk = k0 + tx;
+            if (rr < j.rows && kk < kp) {
+                float h, l;
+                split_tf32(tile[tx][e], h, l);
+                j.hi[(size_t)rr * kp + kk] = h;
+                j.lo[(size_t)rr * kp + kk] = l;
+            }
         }
     }
 }
@@ -459,15 +476,16 @@ static int launch(Ctx* ctx, const CUtensorMap* maps, const Params& p) {
     return DSC_OK;
 }
 
-static int split_operand(Ctx* ctx, const float* src, bool k_contiguous, int rows, int k, int kp, float* hi, float* lo) {
-    if (k_contiguous) {
-        const int vec_in = ((k % 4) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-        const int grid = grid_for((size_t)rows * (kp / 4), 256 * 4, ctx->sm_count * 8);
-        split_rows_kernel<<<grid, 256, 0, ctx->stream>>>(src, hi, lo, rows, k, kp, vec_in);
-    } else {
-        dim3 grid((rows + 31) / 32, kp / 32);
-        split_transpose_kernel<<<grid, 256, 0, ctx->stream>>>(src, hi, lo, rows, k, kp);
-    }
+static int split_blocks(bool k_contig, int rows, int kp) {
+    if (k_contig) return (int)(((size_t)rows * (kp / 4) + 1023) / 1024);
+    return ((rows + 31) / 32) * (kp / 32);
+}
+
+static int split_pair(Ctx* ctx, const float* A, bool a_kc, int m, float* ahi, float* alo, const float* B, bool b_kc, int n, float* bhi,
+                      float* blo, int k, int kp) {
+    SplitJob ja{A, ahi, alo, m, a_kc ? 1 : 0, split_blocks(a_kc, m, kp)};
+    SplitJob jb{B, bhi, blo, n, b_kc ? 1 : 0, split_blocks(b_kc, n, kp)};
+    split_pair_kernel<<<ja.blocks + jb.blocks, 256, 0, ctx->stream>>>(ja, jb, k, kp);
     DSC_LAUNCH_CHECK(ctx);
     return DSC_OK;
 }
@@ -483,30 +501,43 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
     const int kp = (k + BK - 1) / BK * BK;
 
     // ---- plan: tile width, split-K, workspace (all decided before anything is launched) ----
-    // tile width: shared-memory traffic per output column block is ~ (BM + BN) rows per k-block
-    int bn = 256;
+    // Cycle model per CTA and 32-wide k-block (B300_MICROARCH.md pacing law, measured here):
+    //   tensor pipe  : 4 k-slices x 3 MMAs x (BN/256 x 128) = 6 BN cycles
+    //   smem fill    : (BM + BN) rows x 128 B x 2 planes at 128 B/cycle       = 2 (BM + BN) cycles
+    //   L2 -> SM     : the same bytes from every active CTA through ~10 KB/cycle of L2 bandwidth
+    // plus ~4000 cycles of prologue / epilogue per unit.  Wide tiles win on big problems (less operand
+    // traffic), narrow tiles and split-K win when the output has fewer tiles than the machine has SMs.
+    const int num_kb = kp / BK;
+    const int chunks = (num_kb + kChunkKb - 1) / kChunkKb;
+    const int tiles_m = (m + BM - 1) / BM;
+    int bn = 256, splits = 1;
     {
-        long best = -1;
-        const int cands[3] = {64, 128, 256};
+        double best = -1.0;
+        const int cands[3] = {256, 128, 64};
         for (int c : cands) {
-            const long tn = (n + c - 1) / c;
-            const long cost = tn * (BM + c);
-            if (best < 0 || cost < best) { best = cost; bn = c; }
+            const int tn = (n + c - 1) / c, tiles = tiles_m * tn;
+            int max_split = chunks / 2 > 0 ? chunks / 2 : 1;   // every split keeps >= 2 chunks of K
+            if (max_split > 16) max_split = 16;
+            for (int sp = 1; sp <= max_split; sp *= 2) {
+                const int cps = (chunks + sp - 1) / sp;
+                const int real_sp = (chunks + cps - 1) / cps;
+                const long units = (long)tiles * real_sp;
+                const long waves = (units + ctx->sm_count - 1) / ctx->sm_count;
+                const double active = units < ctx->sm_count ? (double)units : (double)ctx->sm_count;
+                const double bytes_kb = (double)(BM + c) * 256.0;
+                double per_kb = 6.0 * c;
+                if (2.0 * (BM + c) > per_kb) per_kb = 2.0 * (BM + c);
+                if (bytes_kb * active / 10000.0 > per_kb) per_kb = bytes_kb * active / 10000.0;
+                double cost = (double)waves * ((double)cps * kChunkKb * per_kb + 4000.0);
+                if (real_sp > 1) cost += 3000.0 + (double)real_sp * m * n * 8.0 / 3500.0;  // partial planes written + reduced
+                if (best < 0 || cost < best) { best = cost; bn = c; splits = real_sp; }
+            }
         }
     }
     Params p;
-    p.m = m; p.n = n; p.num_kb = kp / BK;
-    p.tiles_m = (m + BM - 1) / BM;
+    p.m = m; p.n = n; p.num_kb = num_kb;
+    p.tiles_m = tiles_m;
     p.tiles_n = (n + bn - 1) / bn;
-    const int tiles = p.tiles_m * p.tiles_n;
-    const int chunks = (p.num_kb + kChunkKb - 1) / kChunkKb;
-    int splits = 1;
-    if (tiles * 2 <= ctx->sm_count && chunks >= 4) {  // every split keeps >= 2 chunks of K
-        splits = ctx->sm_count / tiles;
-        if (splits > chunks / 2) splits = chunks / 2;
-        if (splits > 16) splits = 16;
-        if (splits < 1) splits = 1;
-    }
     const int chunks_per_split = (chunks + splits - 1) / splits;
     splits = (chunks + chunks_per_split - 1) / chunks_per_split;
     p.splits = splits;
@@ -523,8 +554,7 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
 
     // ---- (1) split pre-pass ----
     // op(A)(m x k): stored m x k (K contiguous) unless ta; op(B)(k x n): stored k x n (K NOT contiguous) unless tb
-    DSC_TRY(split_operand(ctx, A, !ta, m, k, kp, ahi, alo));
-    DSC_TRY(split_operand(ctx, B, tb != 0, n, k, kp, bhi, blo));
+    DSC_TRY(split_pair(ctx, A, !ta, m, ahi, alo, B, tb != 0, n, bhi, blo, k, kp));
 
     // ---- (2) tensor-core kernel ----
     p.C = splits > 1 ? partial : C;

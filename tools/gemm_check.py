@@ -58,7 +58,7 @@ def main():
                 worst = max(worst, check(b, m, n, k, ta, tb))
     worst = max(worst, check(b, 1024, 1024, 8192, 0, 0, positive=True))
     worst = max(worst, check(b, 1024, 1024, 8192, 1, 0, positive=True))
-    for m, n, k in [(8192, 1024, 1024), (8192, 1024, 784), (1024, 1024, 8192), (4096, 4096, 4096), (8192, 8192, 8192) if which == "f32" else (4096, 4096, 4096)]:
+    for m, n, k in [(128, 300, 784), (1024, 1024, 1024), (2048, 1024, 1024), (4096, 1024, 1024), (1024, 1024, 2048), (8192, 1024, 1024), (8192, 1024, 784), (1024, 1024, 8192), (4096, 4096, 4096), (8192, 8192, 8192) if which == "f32" else (4096, 4096, 4096)]:
         worst = max(worst, check(b, m, n, k, 0, 0, time_it=True))
     worst = max(worst, check(b, 1024, 1024, 8192, 1, 0, time_it=True))
     worst = max(worst, check(b, 8192, 1024, 1024, 0, 1, time_it=True))
