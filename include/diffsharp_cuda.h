@@ -154,6 +154,7 @@ DSC_API int dsc_buf_download_async(dsc_buf_t h, int32_t off, void* pinned_host, 
 DSC_API int dsc_buf_fill(dsc_buf_t h, int32_t off, int32_t n, double v);
 DSC_API int dsc_buf_view(dsc_buf_t h, int32_t off, int32_t n, dsc_buf_t* out);                /* GetValues: same storage */
 DSC_API int dsc_buf_copy(dsc_buf_t h, dsc_buf_t* out);                                        /* DeepCopy; ReshapeCopy_MRows_V; ReshapeCopy_V_MRows (Backend.fs:109,134) */
+DSC_API int dsc_buf_share(dsc_buf_t h, dsc_buf_t* out);                                       /* DeepCopy semantics, copy-on-write: the copy happens only if either handle is written in place later */
 DSC_API int dsc_buf_gather2d(dsc_buf_t h, int32_t rows, int32_t cols, int32_t r0, int32_t r1,
                              int32_t c0, int32_t c1, dsc_buf_t* out);                         /* GetStackedValues (Util.fs:138,204-210), inclusive bounds */
 DSC_API int dsc_buf_info(dsc_buf_t h, int* dtype, int32_t* length, int32_t* offset,
@@ -207,6 +208,11 @@ DSC_API int dsc_host_free_pinned(void* p);
                                            int32_t doff, int32_t n);                                              \
     /* fused adjoint chains, see dsc_fused_kind: out = chain(dA, p)                                            */ \
     DSC_API int dsc_##P##fused_bwd(dsc_ctx_t ctx, int kind, dsc_buf_t dA, dsc_buf_t p, dsc_buf_t* out);           \
+    /* z[i,j] = A[i,j] + v[j]  ==  Add_M_M(A, RepeatReshapeCopy_V_MRows(m, v))  (Backend.fs:112,135): how the  */ \
+    /* fork broadcasts a bias (AD.Float32.fs:1860-1865) without materialising the m copies.  If op >= 0,       */ \
+    /* additionally h = Map_F_M(op, z) (Backend.fs:130) from the same pass; h may be NULL when op < 0.          */ \
+    DSC_API int dsc_##P##bias_rows_act(dsc_ctx_t ctx, int op, int32_t m, int32_t n, dsc_buf_t A, dsc_buf_t v,     \
+                                       dsc_buf_t* z, dsc_buf_t* h);                                               \
     /* ---- layout ----                                                                                        */ \
     DSC_API int dsc_##P##transpose(dsc_ctx_t ctx, int32_t m, int32_t n, dsc_buf_t A, dsc_buf_t* out);             \
     /* Transpose_M (Backend.fs:127), bit exact                                                                 */ \

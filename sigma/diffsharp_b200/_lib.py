@@ -129,6 +129,7 @@ _sig("dsc_buf_download_async", buf_t, i32, C.c_void_p, i32)
 _sig("dsc_buf_fill", buf_t, i32, i32, C.c_double)
 _sig("dsc_buf_view", buf_t, i32, i32, P(buf_t))
 _sig("dsc_buf_copy", buf_t, P(buf_t))
+_sig("dsc_buf_share", buf_t, P(buf_t))
 _sig("dsc_buf_gather2d", buf_t, i32, i32, i32, i32, i32, i32, P(buf_t))
 _sig("dsc_buf_info", buf_t, P(C.c_int), P(i32), P(i32), P(i32), P(C.c_void_p))
 _sig("dsc_host_alloc_pinned", C.c_size_t, P(C.c_void_p))
@@ -156,6 +157,7 @@ for _p, _T in (("s", C.c_float), ("d", C.c_double)):
     _sig(f"dsc_{_p}add_inplace", ctx_t, buf_t, buf_t)
     _sig(f"dsc_{_p}add_inplace_range", ctx_t, buf_t, i32, buf_t, i32, i32)
     _sig(f"dsc_{_p}fused_bwd", ctx_t, C.c_int, buf_t, buf_t, P(buf_t))
+    _sig(f"dsc_{_p}bias_rows_act", ctx_t, C.c_int, i32, i32, buf_t, buf_t, P(buf_t), C.c_void_p)
     _sig(f"dsc_{_p}transpose", ctx_t, i32, i32, buf_t, P(buf_t))
     _sig(f"dsc_{_p}permute", ctx_t, C.c_int, P(C.c_int64), P(i32), buf_t, P(buf_t))
     _sig(f"dsc_{_p}repeat_rows", ctx_t, i32, buf_t, P(buf_t))

@@ -17,10 +17,14 @@ eager sequence and switchable off with ``CudaBackend(fuse=False)``:
     materialises it.
   * the tanh adjoint chain Map(Cosh) -> Map_F_S(1, Div) -> Had -> Had (AD.Float32.fs:4238-4240) is
     recognised and issued as one fused kernel with the same sequence of roundings.
+  * the fork's bias broadcast ``RepeatReshapeCopy_V_MRows`` -> ``Add_M_M`` [-> ``Map_F_M``]
+    (AD.Float32.fs:1860-1865,2357,2704) is deferred and issued as ONE pass ``dsc_?bias_rows_act``
+    (z = A + rows(v); h = f(z)) instead of materialising the m copies of the bias.
   * zero adjoints are lazy: ``CreateDataBuffer(CreateZeroArray n)`` (two per tape node,
     AD.Float32.fs:1834-1835,3746) allocates nothing; the first ``Add_M_M_InPlace``/``Add_V_V`` into
-    a known-zero buffer is a copy of the addend (0 + v = v; only the sign of a zero can differ), any
-    other use materialises the zeros with a memset.
+    a known-zero buffer is a COPY-ON-WRITE alias of the addend (``dsc_buf_share``: 0 + v = v; only
+    the sign of a zero can differ; the copy happens only if either side is later written in place),
+    any other use materialises the zeros with a memset.
 """
 from __future__ import annotations
 
@@ -147,7 +151,7 @@ class CudaBackend(Backend):
         f = lambda name: getattr(lib, f"dsc_{self._p}{name}")  # noqa: E731
         self._f = {n: f(n) for n in (
             "gemm", "gemv", "ger", "dot", "asum", "nrm2", "amax", "sum", "argmax", "argmin", "sum_dev", "dot_dev",
-            "map", "map_s", "map2", "scalar_op", "add_inplace", "add_inplace_range", "fused_bwd", "transpose",
+            "map", "map_s", "map2", "scalar_op", "add_inplace", "add_inplace_range", "fused_bwd", "bias_rows_act", "transpose",
             "permute", "repeat_rows", "repeat_cols", "colsum_inplace", "add_v_mcols", "diag", "gesv", "sysv",
             "getri", "det", "allreduce_sum", "allgather")}
         self._empty = CudaDataBuffer.empty(self.ctx, self.dtype, 0)
@@ -186,6 +190,14 @@ class CudaBackend(Backend):
         if lz.kind == "Z":
             h = _lib.buf_t()
             check(lib.dsc_buf_alloc_fill(self._h, self._code, lb._length, 0.0, C.byref(h)))
+        elif lz.kind == "R":      # ('R', v, m, n): m copies of v as rows
+            v, m, n = lz.args
+            h = _lib.buf_t()
+            check(self._f["repeat_rows"](self._h, m, v.handle, C.byref(h)))
+        elif lz.kind == "AR":     # ('AR', A, v, m, n): A + rows(v)
+            A, v, m, n = lz.args
+            h = _lib.buf_t()
+            check(self._f["bias_rows_act"](self._h, -1, m, n, A.handle, v.handle, C.byref(h), None))
         elif lz.kind == "T":
             src, m, n = lz.args
             h = _lib.buf_t()
@@ -336,6 +348,12 @@ class CudaBackend(Backend):
         return self._view(self._out(self._f["ger"], da.Length * db.Length, da.handle, db.handle), da.Length, db.Length)
 
     def Add_M_M(self, a, b):
+        if self.fuse:
+            la, lb_ = self._lz(a.DataBuffer), self._lz(b.DataBuffer)
+            for x, lx, y, ly in ((a, la, b, lb_), (b, lb_, a, la)):  # fp add commutes bit for bit
+                if ly is not None and ly.kind == "R" and (lx is None or lx.kind != "R") and x.DataBuffer.Length == y.DataBuffer.Length \
+                        and tuple(x.Shape) == (ly.args[1], ly.args[2]) and isinstance(x.DataBuffer, CudaDataBuffer):
+                    return self._view(LazyCudaBuffer(self, x.DataBuffer.Length, _Lazy("AR", x.DataBuffer, ly.args[0], ly.args[1], ly.args[2])), *x.Shape)
         # shape of the non-empty operand (empty = additive identity)
         shp = a.Shape if a.DataBuffer.Length else b.Shape
         return self._view(self._map2(MapOp.Add, a.DataBuffer, b.DataBuffer), *shp)
@@ -349,7 +367,7 @@ class CudaBackend(Backend):
             if db.Length != da.Length:
                 raise _lib.InvalidArgError(_lib.DSC_E_SHAPE, "Matrices must have same shape.")
             h = _lib.buf_t()
-            check(lib.dsc_buf_copy(db.handle, C.byref(h)))
+            check(lib.dsc_buf_share(db.handle, C.byref(h)))  # copy-on-write alias of the addend
             da._h, da._lazy = h.value, None
             da._finalizer = weakref.finalize(da, lib.dsc_buf_free, h.value)
             return a
@@ -441,6 +459,16 @@ class CudaBackend(Backend):
         return ShapedDataBufferView(a.DataBuffer, *[int(s) for s in newShape])
 
     def Map_F_M(self, op, f, a):
+        lz = self._lz(a.DataBuffer) if self.fuse else None
+        if lz is not None and lz.kind == "AR" and MapOp.Log <= int(op) <= MapOp.Sigmoid:
+            # z = A + rows(v) is still pending: produce z and h = f(z) in one pass
+            A, v, m, n = lz.args
+            z, h = _lib.buf_t(), _lib.buf_t()
+            check(self._f["bias_rows_act"](self._h, int(op), m, n, A.handle, v.handle, C.byref(z), C.byref(h)))
+            zb = a.DataBuffer
+            zb._h, zb._lazy = z.value, None
+            zb._finalizer = weakref.finalize(zb, lib.dsc_buf_free, z.value)
+            return self._view(CudaDataBuffer(self.ctx, self.dtype, h.value, m * n), *a.Shape)
         if self.fuse and int(op) == MapOp.Cosh:
             # possible head of the tanh adjoint chain (AD.Float32.fs:4238): defer
             d = self._dev(a.DataBuffer)
@@ -462,6 +490,8 @@ class CudaBackend(Backend):
 
     def RepeatReshapeCopy_V_MRows(self, m, v):
         d = self._dev(v)
+        if self.fuse and m * d.Length > 0:
+            return self._view(LazyCudaBuffer(self, m * d.Length, _Lazy("R", d, m, d.Length)), m, d.Length)
         return self._view(self._out(self._f["repeat_rows"], m * d.Length, m, d.handle), m, d.Length)
 
     def RepeatReshapeCopy_V_MCols(self, n, v):

@@ -81,6 +81,7 @@ static int allreduce_impl(dsc_ctx_t c, int32_t count, const dsc_buf_t* bufs) {
     for (int i = 0; i < count; ++i) {
         Buf* b;
         DSC_TRY(in_buf(ctx, dtype_of<T>::value, bufs[i], &b, "allreduce: buffer"));
+        DSC_TRY(buf_writable(ctx, b));  // in-place collective
     }
     DSC_TRY(comm_fork(ctx));
     const int dt = sizeof(T) == 4 ? NCCL_FLOAT32 : NCCL_FLOAT64;
@@ -105,6 +106,7 @@ static int allgather_impl(dsc_ctx_t c, dsc_buf_t sendh, dsc_buf_t recvh) {
     if ((int64_t)s->len * ctx->nranks != r->len)
         return fail(DSC_E_SHAPE, "allgather: recv length %d != %d ranks x send length %d", r->len, ctx->nranks, s->len);
     if (s->len == 0) return DSC_OK;
+    DSC_TRY(buf_writable(ctx, r));
     if (ctx->nranks == 1) {
         DSC_CUDA_CHECK(cudaMemcpyAsync(r->ptr<T>(), s->ptr<T>(), (size_t)s->len * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
         return DSC_OK;

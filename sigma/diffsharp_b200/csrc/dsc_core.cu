@@ -126,6 +126,25 @@ int buf_new(Ctx* ctx, int dtype, int32_t n, Buf** out) {
     return DSC_OK;
 }
 
+int buf_writable(Ctx* ctx, Buf* b) {
+    Block* old = b->block;
+    if (!old || !old->cow_shared || old->refs <= 1) return DSC_OK;
+    Block* nb = nullptr;
+    const size_t es = dtype_size(b->dtype);
+    DSC_TRY(pool_alloc(ctx, (size_t)b->len * es, &nb));
+    cudaError_t e = cudaMemcpyAsync(nb->ptr, reinterpret_cast<const char*>(old->ptr) + b->off * es, (size_t)b->len * es,
+                                    cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+        block_release(nb);
+        return fail(DSC_E_CUDA, "copy-on-write copy failed: %s", cudaGetErrorString(e));
+    }
+    ctx->stats.kernel_launches++;
+    block_release(old);
+    b->block = nb;
+    b->off = 0;
+    return DSC_OK;
+}
+
 int out_buf(Ctx* ctx, int dtype, int32_t n, dsc_buf_t* out, Buf** res) {
     if (!out) return fail(DSC_E_INVALID, "null output handle pointer");
     if (*out == 0) {
@@ -140,6 +159,7 @@ int out_buf(Ctx* ctx, int dtype, int32_t n, dsc_buf_t* out, Buf** res) {
     if (b->ctx != ctx) return fail(DSC_E_INVALID, "output buffer belongs to another context");
     if (b->dtype != dtype) return fail(DSC_E_DTYPE, "output buffer has the wrong dtype");
     if (b->len != n) return fail(DSC_E_SHAPE, "output buffer has length %d, expected %d", b->len, n);
+    DSC_TRY(buf_writable(ctx, b));
     *res = b;
     return DSC_OK;
 }
@@ -514,6 +534,7 @@ int dsc_buf_upload(dsc_buf_t h, int32_t off, const void* host, int32_t n) {
     if (n == 0) return DSC_OK;
     if (!host) return fail(DSC_E_INVALID, "upload: null host pointer");
     Ctx* ctx = b->ctx;
+    DSC_TRY(buf_writable(ctx, b));
     size_t es = dtype_size(b->dtype);
     char* dst = reinterpret_cast<char*>(b->block->ptr) + (b->off + off) * es;
     DSC_CUDA_CHECK(cudaMemcpyAsync(dst, host, (size_t)n * es, cudaMemcpyHostToDevice, ctx->stream));
@@ -529,6 +550,7 @@ int dsc_buf_upload_async(dsc_buf_t h, int32_t off, const void* host, int32_t n) 
     if (n == 0) return DSC_OK;
     if (!host) return fail(DSC_E_INVALID, "upload_async: null host pointer");
     Ctx* ctx = b->ctx;
+    DSC_TRY(buf_writable(ctx, b));
     size_t es = dtype_size(b->dtype);
     char* dst = reinterpret_cast<char*>(b->block->ptr) + (b->off + off) * es;
     DSC_CUDA_CHECK(cudaMemcpyAsync(dst, host, (size_t)n * es, cudaMemcpyHostToDevice, ctx->stream));
@@ -571,6 +593,7 @@ int dsc_buf_fill(dsc_buf_t h, int32_t off, int32_t n, double v) {
     Buf* b = as_buf(h);
     if (!b) return fail(DSC_E_INVALID, "fill: bad handle");
     DSC_TRY(check_range(b, off, n, "fill"));
+    if (n > 0) DSC_TRY(buf_writable(b->ctx, b));
     return fill_window(b->ctx, b, off, n, v);
 }
 
@@ -578,6 +601,10 @@ int dsc_buf_view(dsc_buf_t h, int32_t off, int32_t n, dsc_buf_t* out) {
     Buf* b = as_buf(h);
     if (!b || !out) return fail(DSC_E_INVALID, "view: bad handle or null out");
     DSC_TRY(check_range(b, off, n, "view"));
+    if (n > 0) {
+        DSC_TRY(buf_writable(b->ctx, b));  // a true view shares MUTABLE storage: detach from CoW aliases first
+        b->block->has_views = true;
+    }
     Buf* v = new Buf();
     v->dtype = b->dtype;
     v->ctx = b->ctx;
@@ -587,6 +614,27 @@ int dsc_buf_view(dsc_buf_t h, int32_t off, int32_t n, dsc_buf_t* out) {
         v->block->refs++;
         v->off = b->off + off;
     }
+    *out = reinterpret_cast<dsc_buf_t>(v);
+    return DSC_OK;
+}
+
+int dsc_buf_copy(dsc_buf_t h, dsc_buf_t* out);
+
+int dsc_buf_share(dsc_buf_t h, dsc_buf_t* out) {
+    Buf* b = as_buf(h);
+    if (!b || !out) return fail(DSC_E_INVALID, "share: bad handle or null out");
+    if (b->len == 0 || b->block->has_views) {
+        *out = 0;
+        return dsc_buf_copy(h, out);  // a block with true views (shared mutable storage) is copied eagerly
+    }
+    Buf* v = new Buf();
+    v->dtype = b->dtype;
+    v->ctx = b->ctx;
+    v->len = b->len;
+    v->block = b->block;
+    v->off = b->off;
+    b->block->refs++;
+    b->block->cow_shared = true;
     *out = reinterpret_cast<dsc_buf_t>(v);
     return DSC_OK;
 }

@@ -346,6 +346,7 @@ static int add_inplace_impl(dsc_ctx_t c, dsc_buf_t dh, dsc_buf_t sh) {
     DSC_TRY(in_buf(ctx, dtype_of<T>::value, sh, &s, "add_inplace: src"));
     if (s->len == 0) return DSC_OK;  // DNDArray.Zero push (AD.Float32.fs:4245-4248,4272)
     if (s->len != d->len) return fail(DSC_E_SHAPE, "Add_M_M_InPlace: lengths %d and %d", d->len, s->len);
+    DSC_TRY(buf_writable(ctx, d));
     return launch_stream<T, BinaryF<DSC_OP_ADD, T>, 2>(ctx, BinaryF<DSC_OP_ADD, T>(), d->ptr<T>(), s->ptr<T>(), d->ptr<T>(), d->len);
 }
 
@@ -359,6 +360,7 @@ static int add_inplace_range_impl(dsc_ctx_t c, dsc_buf_t sh, int32_t soff, dsc_b
     if (n < 0 || soff < 0 || doff < 0 || (int64_t)soff + n > s->len || (int64_t)doff + n > d->len)
         return fail(DSC_E_SHAPE, "Add_V_V_InPlace: range out of bounds (src %d+%d of %d, dst %d+%d of %d)", soff, n, s->len, doff, n, d->len);
     if (n == 0) return DSC_OK;
+    DSC_TRY(buf_writable(ctx, d));
     return launch_stream<T, BinaryF<DSC_OP_ADD, T>, 2>(ctx, BinaryF<DSC_OP_ADD, T>(), d->ptr<T>() + doff, s->ptr<T>() + soff, d->ptr<T>() + doff, n);
 }
 
@@ -380,6 +382,80 @@ static int fused_bwd_impl(dsc_ctx_t c, int kind, dsc_buf_t dAh, dsc_buf_t ph, ds
     return fail(DSC_E_UNSUPPORTED_OP, "fused_bwd: unknown kind %d", kind);
 }
 
+// z = A + rows(v) [; h = f_op(z)] — one pass over A instead of broadcast + add (+ map).
+// Same roundings as the unfused sequence: z is the fp add, h applies the op to the ROUNDED z.
+template <typename T, int OP, bool ACT, bool VEC>
+__global__ void __launch_bounds__(kThreads) bias_rows_act_kernel(const T* __restrict__ A, const T* __restrict__ v, T* __restrict__ z,
+                                                                  T* __restrict__ h, size_t total, int n) {
+    constexpr int W = VEC ? Vec<T>::N : 1;
+    const size_t nitems = total / W;
+    const size_t base = (size_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+        const size_t i = base + (size_t)u * kThreads;
+        if (i >= nitems) continue;
+        if constexpr (VEC) {
+            using V = typename Vec<T>::type;
+            V a = ldv<T>(A + i * W);
+            const int col = (int)((i * W) % (size_t)n);  // n % W == 0: a vector never straddles two rows
+            V b = ldv<T>(v + col);
+            V zz, hh;
+#pragma unroll
+            for (int l = 0; l < W; ++l) {
+                lane(zz, l) = lane(a, l) + lane(b, l);
+                if constexpr (ACT) lane(hh, l) = unary_op<OP>(lane(zz, l));
+            }
+            stv<T>(z + i * W, zz);
+            if constexpr (ACT) stv<T>(h + i * W, hh);
+        } else {
+            const T zz = A[i] + v[i % (size_t)n];
+            z[i] = zz;
+            if constexpr (ACT) h[i] = unary_op<OP>(zz);
+        }
+    }
+}
+
+template <typename T, int OP, bool ACT>
+static int launch_bias_rows(Ctx* ctx, const T* A, const T* v, T* z, T* h, int m, int n) {
+    const size_t total = (size_t)m * n;
+    const bool vec = (n % Vec<T>::N == 0) && aligned16(A) && aligned16(v) && aligned16(z) && (!ACT || aligned16(h));
+    const size_t items = vec ? total / Vec<T>::N : total;
+    const unsigned grid = (unsigned)((items + (size_t)kThreads * kUnroll - 1) / ((size_t)kThreads * kUnroll));
+    if (vec) bias_rows_act_kernel<T, OP, ACT, true><<<grid, kThreads, 0, ctx->stream>>>(A, v, z, h, total, n);
+    else bias_rows_act_kernel<T, OP, ACT, false><<<grid, kThreads, 0, ctx->stream>>>(A, v, z, h, total, n);
+    DSC_LAUNCH_CHECK(ctx);
+    return DSC_OK;
+}
+
+template <typename T>
+static int bias_rows_act_impl(dsc_ctx_t c, int op, int32_t m, int32_t n, dsc_buf_t Ah, dsc_buf_t vh, dsc_buf_t* zh, dsc_buf_t* hh) {
+    if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
+    Ctx* ctx = as_ctx(c);
+    Buf *A, *v, *z, *h = nullptr;
+    DSC_TRY(in_buf(ctx, dtype_of<T>::value, Ah, &A, "bias_rows_act: A"));
+    DSC_TRY(in_buf(ctx, dtype_of<T>::value, vh, &v, "bias_rows_act: v"));
+    if (m < 0 || n < 0 || (int64_t)m * n != A->len) return fail(DSC_E_SHAPE, "Matrices must have same shape.");
+    if (v->len != n) return fail(DSC_E_SHAPE, "bias_rows_act: vector length %d, matrix has %d columns", v->len, n);
+    if (op >= 0 && (op < DSC_OP_LOG || op >= DSC_OP__COUNT)) return fail(DSC_E_UNSUPPORTED_OP, "bias_rows_act: op-code %d is not a unary MapOp", op);
+    DSC_TRY(out_buf(ctx, dtype_of<T>::value, m * n, zh, &z));
+    if (op >= 0) DSC_TRY(out_buf(ctx, dtype_of<T>::value, m * n, hh, &h));
+    if (m * n == 0) return DSC_OK;
+    const T* Ap = A->ptr<T>();
+    const T* vp = v->ptr<T>();
+    T* zp = z->ptr<T>();
+    T* hp = h ? h->ptr<T>() : nullptr;
+    switch (op) {
+#define CASE(OPC) \
+    case OPC: return launch_bias_rows<T, OPC, true>(ctx, Ap, vp, zp, hp, m, n);
+        CASE(DSC_OP_LOG) CASE(DSC_OP_LOG10) CASE(DSC_OP_EXP) CASE(DSC_OP_SIN) CASE(DSC_OP_COS) CASE(DSC_OP_TAN)
+        CASE(DSC_OP_SQRT) CASE(DSC_OP_SINH) CASE(DSC_OP_COSH) CASE(DSC_OP_TANH) CASE(DSC_OP_ASIN) CASE(DSC_OP_ACOS)
+        CASE(DSC_OP_ATAN) CASE(DSC_OP_ABS) CASE(DSC_OP_SIGN) CASE(DSC_OP_FLOOR) CASE(DSC_OP_CEILING)
+        CASE(DSC_OP_ROUND) CASE(DSC_OP_REL) CASE(DSC_OP_SIGMOID)
+#undef CASE
+        default: return launch_bias_rows<T, 0, false>(ctx, Ap, vp, zp, nullptr, m, n);
+    }
+}
+
 }  // namespace dsc
 
 using namespace dsc;
@@ -394,7 +470,10 @@ extern "C" {
     int dsc_##P##add_inplace_range(dsc_ctx_t c, dsc_buf_t s, int32_t so, dsc_buf_t d, int32_t dof, int32_t n) {            \
         return add_inplace_range_impl<T>(c, s, so, d, dof, n);                                                             \
     }                                                                                                                      \
-    int dsc_##P##fused_bwd(dsc_ctx_t c, int kind, dsc_buf_t dA, dsc_buf_t p, dsc_buf_t* out) { return fused_bwd_impl<T>(c, kind, dA, p, out); }
+    int dsc_##P##fused_bwd(dsc_ctx_t c, int kind, dsc_buf_t dA, dsc_buf_t p, dsc_buf_t* out) { return fused_bwd_impl<T>(c, kind, dA, p, out); } \
+    int dsc_##P##bias_rows_act(dsc_ctx_t c, int op, int32_t m, int32_t n, dsc_buf_t A, dsc_buf_t v, dsc_buf_t* z, dsc_buf_t* h) { \
+        return bias_rows_act_impl<T>(c, op, m, n, A, v, z, h);                                                             \
+    }
 DSC_EW_API(s, float)
 DSC_EW_API(d, double)
 }

@@ -28,6 +28,8 @@ struct Block {
     int refs = 0;
     Ctx* ctx = nullptr;
     int arena = 0;      // 0 = main pool; >0 = id of the CUDA-graph private pool it belongs to
+    bool has_views = false;   // a true view (dsc_buf_view: shared MUTABLE storage) exists or existed
+    bool cow_shared = false;  // copy-on-write aliases (dsc_buf_share) exist or existed
 };
 
 // Device twin of ISigmaDiffDataBuffer<'T> (reference Util.fs:133-141): a window over a Block.
@@ -151,6 +153,8 @@ int buf_new(Ctx* ctx, int dtype, int32_t n, Buf** out);
 int out_buf(Ctx* ctx, int dtype, int32_t n, dsc_buf_t* out, Buf** res);
 // Validate an input handle of the given dtype (zero-length buffers are valid).
 int in_buf(Ctx* ctx, int dtype, dsc_buf_t h, Buf** res, const char* what);
+// Copy-on-write: before writing through `b`, give it a private block if its block has CoW aliases.
+int buf_writable(Ctx* ctx, Buf* b);
 int ensure_red_scratch(Ctx* ctx, size_t bytes);
 int ensure_gemm_ws(Ctx* ctx, size_t bytes);
 

@@ -320,6 +320,7 @@ static int colsum_impl(dsc_ctx_t c, int32_t m, int32_t n, dsc_buf_t Mh, dsc_buf_
     if (m < 0 || n < 0 || (int64_t)m * n > M->len) return fail(DSC_E_SHAPE, "Add_M_Colwise_V_InPlace: %d x %d exceeds buffer length %d", m, n, M->len);
     if (v->len != n) return fail(DSC_E_SHAPE, "Add_M_Colwise_V_InPlace: vector length %d, matrix has %d columns", v->len, n);
     if (m == 0 || n == 0) return DSC_OK;
+    DSC_TRY(buf_writable(ctx, v));
     return colsum_launch<T>(ctx, M->ptr<T>(), v->ptr<T>(), m, n);
 }
 

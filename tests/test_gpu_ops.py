@@ -195,3 +195,47 @@ def test_buffer_interface(cuda_provider):
     assert np.array_equal(w.SubData, np.full(1000, 2.5, np.float32))
     st = b.ctx.stats()
     assert st["kernel_launches"] > 0 and st["pool_hits"] + st["pool_misses"] > 0
+
+
+def test_copy_on_write_share(cuda_provider):
+    """dsc_buf_share: DeepCopy semantics without the copy until somebody writes in place; true views
+    (GetValues) keep sharing mutable storage (Util.fs:137, AD.Float32.fs:663)."""
+    import ctypes as C
+    b = backend(cuda_provider, np.float32)
+    x = b.CreateDataBuffer(np.arange(8, dtype=np.float32))
+    h = _lib.buf_t()
+    _lib.check(_lib.lib.dsc_buf_share(x.handle, C.byref(h)))
+    y = CudaDataBuffer(b.ctx, np.float32, h.value, 8)
+    one = b.CreateDataBuffer(np.ones(8, np.float32))
+    b.Add_V_V_InPlace(one, 0, y, 0, 8)                      # write through the alias: it detaches first
+    assert np.array_equal(x.SubData, np.arange(8)) and np.array_equal(y.SubData, np.arange(8) + 1)
+    _lib.check(_lib.lib.dsc_buf_share(x.handle, C.byref(h)))
+    z = CudaDataBuffer(b.ctx, np.float32, h.value, 8)
+    b.Add_V_V_InPlace(one, 0, x, 0, 8)                      # write through the original: it detaches
+    assert np.array_equal(z.SubData, np.arange(8)) and np.array_equal(x.SubData, np.arange(8) + 1)
+    v = x.GetValues(2, 3)                                   # a true view still sees in-place updates
+    b.Add_V_V_InPlace(one, 0, x, 0, 8)
+    assert np.array_equal(v.SubData, np.arange(2, 5) + 2)
+    _lib.check(_lib.lib.dsc_buf_share(x.handle, C.byref(h)))  # a block with views is copied eagerly
+    w = CudaDataBuffer(b.ctx, np.float32, h.value, 8)
+    b.Add_V_V_InPlace(one, 0, x, 0, 8)
+    assert np.array_equal(w.SubData, np.arange(8) + 2)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("m,n", [(1, 1), (7, 10), (33, 64), (500, 1024)])
+def test_fused_bias_activation_matches_the_unfused_sequence(cuda_provider, cuda_provider_nofuse, dtype, m, n):
+    """RepeatReshapeCopy_V_MRows -> Add_M_M -> Map_F_M issued lazily as one pass == the three eager calls, bit for bit."""
+    rng = np.random.default_rng(m * n)
+    A, v = rng.standard_normal((m, n)).astype(dtype), rng.standard_normal(n).astype(dtype)
+    outs = []
+    for prov in (cuda_provider, cuda_provider_nofuse):
+        b = backend(prov, dtype)
+        dA = ShapedDataBufferView(b.CreateDataBuffer(A.reshape(-1)), m, n)
+        rows = b.RepeatReshapeCopy_V_MRows(m, b.CreateDataBuffer(v))
+        z = b.Add_M_M(dA, rows)
+        hs = [b.Map_F_M(op, None, z).to_numpy() for op in (MapOp.Tanh,)]
+        outs.append((z.to_numpy(), hs[0], b.Add_M_M(rows, dA).to_numpy(), rows.to_numpy()))
+    for f, u in zip(outs[0], outs[1]):
+        assert np.array_equal(f, u)
+    assert np.array_equal(outs[0][3], np.tile(v, (m, 1)))
