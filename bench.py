@@ -35,7 +35,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 LAYERS = [784, 1024, 1024, 10]
-GLOBAL_BATCH = 8192
+GLOBAL_BATCH = int(os.environ.get("DSC_BENCH_BATCH", "8192"))  # override only for experiments; the metric is quoted on 8192
 # algorithmic GEMM work of one C3 step = fwd + dW + dH
 STEP_GFLOP = 78.35
 ALLREDUCE_MB = 7.45
@@ -234,6 +234,112 @@ def op_sweep(provider, peaks, n=4096):
     return out
 
 
+def other_configs(provider, comm, rank, world, peaks):
+    """The remaining BASELINE.json configurations, each as its own small timed loop (CUDA events on the
+    context's stream, eager plugin calls):
+      C1  reverse-mode grad, 784-300-10, B=128, f32      (replicas only: rank 0)
+      C4  forward-mode Jacobian rows of two 4096->4096 tanh layers, f64, tangent rows sharded over ranks
+      C5  reverse-on-forward Hessian-vector product, n = 1e6, f64 (replicas only: rank 0)"""
+    from sigma.diffsharp_b200 import dist as D, workloads as wl
+    from sigma.diffsharp_b200.buffers import CudaDataBuffer
+    ctx = provider.ctx
+    out = {}
+    e0, e1 = ctx.event(), ctx.event()
+
+    def timed(fn, iters, warm=2):
+        for _ in range(warm):
+            fn()
+        ctx.sync()
+        D.barrier()
+        ctx.record(e0)
+        for _ in range(iters):
+            r = fn()
+        ctx.record(e1)
+        ctx.sync()
+        D.barrier()
+        return D.max_over_ranks(ctx.elapsed_ms(e0, e1)) / iters, r
+
+    # ---- C4: Jacobian, columns (tangent rows) sharded, all-gather at the end ----
+    n = 4096
+    W1, b1, W2, b2, x = wl.jacobian_inputs(n)
+    dW1, db1, dW2, db2, dx = wl.to_DM(W1), wl.to_DV(b1), wl.to_DM(W2), wl.to_DV(b2), wl.to_DV(x)
+    c0, c1 = D.shard_range(n, rank, world)
+    full = CudaDataBuffer.empty(ctx, np.float64, n * n) if world > 1 else None
+
+    tangent = wl.identity_rows(n, c0, c1 - c0)   # the matrix tangent is an input: built and uploaded once
+
+    def c4():
+        J = wl.jacobian_rows(dW1, db1, dW2, db2, dx, c0, c1 - c0, tangent)
+        if world > 1:
+            comm.allgather(J.Buffer.DataBuffer, full)
+            comm.join()
+        return J
+    ms, J = timed(c4, 3, warm=1)
+    tangent_gflop = 2 * 2.0 * n * n * (c1 - c0) / 1e9           # SURVEY 8(d): tangent GEMMs only
+    issued_gflop = 2 * tangent_gflop                            # the faithful sequence also runs the replicated-primal GEMMs
+    sample = J.ToArray()[:4]
+    ref = wl.jacobian_closed_form(W1, b1, W2, b2, x)[c0:c0 + 4]
+    out["C4_jacobian_f64"] = {
+        "ms": round(ms, 3), "rows_per_gpu": c1 - c0, "jacobians_per_s": round(1e3 / ms, 3),
+        "algorithmic_TFLOP/s_per_gpu": round(tangent_gflop / ms, 2), "issued_TFLOP/s_per_gpu": round(issued_gflop / ms, 2),
+        "peak": round(peaks["fp64_tflops"], 1), "frac_issued": round(issued_gflop / ms / peaks["fp64_tflops"], 3),
+        "max_rel_err_vs_closed_form": float(np.abs(sample - ref).max() / np.abs(ref).max()), "scaling": "strong (n = 4096 fixed)"}
+    del full, J, tangent
+
+    def graph_timed(fn, backends, iters):
+        """capture fn() once, replay `iters` times; device time per replay"""
+        fn()
+        ctx.sync()
+        for b in backends:
+            b.capture_scalars = []
+        ctx.graph_begin()
+        try:
+            keep = fn()
+        finally:
+            g = ctx.graph_end()
+            for b in backends:
+                b.capture_scalars = None
+        ctx.graph_launch(g)
+        ctx.sync()
+        ctx.record(e0)
+        for _ in range(iters):
+            ctx.graph_launch(g)
+        ctx.record(e1)
+        ms = ctx.elapsed_ms(e0, e1) / iters
+        return ms, keep, g
+
+    b32 = provider.GetBackend(np.float32(0)).BackendHandle
+    b64 = provider.GetBackend(np.float64(0)).BackendHandle
+    if rank == 0:
+        # ---- C1 ----
+        X, Y, Ws, bs = wl.mlp_inputs([784, 300, 10], 128)
+        dX, dY = wl.to_DM(X), wl.to_DM(Y)
+        dWs, dbs = [wl.to_DM(w) for w in Ws], [wl.to_DV(b) for b in bs]
+    if world == 1:
+        ms, _ = timed(lambda: wl.mlp_grad(dX, dY, dWs, dbs), 50, warm=5)
+        gms, keep, g = graph_timed(lambda: wl.mlp_grad(dX, dY, dWs, dbs), [b32], 200)
+        del keep
+        ctx.graph_destroy(g)
+        out["C1_mlp_784_300_10_B128_f32"] = {"eager_ms": round(ms, 4), "eager_steps_per_s": round(1e3 / ms, 1),
+                                               "graph_ms": round(gms, 4), "graph_steps_per_s": round(1e3 / gms, 1),
+                                               "note": "latency-bound (0.123 GFLOP/step): eager = host-driven plugin calls, graph = replayed call sequence"}
+        # ---- C5 ----
+        xx, vv, dd = wl.hvp_inputs(1_000_000)
+        dxx, dvv, ddd = wl.to_DV(xx), wl.to_DV(vv), wl.to_DV(dd)
+        ms, hv = timed(lambda: wl.hvp(ddd, dxx, dvv), 20, warm=3)
+        ref = wl.hvp_closed_form(xx, vv, dd)
+        gms, keep, g = graph_timed(lambda: wl.hvp(ddd, dxx, dvv), [b64], 50)
+        out["C5_hvp_n1e6_f64"] = {"eager_ms": round(ms, 4), "eager_hvp_per_s": round(1e3 / ms, 1),
+                                   "graph_ms": round(gms, 4), "graph_hvp_per_s": round(1e3 / gms, 1),
+                                   "algorithmic_GB/s": round(32e-3 / gms * 1e3, 1), "frac_hbm_algorithmic": round(32e-3 / gms * 1e3 / peaks["hbm_gbs"], 4),
+                                   "max_rel_err_vs_closed_form": float(np.abs(hv.ToArray() - ref).max() / np.abs(ref).max()),
+                                   "graph_max_rel_err_vs_closed_form": float(np.abs(keep.ToArray() - ref).max() / np.abs(ref).max()),
+                                   "note": "algorithmic = 4 vectors x 8 MB (minimal formula); the unfused call sequence moves ~50 vectors"}
+        del keep
+        ctx.graph_destroy(g)
+    return out
+
+
 def run_ours(args):
     from sigma.diffsharp_b200 import _lib, dist as D, workloads as wl
     from sigma.diffsharp_b200._lib import check, lib
@@ -380,6 +486,9 @@ def run_ours(args):
         "loss": loss_graph, "loss_e2e": loss_e2e,
         "clocks": clocks, "roofline": roofline, "peaks": peaks,
     }
+    if not args.no_other:
+        oc = other_configs(provider, comm, rank, world, peaks)
+        line["other_configs"] = oc
     if world == 1 and rank == 0 and not args.no_sweep:
         line["op_sweep"] = op_sweep(provider, peaks)
     if world == 1 and rank == 0 and not args.no_cpu:
@@ -425,6 +534,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-sweep", action="store_true", help="skip the config-2 op sweep")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-other", action="store_true", help="skip configs C1/C4/C5")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -235,6 +235,12 @@ class CudaBackend(Backend):
 
     # ---- Scalar valued (Backend.fs:81-88) -------------------------------------------------------
     def _scalar_red(self, name, *bufs):
+        if self.capture_scalars is not None and name in ("sum", "dot"):
+            # under CUDA-graph capture the scalar stays on the device (a host scalar needs a sync);
+            # the AD layer gets a placeholder: adjoints never depend on the value of a reduction
+            devs = [self._dev(b) for b in bufs]
+            self.capture_scalars.append(self._out(self._f[name + "_dev"], 1, *[d.handle for d in devs]))
+            return self.dtype.type(0)
         out = self._scalar()
         check(self._f[name](self._h, *[self._dev(b).handle for b in bufs], C.byref(out)))
         return self.dtype.type(out.value)
@@ -245,12 +251,7 @@ class CudaBackend(Backend):
     def SupNorm_V(self, a): return self._scalar_red("amax", a)
     def Sum_V(self, a): return self._scalar_red("sum", a)
 
-    def Sum_M(self, a):
-        if self.capture_scalars is not None:  # under graph capture the scalar stays on the device
-            d = self._dev(a)
-            self.capture_scalars.append(self._out(self._f["sum_dev"], 1, d.handle))
-            return self.dtype.type(0)
-        return self._scalar_red("sum", a)
+    def Sum_M(self, a): return self._scalar_red("sum", a)
 
     def _index_red(self, name, a):
         out = C.c_int32()

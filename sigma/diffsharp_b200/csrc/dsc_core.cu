@@ -311,6 +311,7 @@ int dsc_destroy(dsc_ctx_t c) {
     if (ctx->red_host) cudaFreeHost(ctx->red_host);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     if (ctx->gemm_ws) cudaFree(ctx->gemm_ws);
+    if (ctx->comm_stage) cudaFree(ctx->comm_stage);
     cudaEventDestroy(ctx->ev_compute);
     cudaEventDestroy(ctx->ev_comm);
     cudaStreamDestroy(ctx->stream);

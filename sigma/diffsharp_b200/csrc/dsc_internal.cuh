@@ -87,6 +87,8 @@ struct Ctx {
     size_t gemm_ws_bytes = 0;
     // NCCL
     void* nccl_comm = nullptr;
+    void* comm_stage = nullptr;    // contiguous staging buffer for packed all-reduces
+    size_t comm_stage_bytes = 0;
     int nranks = 1, rank = 0;
     dsc_stats stats{};
     int sm_count = kNumSMs;

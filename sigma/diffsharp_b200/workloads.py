@@ -107,17 +107,24 @@ def layers_fn(W1: DNDArray, b1: DVector, W2: DNDArray, b2: DVector):
     return f
 
 
-def jacobian_rows(W1, b1, W2, b2, x: DVector, col_start: int, col_count: int) -> DNDArray:
+def identity_rows(n: int, col_start: int, col_count: int, dtype=np.float64) -> DNDArray:
+    """Rows [col_start, col_start+col_count) of the n x n identity as a primal DM: the matrix tangent."""
+    T = np.zeros((col_count, n), dtype)
+    T[np.arange(col_count), col_start + np.arange(col_count)] = 1
+    return to_DM(T)
+
+
+def jacobian_rows(W1, b1, W2, b2, x: DVector, col_start: int, col_count: int, tangent: DNDArray | None = None) -> DNDArray:
     """Rows [col_start, col_start+col_count) of J^T, J = df/dx: ONE forward sweep whose tangent is a
     block of identity rows (same unchanged AD code, GEMM-bound instead of GEMV-bound).
     The faithful call sequence carries a row-replicated primal (RepeatReshapeCopy_V_MRows)."""
     backend = ad.Backend(W1)
     n = x.Length
     Xp = DNDArray.OfRows(col_count, x, backend)
-    T = np.zeros((col_count, n), x.dtype)
-    T[np.arange(col_count), col_start + np.arange(col_count)] = 1
-    primal, tangent = ad.jacobianv_(layers_fn(W1, b1, W2, b2), Xp, to_DM(T))
-    return tangent
+    if tangent is None:
+        tangent = identity_rows(n, col_start, col_count, x.dtype)
+    primal, tan = ad.jacobianv_(layers_fn(W1, b1, W2, b2), Xp, tangent)
+    return tan
 
 
 def jacobian_closed_form(W1, b1, W2, b2, x):

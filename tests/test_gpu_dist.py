@@ -1,0 +1,92 @@
+"""N > 1 on real GPUs: batch-row shards + ONE packed NCCL all-reduce of the adjoints reproduce the
+single-GPU gradient; tangent-row shards + all-gather reproduce the Jacobian.  Needs >= 2 GPUs
+(skipped on the 1-GPU box; the same host logic runs on CPU/gloo in test_dist_cpu.py)."""
+import ctypes as C
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpus():
+    try:
+        from sigma.diffsharp_b200 import _lib
+        n = C.c_int()
+        return n.value if _lib.lib.dsc_device_count(C.byref(n)) == 0 else 0
+    except Exception:
+        return 0
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from sigma.diffsharp_b200 import dist as D, workloads as wl
+    from sigma.diffsharp_b200.buffers import CudaDataBuffer
+    from sigma.diffsharp_b200.config import CudaBackendProvider, GlobalConfig
+    D.init_process_group()
+    prov = CudaBackendProvider(device=rank)
+    GlobalConfig.BackendProvider = prov
+    comm = D.NcclComm(prov.ctx)
+    layers, B = [96, 80, 64, 10], 300
+    r0, r1 = D.shard_range(B, rank, world)
+    X, Y, Ws, bs = wl.mlp_inputs(layers, B, row_range=(r0, r1))
+    L, dW, db = D.sharded_mlp_grad(comm, wl.to_DM(X), wl.to_DM(Y), [wl.to_DM(w) for w in Ws], [wl.to_DV(b) for b in bs])
+    comm.join()
+    grads = [a.ToArray().copy() for a in dW + db]
+    # config-4 shape in miniature: tangent rows sharded, all-gather at the end
+    n = 64
+    W1, b1, W2, b2, x = wl.jacobian_inputs(n)
+    c0, c1 = D.shard_range(n, rank, world)
+    J = wl.jacobian_rows(wl.to_DM(W1), wl.to_DV(b1), wl.to_DM(W2), wl.to_DV(b2), wl.to_DV(x), c0, c1 - c0)
+    full = CudaDataBuffer.empty(prov.ctx, np.float64, n * n)
+    comm.allgather(J.Buffer.DataBuffer, full)
+    comm.join()
+    Jfull = full.SubData.reshape(n, n)
+    if rank == 0:
+        out.put((float(L), grads, Jfull))
+    D.barrier()
+    comm.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs")
+def test_two_gpu_sharded_gradient_and_jacobian():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    L0, grads, Jfull = q.get()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    from oracle.backend import OracleBackend
+    from sigma.diffsharp_b200 import workloads as wl
+    from sigma.diffsharp_b200.config import DictBackendProvider, GlobalConfig
+    old = GlobalConfig.BackendProvider
+    GlobalConfig.BackendProvider = DictBackendProvider(OracleBackend(np.float32), OracleBackend(np.float64))
+    try:
+        X, Y, Ws, bs = wl.mlp_inputs([96, 80, 64, 10], 300)
+        L, dW, db = wl.mlp_grad(wl.to_DM(X), wl.to_DM(Y), [wl.to_DM(w) for w in Ws], [wl.to_DV(b) for b in bs])
+        for g, a in zip(grads, dW + db):
+            ref = a.ToArray()
+            assert np.abs(g - ref).max() <= 1e-5 * np.abs(ref).max()
+        W1, b1, W2, b2, x = wl.jacobian_inputs(64)
+        ref = wl.jacobian_closed_form(W1, b1, W2, b2, x)
+        assert np.abs(Jfull - ref).max() <= 1e-12 * np.abs(ref).max()
+    finally:
+        GlobalConfig.BackendProvider = old
