@@ -114,6 +114,9 @@ _sig("dsc_event_create", ctx_t, P(C.c_uint64))
 _sig("dsc_event_record", ctx_t, C.c_uint64)
 _sig("dsc_event_elapsed_ms", ctx_t, C.c_uint64, C.c_uint64, P(C.c_float))
 _sig("dsc_event_destroy", ctx_t, C.c_uint64)
+_sig("dsc_event_record_copy", ctx_t, C.c_uint64)
+_sig("dsc_event_sync", ctx_t, C.c_uint64)
+_sig("dsc_compute_wait_event", ctx_t, C.c_uint64)
 _sig("dsc_graph_begin", ctx_t)
 _sig("dsc_graph_end", ctx_t, P(C.c_uint64))
 _sig("dsc_graph_launch", ctx_t, C.c_uint64)
@@ -127,6 +130,11 @@ _sig("dsc_buf_download", buf_t, i32, C.c_void_p, i32)
 _sig("dsc_buf_upload_async", buf_t, i32, C.c_void_p, i32)
 _sig("dsc_buf_download_async", buf_t, i32, C.c_void_p, i32)
 _sig("dsc_buf_fill", buf_t, i32, i32, C.c_double)
+_sig("dsc_copy_upload", buf_t, i32, C.c_void_p, i32)
+_sig("dsc_copy_download", buf_t, i32, C.c_void_p, i32)
+_sig("dsc_copy_wait_compute", ctx_t)
+_sig("dsc_compute_wait_copy", ctx_t)
+_sig("dsc_copy_sync", ctx_t)
 _sig("dsc_buf_view", buf_t, i32, i32, P(buf_t))
 _sig("dsc_buf_copy", buf_t, P(buf_t))
 _sig("dsc_buf_share", buf_t, P(buf_t))

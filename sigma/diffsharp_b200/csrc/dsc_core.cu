@@ -287,6 +287,9 @@ int dsc_create(int device, uint32_t flags, dsc_ctx_t* out) {
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     DSC_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     DSC_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    DSC_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    DSC_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_copy_a, cudaEventDisableTiming));
+    DSC_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_copy_b, cudaEventDisableTiming));
     DSC_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming));
     DSC_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
     DSC_CUDA_CHECK(cudaMallocHost(&ctx->red_host, 256));
@@ -304,6 +307,10 @@ int dsc_destroy(dsc_ctx_t c) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->comm_stream);
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaEventDestroy(ctx->ev_copy_a);
+    cudaEventDestroy(ctx->ev_copy_b);
+    cudaStreamDestroy(ctx->copy_stream);
     if (ctx->nccl_comm) dsc_comm_destroy(c);
     for (auto& kv : ctx->pool.free_blocks) cudaFree(kv.second);
     ctx->pool.free_blocks.clear();
@@ -384,6 +391,23 @@ int dsc_event_elapsed_ms(dsc_ctx_t c, dsc_event_t a, dsc_event_t b, float* ms) {
 int dsc_event_destroy(dsc_ctx_t c, dsc_event_t ev) {
     if (!ctx_ok(c) || !ev) return fail(DSC_E_INVALID, "bad context or event");
     DSC_CUDA_CHECK(cudaEventDestroy(reinterpret_cast<cudaEvent_t>(ev)));
+    return DSC_OK;
+}
+
+int dsc_event_record_copy(dsc_ctx_t c, dsc_event_t ev) {
+    if (!ctx_ok(c) || !ev) return fail(DSC_E_INVALID, "bad context or event");
+    DSC_CUDA_CHECK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev), as_ctx(c)->copy_stream));
+    return DSC_OK;
+}
+int dsc_event_sync(dsc_ctx_t c, dsc_event_t ev) {
+    if (!ctx_ok(c) || !ev) return fail(DSC_E_INVALID, "bad context or event");
+    DSC_CUDA_CHECK(cudaEventSynchronize(reinterpret_cast<cudaEvent_t>(ev)));
+    return DSC_OK;
+}
+
+int dsc_compute_wait_event(dsc_ctx_t c, dsc_event_t ev) {
+    if (!ctx_ok(c) || !ev) return fail(DSC_E_INVALID, "bad context or event");
+    DSC_CUDA_CHECK(cudaStreamWaitEvent(as_ctx(c)->stream, reinterpret_cast<cudaEvent_t>(ev), 0));
     return DSC_OK;
 }
 
@@ -587,6 +611,59 @@ int dsc_buf_download_async(dsc_buf_t h, int32_t off, void* host, int32_t n) {
     const char* src = reinterpret_cast<const char*>(b->block->ptr) + (b->off + off) * es;
     DSC_CUDA_CHECK(cudaMemcpyAsync(host, src, (size_t)n * es, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->stats.memcpy_d2h_bytes += (size_t)n * es;
+    return DSC_OK;
+}
+
+int dsc_copy_upload(dsc_buf_t h, int32_t off, const void* host, int32_t n) {
+    Buf* b = as_buf(h);
+    if (!b) return fail(DSC_E_INVALID, "copy_upload: bad handle");
+    DSC_TRY(check_range(b, off, n, "copy_upload"));
+    if (n == 0) return DSC_OK;
+    if (!host) return fail(DSC_E_INVALID, "copy_upload: null host pointer");
+    Ctx* ctx = b->ctx;
+    if (ctx->capturing) return fail(DSC_E_INVALID, "copy-stream transfers cannot be captured");
+    size_t es = dtype_size(b->dtype);
+    char* dst = reinterpret_cast<char*>(b->block->ptr) + (b->off + off) * es;
+    DSC_CUDA_CHECK(cudaMemcpyAsync(dst, host, (size_t)n * es, cudaMemcpyHostToDevice, ctx->copy_stream));
+    ctx->stats.memcpy_h2d_bytes += (size_t)n * es;
+    return DSC_OK;
+}
+
+int dsc_copy_download(dsc_buf_t h, int32_t off, void* host, int32_t n) {
+    Buf* b = as_buf(h);
+    if (!b) return fail(DSC_E_INVALID, "copy_download: bad handle");
+    DSC_TRY(check_range(b, off, n, "copy_download"));
+    if (n == 0) return DSC_OK;
+    if (!host) return fail(DSC_E_INVALID, "copy_download: null host pointer");
+    Ctx* ctx = b->ctx;
+    if (ctx->capturing) return fail(DSC_E_INVALID, "copy-stream transfers cannot be captured");
+    size_t es = dtype_size(b->dtype);
+    const char* src = reinterpret_cast<const char*>(b->block->ptr) + (b->off + off) * es;
+    DSC_CUDA_CHECK(cudaMemcpyAsync(host, src, (size_t)n * es, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    ctx->stats.memcpy_d2h_bytes += (size_t)n * es;
+    return DSC_OK;
+}
+
+int dsc_copy_wait_compute(dsc_ctx_t c) {
+    if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
+    Ctx* ctx = as_ctx(c);
+    DSC_TRY(dsc_comm_join(c));
+    DSC_CUDA_CHECK(cudaEventRecord(ctx->ev_copy_a, ctx->stream));
+    DSC_CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy_a, 0));
+    return DSC_OK;
+}
+
+int dsc_compute_wait_copy(dsc_ctx_t c) {
+    if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
+    Ctx* ctx = as_ctx(c);
+    DSC_CUDA_CHECK(cudaEventRecord(ctx->ev_copy_b, ctx->copy_stream));
+    DSC_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_b, 0));
+    return DSC_OK;
+}
+
+int dsc_copy_sync(dsc_ctx_t c) {
+    if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
+    DSC_CUDA_CHECK(cudaStreamSynchronize(as_ctx(c)->copy_stream));
     return DSC_OK;
 }
 

@@ -66,6 +66,8 @@ struct Ctx {
     uint32_t flags = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t comm_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy_a = nullptr, ev_copy_b = nullptr;
     cudaEvent_t ev_compute = nullptr, ev_comm = nullptr;
     bool comm_pending = false;
     Pool pool;
