@@ -91,7 +91,15 @@ __global__ void gemv_t_stage2(const T* __restrict__ partial, const T* __restrict
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     T s = T(0);
-    for (int c = 0; c < chunks; ++c) s += partial[(size_t)c * n + j];
+    int c = 0;
+    for (; c + 8 <= chunks; c += 8) {  // 8 independent loads in flight, adds in slab order
+        T v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = partial[(size_t)(c + u) * n + j];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; c < chunks; ++c) s += partial[(size_t)c * n + j];
     out[j] = y ? s + y[j] : s;
 }
 
@@ -149,7 +157,7 @@ static int gemv_impl(dsc_ctx_t c, int trans, int32_t m, int32_t n, dsc_buf_t Ah,
     if (vec) gemv_t_stage1<T, W><<<grid, block, 0, ctx->stream>>>(A->ptr<T>(), x->ptr<T>(), partial, m, n, rows_per_chunk);
     else gemv_t_stage1<T, 1><<<grid, block, 0, ctx->stream>>>(A->ptr<T>(), x->ptr<T>(), partial, m, n, rows_per_chunk);
     DSC_LAUNCH_CHECK(ctx);
-    gemv_t_stage2<T><<<(n + 255) / 256, 256, 0, ctx->stream>>>(partial, yp, o->ptr<T>(), n, chunks);
+    gemv_t_stage2<T><<<(n + 63) / 64, 64, 0, ctx->stream>>>(partial, yp, o->ptr<T>(), n, chunks);
     DSC_LAUNCH_CHECK(ctx);
     return DSC_OK;
 }

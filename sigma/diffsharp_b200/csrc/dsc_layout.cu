@@ -210,7 +210,15 @@ __global__ void colsum_stage2(const T* __restrict__ partial, T* __restrict__ v, 
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     T s = T(0);
-    for (int c = 0; c < chunks; ++c) s += partial[(size_t)c * n + j];
+    int c = 0;
+    for (; c + 8 <= chunks; c += 8) {  // 8 independent loads in flight, adds in slab order
+        T v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = partial[(size_t)(c + u) * n + j];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; c < chunks; ++c) s += partial[(size_t)c * n + j];
     v[j] += s;
 }
 
@@ -235,7 +243,7 @@ int colsum_launch(Ctx* ctx, const T* M, T* v, int m, int n) {
     if (vec) colsum_stage1<T, W><<<grid, block, 0, ctx->stream>>>(M, partial, m, n, rows_per_chunk);
     else colsum_stage1<T, 1><<<grid, block, 0, ctx->stream>>>(M, partial, m, n, rows_per_chunk);
     DSC_LAUNCH_CHECK(ctx);
-    colsum_stage2<T><<<(n + 255) / 256, 256, 0, ctx->stream>>>(partial, v, n, chunks);
+    colsum_stage2<T><<<(n + 63) / 64, 64, 0, ctx->stream>>>(partial, v, n, chunks);
     DSC_LAUNCH_CHECK(ctx);
     return DSC_OK;
 }

@@ -127,7 +127,7 @@ def test_transpose_bit_exact_and_involutive(cuda_provider_nofuse, dtype, shape):
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("m,k,n", [(1, 1, 1), (5, 7, 3), (128, 784, 300), (128, 300, 10), (300, 128, 10), (257, 129, 65),
-                                   (512, 512, 512), (1024, 96, 2048), (64, 4096, 64), (2048, 512, 10), (512, 4100, 10), (777, 333, 16)])
+                                   (512, 512, 512), (1024, 96, 2048), (64, 4096, 64), (2048, 512, 10), (512, 4100, 10), (777, 333, 16), (2048, 10, 512), (300, 16, 4096), (129, 7, 1000)])
 def test_gemm_all_transposes_against_openblas(cuda_provider, dtype, m, k, n):
     """Mul_M_M and the transposed-operand forms of dsc_?gemm (what Transpose_M + Mul_M_M computes)."""
     import ctypes as C
