@@ -295,6 +295,8 @@ int dsc_create(int device, uint32_t flags, dsc_ctx_t* out) {
     DSC_CUDA_CHECK(cudaMallocHost(&ctx->red_host, 256));
     int s = ensure_red_scratch(ctx, 32u << 20);
     if (s != DSC_OK) return s;
+    DSC_CUDA_CHECK(cudaMalloc(&ctx->tickets, kNumTickets * sizeof(unsigned int)));
+    DSC_CUDA_CHECK(cudaMemsetAsync(ctx->tickets, 0, kNumTickets * sizeof(unsigned int), ctx->stream));
     *out = reinterpret_cast<dsc_ctx_t>(ctx);
     return DSC_OK;
 }
@@ -315,6 +317,7 @@ int dsc_destroy(dsc_ctx_t c) {
     for (auto& kv : ctx->pool.free_blocks) cudaFree(kv.second);
     ctx->pool.free_blocks.clear();
     if (ctx->red_scratch) cudaFree(ctx->red_scratch);
+    if (ctx->tickets) cudaFree(ctx->tickets);
     if (ctx->red_host) cudaFreeHost(ctx->red_host);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     if (ctx->gemm_ws) cudaFree(ctx->gemm_ws);

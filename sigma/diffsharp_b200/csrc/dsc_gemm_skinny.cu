@@ -147,6 +147,264 @@ __global__ void skinny_cols_stage2(const T* __restrict__ partial, const T* __res
     }
 }
 
+// ================================================================================================
+// 128-bit paths (the ones the MLP's output layer takes; the scalar kernels above stay as the generic
+// fallback for unaligned windows / K or M not a multiple of the vector width)
+// ================================================================================================
+template <typename T> struct V16;
+template <> struct V16<float> { using type = float4; static constexpr int W = 4; };
+template <> struct V16<double> { using type = double2; static constexpr int W = 2; };
+__device__ __forceinline__ float vget(const float4& v, int i) { return (&v.x)[i]; }
+__device__ __forceinline__ double vget(const double2& v, int i) { return (&v.x)[i]; }
+
+// Sum 16 per-lane values over the 32 lanes of a warp with 16 shuffles (instead of 16 x 5): at every
+// step a lane keeps one half of its values and sends the other half to its partner.  On return
+// v[0] of lane l is the total of value index 8*b4 + 4*b3 + 2*b2 + b1 (b_i = bit i of l); the
+// combine order is fixed, so the result is deterministic.
+template <typename T>
+__device__ __forceinline__ void warp_sum16(T (&v)[16], int lane) {
+#pragma unroll
+    for (int s = 8; s >= 1; s >>= 1) {
+        const bool up = (lane & (2 * s)) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const T send = up ? v[i] : v[i + s];
+            const T keep = up ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * s);
+        }
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// ---- A has K contiguous (ta = 0), 128-bit loads ------------------------------------------------
+// One warp owns RPW output rows; lane l reads the 16-byte vectors q = it*32 + l of each row (8 per
+// K chunk, all issued before the first FMA), B^T sits in shared memory as Bs[j][kk] so the same lane
+// reads the matching 16 bytes of every B column without bank conflicts.  NJ = n rounded up to 4.
+template <typename T, int RPW, int NJ>
+__global__ void __launch_bounds__(256, 2) skinny_rows_vec_kernel(const T* __restrict__ A, const T* __restrict__ B, const T* __restrict__ bias,
+                                                                  T* __restrict__ C, int m, int n, int k, int tb) {
+    using V = typename V16<T>::type;
+    constexpr int W = V16<T>::W;
+    constexpr int ITS = 8;
+    constexpr int KC = 32 * W * ITS;  // 1024 floats / 512 doubles per chunk
+    constexpr int KCP = KC + W;       // +16 bytes per row
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* Bs = reinterpret_cast<T*>(smem_raw);  // [NJ][KCP]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles = (m + 8 * RPW - 1) / (8 * RPW);
+    const bool single = k <= KC;
+    auto stage = [&](int k0, int kc) {
+        for (int kk = threadIdx.x; kk < KC; kk += 256) {
+            if (kk < kc) {
+                if (tb) {
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) Bs[j * KCP + kk] = j < n ? B[(size_t)j * k + k0 + kk] : T(0);
+                } else {
+                    const T* src = B + (size_t)(k0 + kk) * n;
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) Bs[j * KCP + kk] = j < n ? src[j] : T(0);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) Bs[j * KCP + kk] = T(0);
+            }
+        }
+        __syncthreads();
+    };
+    if (single) stage(0, k);
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int row0 = (tile * 8 + warp) * RPW;
+        T acc[RPW][NJ];
+#pragma unroll
+        for (int r = 0; r < RPW; ++r)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) acc[r][j] = T(0);
+        for (int k0 = 0; k0 < k; k0 += KC) {
+            const int kc = min(KC, k - k0);
+            if (!single) {
+                __syncthreads();  // every warp is done with the previous chunk of B
+                stage(k0, kc);
+            }
+            V av[ITS][RPW];
+#pragma unroll
+            for (int it = 0; it < ITS; ++it) {
+                const int q = it * 32 + lane;
+#pragma unroll
+                for (int r = 0; r < RPW; ++r) {
+                    const T* arow = A + (size_t)min(row0 + r, m - 1) * k + k0;  // clamped rows are discarded at the store
+                    if (q * W < kc) av[it][r] = *reinterpret_cast<const V*>(arow + q * W);
+                    else {
+#pragma unroll
+                        for (int l = 0; l < W; ++l) (&av[it][r].x)[l] = T(0);
+                    }
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < ITS; ++it) {
+                const int q = it * 32 + lane;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const V bv = *reinterpret_cast<const V*>(Bs + j * KCP + q * W);
+#pragma unroll
+                    for (int r = 0; r < RPW; ++r)
+#pragma unroll
+                        for (int l = 0; l < W; ++l) acc[r][j] = fma(vget(av[it][r], l), vget(bv, l), acc[r][j]);
+                }
+            }
+        }
+        const int j_out = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+            T v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = j < NJ ? acc[r][j < NJ ? j : 0] : T(0);
+            warp_sum16(v, lane);
+            const int row = row0 + r;
+            if (!(lane & 1) && j_out < n && row < m) C[(size_t)row * n + j_out] = v[0] + (bias ? bias[row] : T(0));
+        }
+    }
+}
+
+// ---- A has M contiguous (ta = 1, stored k x m), 128-bit loads -----------------------------------
+// grid (ceil(m / 32), chunks).  A CTA owns 32 output rows (= 32 columns of the stored A, one
+// 128-byte segment per k-row) and one K chunk.  Warp w, lane l: column vector l / W (W adjacent
+// output rows) and k-lane w*W + l % W of 8W, so the CTA walks 8W k-rows per step.  After the K loop
+// the W k-lanes of a warp are combined with shuffles (lane ends up with one output row), the 8 warps
+// through shared memory in warp order, and the CTA writes one partial per chunk.  Chunks are then
+// summed in two fixed levels by whichever CTA arrives last (groups of 8 chunks, then the groups):
+// one launch, and the summation order does not depend on the arrival order.
+template <typename T, int NJ>
+__global__ void __launch_bounds__(256) skinny_cols_vec_kernel(const T* __restrict__ A, const T* __restrict__ B, const T* __restrict__ bias,
+                                                               T* __restrict__ partial, T* __restrict__ partial2, T* __restrict__ C,
+                                                               unsigned int* __restrict__ tickets, int m, int n, int k, int tb, int rows_per_chunk) {
+    using V = typename V16<T>::type;
+    constexpr int W = V16<T>::W;
+    constexpr int COLS = 32;
+    constexpr int KL = 8 * W;   // k-lanes per CTA
+    constexpr int KCH = 256;    // k-rows of B staged per pass
+    constexpr int GROUP = 8;
+    // the B chunk and the cross-warp reduction buffer share storage (B is dead after the K loop)
+    constexpr int kBsElems = KCH * NJ, kRedElems = 8 * COLS * (NJ + 1);
+    __shared__ __align__(16) T smem_u[kBsElems > kRedElems ? kBsElems : kRedElems];
+    T (*Bs)[NJ] = reinterpret_cast<T (*)[NJ]>(smem_u);
+    T (*red)[COLS][NJ + 1] = reinterpret_cast<T (*)[COLS][NJ + 1]>(smem_u);
+    __shared__ int s_last;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int klo = lane % W, cv = lane / W;
+    const int kl = warp * W + klo;
+    const int col0 = blockIdx.x * COLS + cv * W;
+    const int chunks = gridDim.y;
+    const int kbeg = blockIdx.y * rows_per_chunk, kend = min(k, kbeg + rows_per_chunk);
+    T acc[W][NJ];
+#pragma unroll
+    for (int c = 0; c < W; ++c)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[c][j] = T(0);
+    for (int k0 = kbeg; k0 < kend; k0 += KCH) {
+        const int kc = min(KCH, kend - k0);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < KCH * NJ; idx += 256) {
+            const int kk = idx / NJ, j = idx % NJ;
+            Bs[kk][j] = (kk < kc && j < n) ? ldB(B, tb, k, n, k0 + kk, j) : T(0);
+        }
+        __syncthreads();
+        if (col0 < m) {  // m % W == 0: a column vector is entirely inside or outside
+            const T* a = A + (size_t)k0 * m + col0;
+#pragma unroll 4
+            for (int kk = kl; kk < kc; kk += KL) {
+                const V av = *reinterpret_cast<const V*>(a + (size_t)kk * m);
+#pragma unroll
+                for (int j = 0; j < NJ; j += W) {
+                    const V bv = *reinterpret_cast<const V*>(&Bs[kk][j]);
+#pragma unroll
+                    for (int c = 0; c < W; ++c)
+#pragma unroll
+                        for (int l = 0; l < W; ++l) acc[c][j + l] = fma(vget(av, c), vget(bv, l), acc[c][j + l]);
+                }
+            }
+        }
+    }
+    // combine the W k-lanes of the warp: lane klo keeps output row col0 + klo
+#pragma unroll
+    for (int s = W / 2; s >= 1; s >>= 1) {
+        const bool up = (klo & s) != 0;
+#pragma unroll
+        for (int c = 0; c < s; ++c)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const T send = up ? acc[c][j] : acc[c + s][j];
+                const T keep = up ? acc[c + s][j] : acc[c][j];
+                acc[c][j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+            }
+    }
+    // combine the 8 warps in warp order
+    __syncthreads();  // every warp is done reading Bs
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) red[warp][cv * W + klo][j] = acc[0][j];
+    __syncthreads();
+    const int blk_cols = min(COLS, m - blockIdx.x * COLS);
+    const int E = blk_cols * n;  // this CTA's outputs are contiguous in C and in every partial plane
+    const size_t blk_off = (size_t)blockIdx.x * COLS * n;
+    T* my_out = chunks == 1 ? C + blk_off : partial + (size_t)blockIdx.y * m * n + blk_off;
+    for (int e = threadIdx.x; e < E; e += 256) {
+        const int c = e / n, j = e % n;
+        T s = red[0][c][j];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) s += red[w][c][j];
+        if (chunks == 1 && bias) s += bias[blockIdx.x * COLS + c];
+        my_out[e] = s;
+    }
+    if (chunks == 1) return;
+    // ---- level 1: the last CTA of a group of 8 chunks adds the group's partials in chunk order ----
+    const int ngroups = (chunks + GROUP - 1) / GROUP;
+    const int g = blockIdx.y / GROUP;
+    const int g_first = g * GROUP, g_size = min(GROUP, chunks - g_first);
+    unsigned int* tk = tickets + blockIdx.x * (ngroups + 1);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&tk[g], 1u) == (unsigned)g_size - 1u);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    {
+        T* dst = ngroups == 1 ? C + blk_off : partial2 + (size_t)g * m * n + blk_off;
+        for (int e = threadIdx.x; e < E; e += 256) {
+            T v[GROUP];
+#pragma unroll
+            for (int c = 0; c < GROUP; ++c) v[c] = c < g_size ? __ldcg(partial + (size_t)(g_first + c) * m * n + blk_off + e) : T(0);
+            T s = v[0];
+#pragma unroll
+            for (int c = 1; c < GROUP; ++c) s += v[c];
+            if (ngroups == 1 && bias) s += bias[blockIdx.x * COLS + e / n];
+            dst[e] = s;
+        }
+    }
+    if (threadIdx.x == 0) tk[g] = 0;
+    if (ngroups == 1) return;
+    // ---- level 2: the last group adds the group sums in group order ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&tk[ngroups], 1u) == (unsigned)ngroups - 1u);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int e = threadIdx.x; e < E; e += 256) {
+        T s = T(0);
+        int c = 0;
+        for (; c + 8 <= ngroups; c += 8) {
+            T v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(partial2 + (size_t)(c + u) * m * n + blk_off + e);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
+        for (; c < ngroups; ++c) s += __ldcg(partial2 + (size_t)c * m * n + blk_off + e);
+        if (bias) s += bias[blockIdx.x * COLS + e / n];
+        C[blk_off + e] = s;
+    }
+    if (threadIdx.x == 0) tk[ngroups] = 0;
+}
+
 // ---- tiny K (k <= NMAX): C(m x n) = A(m x k) op(B)(k x n), output-write bound -----------------
 // (the input adjoint of the output layer: dZ (B x 10) * W3^T (10 x 1024)).  A thread keeps the k
 // B-values of its 4 (2 for double) output columns in registers and walks the rows of its CTA's slab.
@@ -201,6 +459,71 @@ __global__ void __launch_bounds__(256) tiny_k_kernel(const T* __restrict__ A, co
 
 }  // namespace skinny
 
+template <typename T, int RPW, int NJ>
+static int launch_rows_vec_inst(Ctx* ctx, int m, int n, int k, int tb, const T* A, const T* B, const T* bias, T* C) {
+    using namespace skinny;
+    constexpr int W = 16 / (int)sizeof(T);
+    constexpr int KCP = 32 * W * 8 + W;
+    const int smem = NJ * KCP * (int)sizeof(T);
+    static bool attr_set = false;
+    if (!attr_set) {
+        DSC_CUDA_CHECK(cudaFuncSetAttribute(skinny_rows_vec_kernel<T, RPW, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    const int tiles = (m + 8 * RPW - 1) / (8 * RPW);
+    const int grid = tiles < ctx->sm_count * 2 ? tiles : ctx->sm_count * 2;
+    skinny_rows_vec_kernel<T, RPW, NJ><<<grid, 256, smem, ctx->stream>>>(A, B, bias, C, m, n, k, tb);
+    DSC_LAUNCH_CHECK(ctx);
+    return DSC_OK;
+}
+
+template <typename T, int RPW>
+static int launch_rows_vec_nj(Ctx* ctx, int m, int n, int k, int tb, const T* A, const T* B, const T* bias, T* C) {
+    if (n <= 4) return launch_rows_vec_inst<T, RPW, 4>(ctx, m, n, k, tb, A, B, bias, C);
+    if (n <= 8) return launch_rows_vec_inst<T, RPW, 8>(ctx, m, n, k, tb, A, B, bias, C);
+    if (n <= 12) return launch_rows_vec_inst<T, RPW, 12>(ctx, m, n, k, tb, A, B, bias, C);
+    return launch_rows_vec_inst<T, RPW, 16>(ctx, m, n, k, tb, A, B, bias, C);
+}
+
+template <typename T>
+static int launch_rows_vec(Ctx* ctx, int m, int n, int k, int tb, const T* A, const T* B, const T* bias, T* C) {
+    // two rows per warp once that still leaves >= 2 CTAs per SM (B^T is staged once per CTA)
+    if (m >= ctx->sm_count * 2 * 16) return launch_rows_vec_nj<T, 2>(ctx, m, n, k, tb, A, B, bias, C);
+    return launch_rows_vec_nj<T, 1>(ctx, m, n, k, tb, A, B, bias, C);
+}
+
+template <typename T, int NJ>
+static int launch_cols_vec_inst(Ctx* ctx, int m, int n, int k, int tb, const T* A, const T* B, const T* bias, T* C) {
+    using namespace skinny;
+    constexpr int W = 16 / (int)sizeof(T);
+    const int gx = (m + 31) / 32;
+    // ~2 CTAs per SM; every k-lane (8W per CTA) gets at least 4 k-rows
+    int chunks = (ctx->sm_count * 2 + gx - 1) / gx;
+    const int max_chunks = (k + 32 * W - 1) / (32 * W);
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    int rows_per_chunk = (k + chunks - 1) / chunks;
+    chunks = (k + rows_per_chunk - 1) / rows_per_chunk;
+    const int ngroups = (chunks + 7) / 8;
+    if ((long)gx * (ngroups + 1) > kNumTickets) return 1;  // caller falls back to the two-stage kernels
+    const size_t p1 = (size_t)chunks * m * n * sizeof(T), p2 = (size_t)ngroups * m * n * sizeof(T);
+    DSC_TRY(ensure_red_scratch(ctx, 256 + p1 + p2 + 32));
+    char* base = reinterpret_cast<char*>(ctx->red_scratch) + 256;
+    T* partial = reinterpret_cast<T*>(base);
+    T* partial2 = reinterpret_cast<T*>(base + ((p1 + 15) & ~size_t(15)));
+    skinny_cols_vec_kernel<T, NJ><<<dim3(gx, chunks), 256, 0, ctx->stream>>>(A, B, bias, partial, partial2, C, ctx->tickets, m, n, k, tb, rows_per_chunk);
+    DSC_LAUNCH_CHECK(ctx);
+    return DSC_OK;
+}
+
+template <typename T>
+static int launch_cols_vec(Ctx* ctx, int m, int n, int k, int tb, const T* A, const T* B, const T* bias, T* C) {
+    if (n <= 4) return launch_cols_vec_inst<T, 4>(ctx, m, n, k, tb, A, B, bias, C);
+    if (n <= 8) return launch_cols_vec_inst<T, 8>(ctx, m, n, k, tb, A, B, bias, C);
+    if (n <= 12) return launch_cols_vec_inst<T, 12>(ctx, m, n, k, tb, A, B, bias, C);
+    return launch_cols_vec_inst<T, 16>(ctx, m, n, k, tb, A, B, bias, C);
+}
+
 // returns DSC_OK when handled, 1 when the shape is not a skinny / tiny-K product
 template <typename T>
 int gemm_skinny(Ctx* ctx, int ta, int tb, int m, int n, int k, const T* A, const T* B, const T* bias, T* C) {
@@ -210,7 +533,7 @@ int gemm_skinny(Ctx* ctx, int ta, int tb, int m, int n, int k, const T* A, const
         const int gx = (n + 256 * W - 1) / (256 * W);
         int gy = (ctx->sm_count * 4 + gx - 1) / gx;
         int rows_per_cta = (m + gy - 1) / gy;
-        rows_per_cta = (rows_per_cta + 63) / 64 * 64;
+        rows_per_cta = (rows_per_cta + 15) / 16 * 16;
         gy = (m + rows_per_cta - 1) / rows_per_cta;
         tiny_k_kernel<T><<<dim3(gx, gy), 256, 0, ctx->stream>>>(A, B, bias, C, m, n, k, ta, tb, rows_per_cta);
         DSC_LAUNCH_CHECK(ctx);
@@ -218,7 +541,14 @@ int gemm_skinny(Ctx* ctx, int ta, int tb, int m, int n, int k, const T* A, const
         return DSC_OK;
     }
     if (n > NMAX || (long)m * k < 65536) return 1;
-    if (!ta) {
+    constexpr int W = 16 / (int)sizeof(T);
+    const bool a16 = (reinterpret_cast<uintptr_t>(A) & 15) == 0;
+    int vec_cols = 1;
+    if (!ta && a16 && k % W == 0) {
+        DSC_TRY((launch_rows_vec<T>(ctx, m, n, k, tb, A, B, bias, C)));
+    } else if (ta && a16 && m % W == 0 && (vec_cols = launch_cols_vec<T>(ctx, m, n, k, tb, A, B, bias, C)) != 1) {
+        if (vec_cols != DSC_OK) return vec_cols;
+    } else if (!ta) {
         constexpr int KC = sizeof(T) == 4 ? 1024 : 512;
         constexpr int RPW = 4;
         const int smem = NMAX * KC * (int)sizeof(T);

@@ -5,24 +5,28 @@
 //   C(m x n) = op(A) op(B) [+ bias[i]]        Mul_M_M / Mul_M_M_Add_V_MCols (Backend.fs:119,121)
 //
 // Two launches per GEMM:
-//  (1) split pre-pass (HBM-bound): every operand is rounded to TF32 (hi = rna_tf32(x)) and its
-//      residual again (lo = rna_tf32(x - hi), x - hi is exact in fp32), and written as two K-MAJOR
-//      planes [rows x Kp] (Kp = K rounded up to 32, zero padded).  The pre-pass also normalises the
-//      layout: an operand whose K index is not contiguous (B of an NN product, A of a TN product) is
-//      transposed through shared memory on the way, so the tensor-core kernel only ever sees K-major
-//      SWIZZLE_128B tiles.  A lazily transposed operand (Transpose_M feeding Mul_M_M,
-//      AD.Float32.fs:4127-4143) therefore costs nothing extra.
-//  (2) persistent warp-specialised kernel, one CTA per SM, 192 threads:
-//        warp 0    TMA producer: 4 tile loads per k-block (A_hi, A_lo, B_hi, B_lo) into a
-//                  STAGES-deep shared-memory ring, completion on a `full` mbarrier (expect_tx)
+//  (1) split pre-pass (HBM-bound, one launch for both operands).  kind::tf32 reads fp32 words from
+//      shared memory and IGNORES the low 13 mantissa bits, so the "hi" operand needs no plane of its
+//      own: the tensor core is pointed at the source buffer and sees hi = trunc_tf32(x).  The pre-pass
+//      only writes lo = rna_tf32(x - trunc_tf32(x)) (x - hi is exact in fp32), in the SAME layout as
+//      the source — 4 bytes read + 4 written per element instead of 4 + 8, and no transposes: an
+//      operand whose K index is not contiguous (B of an NN product, A of a TN product — every weight
+//      adjoint GEMM, AD.Float32.fs:4127-4143) is fed to the tensor core as an MN-major tile.
+//      Operands TMA cannot address directly (window not 16-byte aligned, contiguous extent not a
+//      multiple of 4) take the general route: hi and lo are both written as zero-padded K-major
+//      planes [rows x Kp], transposed through shared memory on the way if needed.
+//  (2) persistent warp-specialised kernel, one CTA per SM, 320 threads:
+//        warp 0    TMA producer: per k-block the hi and lo tiles of A and B into a STAGES-deep
+//                  shared-memory ring (K-major operand: one 32 x rows box per plane; MN-major operand:
+//                  one 32(MN) x 32(K) box per 32-wide MN block), completion on a `full` mbarrier
 //        warp 1    allocates TMEM and issues tcgen05.mma from one thread: per 8-wide k-slice
 //                  D += A_lo*B_hi; D += A_hi*B_lo; D += A_hi*B_hi  (128 x BN fp32 accumulator in
 //                  TMEM); tcgen05.commit releases the smem stage (`empty`) and, after the last
-//                  k-block, publishes the accumulator (`tmem_full`)
-//        warps 2-5 epilogue: tcgen05.ld the accumulator (each warp owns the 32 TMEM lanes of its
-//                  quadrant), add the bias, predicated float4 stores to C, then hand the
-//                  accumulator stage back (`tmem_empty`).  Two accumulator stages (2 x BN TMEM
-//                  columns) let the epilogue of tile i overlap the main loop of tile i+1.
+//                  k-block of a chunk, publishes the accumulator (`tmem_full`)
+//        warps 2-9 epilogue: tcgen05.ld the accumulator (each warp owns the 32 TMEM lanes of its
+//                  quadrant and half of the columns), add the chunk into registers, and after the
+//                  last chunk add the bias and store float4s to C.  Two accumulator stages (2 x BN
+//                  TMEM columns) let the drain of chunk c overlap the MMAs of chunk c+1.
 // The a_lo*b_lo term (<= 2^-22 relative) is dropped: that is the "3x" in 3xTF32.
 //
 // Accuracy of long reductions.  The tensor core's fp32 accumulator TRUNCATES on every accumulate
@@ -37,6 +41,7 @@
 // the chunks of one tile are dealt to `splits` CTAs; each writes an fp32 partial tile and a second
 // kernel adds the partials in split order (deterministic) and applies the bias.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "dsc_internal.cuh"
 
@@ -141,8 +146,25 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     return d;
 }
 
-// Instruction descriptor, kind::tf32: D = F32 (bits 4-5 = 1), A/B = TF32 (bits 7-9, 10-12 = 2), both
-// K-major (bits 15,16 = 0), N >> 3 in bits [17,23), M >> 4 in bits [24,29).
+// MN-major tile of a 32-bit operand: [MN/32 blocks][32 k-rows][32 floats]; a k-row of a block is
+// 128 B (32 MN-contiguous elements).  For 32-bit MN-major operands the tensor core accepts one
+// layout only, SWIZZLE_128B_BASE32B (descriptor layout type 1; TMA: SWIZZLE_128B_ATOM_32B): 32-byte
+// chunks of a 128-byte row are XOR-ed with (row % 4), so the swizzle atom is 4 k-rows = 512 B.
+// Canonical form ((4,8,m),(4,k)):((1,4,LBO),(32,SBO)) in elements: LBO = distance between 32-wide
+// MN blocks (32 k-rows x 128 B = 4096 B), SBO = distance between 4-row k groups (512 B).
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(4096 >> 4) << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;
+    return d;
+}
+
+// Instruction descriptor, kind::tf32: D = F32 (bits 4-5 = 1), A/B = TF32 (bits 7-9, 10-12 = 2),
+// A / B major-ness in bits 15 / 16 (0 = K-major, 1 = MN-major), N >> 3 in bits [17,23), M >> 4 in
+// bits [24,29).
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -154,6 +176,7 @@ struct Params {
     float* C;                  // splits == 1: the result; splits > 1: partial planes [splits][m][n]
     const float* bias;         // applied here only when splits == 1
     int vec4;                  // output rows are 16-byte aligned and n % 4 == 0
+    int a_mn, b_mn;            // operand tiles are MN-major (source read in place, K index strided)
 };
 
 template <int BN>
@@ -214,10 +237,26 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     const uint32_t st = smem_base + s * cfg::kStageBytes;
                     mbar_expect_tx(full_bar(s), cfg::kStageBytes);
-                    tma_load_2d(st, &map_ahi, full_bar(s), kb * BK, m0);
-                    tma_load_2d(st + kAPlaneBytes, &map_alo, full_bar(s), kb * BK, m0);
-                    tma_load_2d(st + 2 * kAPlaneBytes, &map_bhi, full_bar(s), kb * BK, n0);
-                    tma_load_2d(st + 2 * kAPlaneBytes + cfg::kBPlaneBytes, &map_blo, full_bar(s), kb * BK, n0);
+                    if (!p.a_mn) {
+                        tma_load_2d(st, &map_ahi, full_bar(s), kb * BK, m0);
+                        tma_load_2d(st + kAPlaneBytes, &map_alo, full_bar(s), kb * BK, m0);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BM / 32; ++i) {
+                            tma_load_2d(st + i * 4096, &map_ahi, full_bar(s), m0 + 32 * i, kb * BK);
+                            tma_load_2d(st + kAPlaneBytes + i * 4096, &map_alo, full_bar(s), m0 + 32 * i, kb * BK);
+                        }
+                    }
+                    if (!p.b_mn) {
+                        tma_load_2d(st + 2 * kAPlaneBytes, &map_bhi, full_bar(s), kb * BK, n0);
+                        tma_load_2d(st + 2 * kAPlaneBytes + cfg::kBPlaneBytes, &map_blo, full_bar(s), kb * BK, n0);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BN / 32; ++i) {
+                            tma_load_2d(st + 2 * kAPlaneBytes + i * 4096, &map_bhi, full_bar(s), n0 + 32 * i, kb * BK);
+                            tma_load_2d(st + 2 * kAPlaneBytes + cfg::kBPlaneBytes + i * 4096, &map_blo, full_bar(s), n0 + 32 * i, kb * BK);
+                        }
+                    }
                     if (++s == cfg::kStages) { s = 0; ph ^= 1u; }
                 }
             }
@@ -225,7 +264,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+            const uint32_t idesc = make_idesc_tf32(BM, BN) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16);
+            // per 8-wide k-slice the descriptor start address moves by 32 B inside the swizzle row
+            // (K-major) or by one 1024-byte group of 8 k-rows (MN-major); units of 16 B
+            const uint64_t a_adv = p.a_mn ? 64u : 2u, b_adv = p.b_mn ? 64u : 2u;
             int s = 0, as = 0;
             uint32_t ph = 0, aph = 0;
             for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
@@ -241,17 +283,17 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                         mbar_wait(full_bar(s), ph);        // TMA bytes have landed
                         tcgen05_fence_after();
                         const uint32_t st = smem_base + s * cfg::kStageBytes;
-                        const uint64_t ahi = make_kmajor_sw128_desc(st);
-                        const uint64_t alo = make_kmajor_sw128_desc(st + kAPlaneBytes);
-                        const uint64_t bhi = make_kmajor_sw128_desc(st + 2 * kAPlaneBytes);
-                        const uint64_t blo = make_kmajor_sw128_desc(st + 2 * kAPlaneBytes + cfg::kBPlaneBytes);
+                        const uint64_t ahi = p.a_mn ? make_mnmajor_sw128_desc(st) : make_kmajor_sw128_desc(st);
+                        const uint64_t alo = p.a_mn ? make_mnmajor_sw128_desc(st + kAPlaneBytes) : make_kmajor_sw128_desc(st + kAPlaneBytes);
+                        const uint64_t bhi = p.b_mn ? make_mnmajor_sw128_desc(st + 2 * kAPlaneBytes) : make_kmajor_sw128_desc(st + 2 * kAPlaneBytes);
+                        const uint64_t blo = p.b_mn ? make_mnmajor_sw128_desc(st + 2 * kAPlaneBytes + cfg::kBPlaneBytes)
+                                                    : make_kmajor_sw128_desc(st + 2 * kAPlaneBytes + cfg::kBPlaneBytes);
 #pragma unroll
                         for (int k = 0; k < BK / 8; ++k) {
-                            // advance 8 floats = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-                            const uint64_t adv = (uint64_t)(k * 2);
-                            umma_tf32(d_tmem, alo + adv, bhi + adv, idesc, (uint32_t)((kb != c0) | (k != 0)));
-                            umma_tf32(d_tmem, ahi + adv, blo + adv, idesc, 1u);
-                            umma_tf32(d_tmem, ahi + adv, bhi + adv, idesc, 1u);
+                            const uint64_t aa = a_adv * (uint64_t)k, ba = b_adv * (uint64_t)k;
+                            umma_tf32(d_tmem, alo + aa, bhi + ba, idesc, (uint32_t)((kb != c0) | (k != 0)));
+                            umma_tf32(d_tmem, ahi + aa, blo + ba, idesc, 1u);
+                            umma_tf32(d_tmem, ahi + aa, bhi + ba, idesc, 1u);
                         }
                         tcgen05_commit(empty_bar(s));      // smem stage is free once these MMAs retire
                         if (++s == cfg::kStages) { s = 0; ph ^= 1u; }
@@ -358,9 +400,17 @@ __device__ __forceinline__ float tf32_rna(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// what the tensor core makes of a raw fp32 word under kind::tf32: the low 13 mantissa bits are ignored
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+// lo plane for an operand whose hi part is the source itself
+__device__ __forceinline__ float lo_of(float x) {
+    const float res = x - tf32_trunc(x);  // exact in fp32; 0 for +-inf after the isfinite test below
+    return isfinite(res) ? tf32_rna(res) : 0.f;
+}
+// general route: both planes are written, hi rounded to nearest
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     float h = tf32_rna(x);
-    if (!isfinite(h)) h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);  // rounding overflowed: truncate instead
+    if (!isfinite(h)) h = tf32_trunc(x);  // rounding overflowed: truncate instead
     hi = h;
     const float res = x - h;  // exact in fp32
     lo = isfinite(res) ? tf32_rna(res) : 0.f;
@@ -368,22 +418,36 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 
 struct SplitJob {
     const float* src;
-    float* hi;
+    float* hi;            // null: the tensor core reads `src` in place (mode 0)
     float* lo;
-    int rows, k_contig;   // k_contig: src is [rows x k] (K contiguous); else src is [k x rows]
+    int rows;             // extent of the operand's M / N index
+    int mode;             // 0: lo only, same layout as src (count = rows * k elements, multiple of 4)
+                          // 1: src is [rows x k] (K contiguous) -> padded planes [rows x kp]
+                          // 2: src is [k x rows]                 -> padded planes [rows x kp], transposed
     int blocks;           // CTAs assigned to this operand
 };
 
-// One launch splits BOTH operands of a GEMM (blockIdx.x < jobs[0].blocks -> operand A, else B).
-//  K-contiguous source  [rows x k] : each CTA converts 256 x 4 consecutive output float4 groups
-//  K-strided source     [k x rows] : each CTA transposes one 32 x 32 tile through shared memory
-// Output planes are [rows x kp] with kp = K rounded up to 32, zero padded.
+// One launch splits BOTH operands of a GEMM (blockIdx.x < ja.blocks -> operand A, else B).
 __global__ void __launch_bounds__(256) split_pair_kernel(const SplitJob ja, const SplitJob jb, int k, int kp) {
     __shared__ float tile[32][33];
     const bool second = blockIdx.x >= (unsigned)ja.blocks;
     const SplitJob& j = second ? jb : ja;
     const int bid = second ? blockIdx.x - ja.blocks : blockIdx.x;
-    if (j.k_contig) {
+    if (j.mode == 0) {
+        const size_t nvec = (size_t)j.rows * k / 4;
+        const size_t base = (size_t)bid * 1024 + threadIdx.x;
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const size_t i = base + u * 256;
+            if (i < nvec) v[u] = reinterpret_cast<const float4*>(j.src)[i];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const size_t i = base + u * 256;
+            if (i < nvec) reinterpret_cast<float4*>(j.lo)[i] = make_float4(lo_of(v[u].x), lo_of(v[u].y), lo_of(v[u].z), lo_of(v[u].w));
+        }
+    } else if (j.mode == 1) {
         const int vec_in = ((k % 4) == 0) && ((reinterpret_cast<uintptr_t>(j.src) & 15) == 0);
         const int kq = kp / 4;
         const size_t total = (size_t)j.rows * kq;
@@ -448,16 +512,21 @@ static int load_encode() {
     return DSC_OK;
 }
 
-// plane is [rows x kp] fp32, K-major; box = 32 floats (128 B) x box_rows, SWIZZLE_128B, OOB rows read as zero
-static int make_map(CUtensorMap* map, const float* plane, int rows, int kp, int box_rows) {
-    cuuint64_t dims[2] = {(cuuint64_t)kp, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)kp * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+// 2-D map over a row-major fp32 array [outer x inner] (row pitch `pitch` elements); box = 32 floats
+// (128 B, one swizzle row) x box_outer rows, SWIZZLE_128B, out-of-range elements read as zero.
+//   K-major operand : inner = K, outer = M/N rows, box_outer = tile rows
+//   MN-major operand: inner = M/N, outer = K,      box_outer = BK (one box per 32-wide MN block),
+//                     SWIZZLE_128B_ATOM_32B (the only layout the tensor core takes for 32-bit MN-major)
+static int make_map(CUtensorMap* map, const float* base, int inner, int outer, size_t pitch, int box_outer, bool mn_major = false) {
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_outer};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(plane), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(DSC_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %d x %d plane, box rows %d", (int)r, rows, kp, box_rows);
+    if (r != CUDA_SUCCESS) return fail(DSC_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %d x %d array, box rows %d", (int)r, outer, inner, box_outer);
     return DSC_OK;
 }
 
@@ -476,18 +545,30 @@ static int launch(Ctx* ctx, const CUtensorMap* maps, const Params& p) {
     return DSC_OK;
 }
 
-static int split_blocks(bool k_contig, int rows, int kp) {
-    if (k_contig) return (int)(((size_t)rows * (kp / 4) + 1023) / 1024);
-    return ((rows + 31) / 32) * (kp / 32);
+// How one operand reaches the tensor core.
+struct OperandPlan {
+    bool direct;       // hi = the source buffer in place; only a lo plane is written
+    bool mn_major;     // tiles are MN-major (direct operands whose K index is strided)
+    int mode;          // SplitJob mode
+    size_t ws_floats;  // workspace floats (lo plane, or hi + lo padded planes)
+};
+
+// src_k_contig: the stored array is [mn x k]; otherwise [k x mn]
+static OperandPlan plan_operand(const float* src, bool src_k_contig, int mn, int k, int kp) {
+    OperandPlan o;
+    const int contig = src_k_contig ? k : mn;
+    static const bool force_planes = [] { const char* e = getenv("DSC_GEMM_PLANES"); return e && *e == '1'; }();
+    o.direct = !force_planes && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (contig % 4) == 0;
+    o.mn_major = o.direct && !src_k_contig;
+    o.mode = o.direct ? 0 : (src_k_contig ? 1 : 2);
+    o.ws_floats = o.direct ? (size_t)mn * k : 2 * (size_t)mn * kp;
+    return o;
 }
 
-static int split_pair(Ctx* ctx, const float* A, bool a_kc, int m, float* ahi, float* alo, const float* B, bool b_kc, int n, float* bhi,
-                      float* blo, int k, int kp) {
-    SplitJob ja{A, ahi, alo, m, a_kc ? 1 : 0, split_blocks(a_kc, m, kp)};
-    SplitJob jb{B, bhi, blo, n, b_kc ? 1 : 0, split_blocks(b_kc, n, kp)};
-    split_pair_kernel<<<ja.blocks + jb.blocks, 256, 0, ctx->stream>>>(ja, jb, k, kp);
-    DSC_LAUNCH_CHECK(ctx);
-    return DSC_OK;
+static int split_blocks(const OperandPlan& o, int rows, int k, int kp) {
+    if (o.mode == 0) return (int)(((size_t)rows * k / 4 + 1023) / 1024);
+    if (o.mode == 1) return (int)(((size_t)rows * (kp / 4) + 1023) / 1024);
+    return ((rows + 31) / 32) * (kp / 32);
 }
 
 }  // namespace tf32x3
@@ -543,28 +624,52 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
     p.splits = splits;
     p.kb_per_split = chunks_per_split * kChunkKb;
 
-    const size_t plane_a = (size_t)m * kp, plane_b = (size_t)n * kp;
-    const size_t planes_bytes = ((2 * plane_a + 2 * plane_b) * sizeof(float) + 1023) & ~size_t(1023);
+    // op(A)(m x k): stored m x k (K contiguous) unless ta; op(B)(k x n): stored n x k (K contiguous) only if tb
+    const OperandPlan pa = plan_operand(A, !ta, m, k, kp), pb = plan_operand(B, tb != 0, n, k, kp);
+    const size_t a_floats = (pa.ws_floats + 255) & ~size_t(255), b_floats = (pb.ws_floats + 255) & ~size_t(255);
+    const size_t planes_bytes = (a_floats + b_floats) * sizeof(float);
     const size_t partial_bytes = splits > 1 ? (size_t)splits * m * n * sizeof(float) : 0;
     DSC_TRY(ensure_gemm_ws(ctx, planes_bytes + partial_bytes + 2048));
     char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ctx->gemm_ws) + 1023) & ~uintptr_t(1023));
     float* ws = reinterpret_cast<float*>(base);
-    float *ahi = ws, *alo = ws + plane_a, *bhi = ws + 2 * plane_a, *blo = ws + 2 * plane_a + plane_b;
+    // direct: [lo]; planes: [hi | lo]
+    float* a_lo = pa.direct ? ws : ws + (size_t)m * kp;
+    float* b_lo = pb.direct ? ws + a_floats : ws + a_floats + (size_t)n * kp;
+    const float* a_hi = pa.direct ? A : ws;
+    const float* b_hi = pb.direct ? B : ws + a_floats;
     float* partial = splits > 1 ? reinterpret_cast<float*>(base + planes_bytes) : nullptr;
 
     // ---- (1) split pre-pass ----
-    // op(A)(m x k): stored m x k (K contiguous) unless ta; op(B)(k x n): stored k x n (K NOT contiguous) unless tb
-    DSC_TRY(split_pair(ctx, A, !ta, m, ahi, alo, B, tb != 0, n, bhi, blo, k, kp));
+    {
+        SplitJob ja{A, pa.direct ? nullptr : ws, a_lo, m, pa.mode, split_blocks(pa, m, k, kp)};
+        SplitJob jb{B, pb.direct ? nullptr : ws + a_floats, b_lo, n, pb.mode, split_blocks(pb, n, k, kp)};
+        split_pair_kernel<<<ja.blocks + jb.blocks, 256, 0, ctx->stream>>>(ja, jb, k, kp);
+        DSC_LAUNCH_CHECK(ctx);
+    }
 
     // ---- (2) tensor-core kernel ----
     p.C = splits > 1 ? partial : C;
     p.bias = splits > 1 ? nullptr : bias;
     p.vec4 = ((n % 4) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    p.a_mn = pa.mn_major ? 1 : 0;
+    p.b_mn = pb.mn_major ? 1 : 0;
     CUtensorMap maps[4];
-    DSC_TRY(make_map(&maps[0], ahi, m, kp, BM));
-    DSC_TRY(make_map(&maps[1], alo, m, kp, BM));
-    DSC_TRY(make_map(&maps[2], bhi, n, kp, bn));
-    DSC_TRY(make_map(&maps[3], blo, n, kp, bn));
+    if (pa.mn_major) {          // stored k x m
+        DSC_TRY(make_map(&maps[0], a_hi, m, k, (size_t)m, BK, true));
+        DSC_TRY(make_map(&maps[1], a_lo, m, k, (size_t)m, BK, true));
+    } else {                    // [m x k] in place, or padded planes [m x kp]
+        const int kk = pa.direct ? k : kp;
+        DSC_TRY(make_map(&maps[0], a_hi, kk, m, (size_t)kk, BM));
+        DSC_TRY(make_map(&maps[1], a_lo, kk, m, (size_t)kk, BM));
+    }
+    if (pb.mn_major) {          // stored k x n
+        DSC_TRY(make_map(&maps[2], b_hi, n, k, (size_t)n, BK, true));
+        DSC_TRY(make_map(&maps[3], b_lo, n, k, (size_t)n, BK, true));
+    } else {
+        const int kk = pb.direct ? k : kp;
+        DSC_TRY(make_map(&maps[2], b_hi, kk, n, (size_t)kk, bn));
+        DSC_TRY(make_map(&maps[3], b_lo, kk, n, (size_t)kk, bn));
+    }
     int s;
     if (bn == 256) s = launch<256>(ctx, maps, p);
     else if (bn == 128) s = launch<128>(ctx, maps, p);

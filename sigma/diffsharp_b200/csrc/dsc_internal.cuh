@@ -18,6 +18,7 @@ namespace dsc {
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs. Grids are sized in multiples of this.
 constexpr uint32_t kBufMagic = 0xD5CB0F01u;
 constexpr uint32_t kCtxMagic = 0xD5CC7801u;
+constexpr int kNumTickets = 4096;
 
 struct Ctx;
 
@@ -82,6 +83,9 @@ struct Ctx {
     void* red_scratch = nullptr;   // device
     size_t red_scratch_bytes = 0;
     void* red_host = nullptr;      // pinned host, 256 B
+    // zero-initialised arrival counters for "last CTA of a group finishes the reduction" kernels
+    // (each kernel resets the counters it used; one stream => no two users at a time)
+    unsigned int* tickets = nullptr;
     void* flush_buf = nullptr;     // L2 flush scratch
     size_t flush_bytes = 0;
     // GEMM operand-split workspace (3xTF32 hi/lo planes)

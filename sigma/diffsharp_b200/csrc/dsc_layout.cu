@@ -166,60 +166,102 @@ __global__ void diag_kernel(const T* __restrict__ A, T* __restrict__ out, int n,
 }
 
 // ---- column reduction (Add_M_Colwise_V_InPlace, Backend.fs:123) ---------------------------
-// v[j] += sum_i M[i,j].  Two deterministic stages: (1) the rows are cut into `chunks` contiguous
-// slabs; block (bx, chunk) sums its slab for 32*W columns with blockDim.y row lanes and a fixed
-// shared-memory tree over the lanes; (2) one thread per column adds the slab partials in slab order.
+// v[j] += sum_i M[i,j] in ONE launch.  The rows are cut into `chunks` contiguous slabs; block
+// (bx, chunk) sums its slab for 32*W columns with 8 row lanes (8 independent 128-bit loads in flight
+// per thread) and a fixed shared-memory tree over the lanes, and writes one partial row.  The CTA
+// that arrives last for a column block (ticket counter) adds the slab partials — row lane ty takes
+// the slabs c = ty (mod 8) in increasing order, then the same fixed tree — and accumulates into v.
+// Which CTA does the last step varies; the order of the additions does not (deterministic).
 template <typename T, int W>
-__global__ void __launch_bounds__(256) colsum_stage1(const T* __restrict__ M, T* __restrict__ partial, int m, int n,
-                                                       int rows_per_chunk) {
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ M, T* __restrict__ partial, T* __restrict__ v,
+                                                      unsigned int* __restrict__ tickets, int m, int n, int rows_per_chunk) {
     __shared__ T sm[8][32 * W + 1];
+    __shared__ int s_last;
     const int col0 = (blockIdx.x * 32 + threadIdx.x) * W;
     const int r_begin = blockIdx.y * rows_per_chunk;
     const int r_end = min(m, r_begin + rows_per_chunk);
+    const int chunks = gridDim.y;
     T acc[W];
 #pragma unroll
     for (int w = 0; w < W; ++w) acc[w] = T(0);
-    if (col0 < n) {
-        for (int r = r_begin + threadIdx.y; r < r_end; r += 8) {
-            const T* row = M + (size_t)r * n + col0;
-            if constexpr (W == 4) {
-                float4 x = *reinterpret_cast<const float4*>(row);
-                acc[0] += x.x; acc[1] += x.y; acc[2] += x.z; acc[3] += x.w;
-            } else if constexpr (W == 2) {
-                double2 x = *reinterpret_cast<const double2*>(row);
-                acc[0] += x.x; acc[1] += x.y;
-            } else {
-                acc[0] += row[0];
+    auto tree = [&]() {   // sum of the 8 row lanes, valid in row lane 0
+#pragma unroll
+        for (int w = 0; w < W; ++w) sm[threadIdx.y][threadIdx.x * W + w] = acc[w];
+        __syncthreads();
+        if (threadIdx.y == 0) {
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                const int c = threadIdx.x * W + w;
+                acc[w] = ((sm[0][c] + sm[1][c]) + (sm[2][c] + sm[3][c])) + ((sm[4][c] + sm[5][c]) + (sm[6][c] + sm[7][c]));
             }
         }
-    }
+    };
+    if (col0 < n) {
+        for (int r = r_begin + threadIdx.y; r < r_end; r += 64) {
+            T x[8][W];
 #pragma unroll
-    for (int w = 0; w < W; ++w) sm[threadIdx.y][threadIdx.x * W + w] = acc[w];
-    __syncthreads();
-    if (threadIdx.y == 0 && col0 < n) {
+            for (int u = 0; u < 8; ++u) {
+                const int rr = r + 8 * u;
 #pragma unroll
-        for (int w = 0; w < W; ++w) {
-            T s = ((sm[0][threadIdx.x * W + w] + sm[1][threadIdx.x * W + w]) + (sm[2][threadIdx.x * W + w] + sm[3][threadIdx.x * W + w])) +
-                  ((sm[4][threadIdx.x * W + w] + sm[5][threadIdx.x * W + w]) + (sm[6][threadIdx.x * W + w] + sm[7][threadIdx.x * W + w]));
-            partial[(size_t)blockIdx.y * n + col0 + w] = s;
+                for (int w = 0; w < W; ++w) x[u][w] = T(0);
+                if (rr < r_end) {
+                    const T* row = M + (size_t)rr * n + col0;
+                    if constexpr (W == 4) {
+                        const float4 q = *reinterpret_cast<const float4*>(row);
+                        x[u][0] = q.x; x[u][1] = q.y; x[u][2] = q.z; x[u][3] = q.w;
+                    } else if constexpr (W == 2) {
+                        const double2 q = *reinterpret_cast<const double2*>(row);
+                        x[u][0] = q.x; x[u][1] = q.y;
+                    } else {
+                        x[u][0] = row[0];
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int w = 0; w < W; ++w) acc[w] += x[u][w];
         }
     }
-}
-template <typename T>
-__global__ void colsum_stage2(const T* __restrict__ partial, T* __restrict__ v, int n, int chunks) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    T s = T(0);
-    int c = 0;
-    for (; c + 8 <= chunks; c += 8) {  // 8 independent loads in flight, adds in slab order
-        T v[8];
+    tree();
+    if (chunks == 1) {
+        if (threadIdx.y == 0 && col0 < n) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = partial[(size_t)(c + u) * n + j];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) s += v[u];
+            for (int w = 0; w < W; ++w) v[col0 + w] += acc[w];
+        }
+        return;
     }
-    for (; c < chunks; ++c) s += partial[(size_t)c * n + j];
-    v[j] += s;
+    if (threadIdx.y == 0 && col0 < n) {
+#pragma unroll
+        for (int w = 0; w < W; ++w) partial[(size_t)blockIdx.y * n + col0 + w] = acc[w];
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) s_last = (atomicAdd(&tickets[blockIdx.x], 1u) == (unsigned)chunks - 1u);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+#pragma unroll
+    for (int w = 0; w < W; ++w) acc[w] = T(0);
+    if (col0 < n) {
+        for (int c = threadIdx.y; c < chunks; c += 64) {
+            T x[8][W];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int w = 0; w < W; ++w) x[u][w] = (c + 8 * u < chunks) ? __ldcg(partial + (size_t)(c + 8 * u) * n + col0 + w) : T(0);
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int w = 0; w < W; ++w) acc[w] += x[u][w];
+        }
+    }
+    tree();
+    if (threadIdx.y == 0 && col0 < n) {
+#pragma unroll
+        for (int w = 0; w < W; ++w) v[col0 + w] += acc[w];
+    }
+    if (threadIdx.x == 0 && threadIdx.y == 0) tickets[blockIdx.x] = 0;
 }
 
 template <typename T>
@@ -228,22 +270,19 @@ int colsum_launch(Ctx* ctx, const T* M, T* v, int m, int n) {
     bool vec = (n % W == 0) && al16(M);
     int cols_per_block = vec ? 32 * W : 32;
     int gx = (n + cols_per_block - 1) / cols_per_block;
-    // enough slabs to put ~4 CTAs on every SM, at least 64 rows per slab
-    int chunks = (ctx->sm_count * 4 + gx - 1) / gx;
-    int max_chunks = (m + 63) / 64;
-    if (chunks > max_chunks) chunks = max_chunks;
-    if (chunks < 1) chunks = 1;
-    if (chunks > 256) chunks = 256;
-    int rows_per_chunk = (m + chunks - 1) / chunks;
-    chunks = (m + rows_per_chunk - 1) / rows_per_chunk;
+    // 64-row slabs (every thread issues its 8 loads at once) unless that leaves the machine idle or
+    // makes more than 512 partial rows
+    int rows_per_chunk = 64;
+    while (rows_per_chunk > 8 && (long)gx * ((m + rows_per_chunk - 1) / rows_per_chunk) < ctx->sm_count * 2) rows_per_chunk /= 2;
+    while ((m + rows_per_chunk - 1) / rows_per_chunk > 512) rows_per_chunk *= 2;
+    int chunks = (m + rows_per_chunk - 1) / rows_per_chunk;
+    if (gx > kNumTickets) return fail(DSC_E_SHAPE, "Add_M_Colwise_V_InPlace: %d columns exceed the supported maximum", n);
     size_t need = 256 + (size_t)chunks * n * sizeof(T);
     DSC_TRY(ensure_red_scratch(ctx, need));
     T* partial = reinterpret_cast<T*>(reinterpret_cast<char*>(ctx->red_scratch) + 256);
     dim3 block(32, 8), grid(gx, chunks);
-    if (vec) colsum_stage1<T, W><<<grid, block, 0, ctx->stream>>>(M, partial, m, n, rows_per_chunk);
-    else colsum_stage1<T, 1><<<grid, block, 0, ctx->stream>>>(M, partial, m, n, rows_per_chunk);
-    DSC_LAUNCH_CHECK(ctx);
-    colsum_stage2<T><<<(n + 63) / 64, 64, 0, ctx->stream>>>(partial, v, n, chunks);
+    if (vec) colsum_kernel<T, W><<<grid, block, 0, ctx->stream>>>(M, partial, v, ctx->tickets, m, n, rows_per_chunk);
+    else colsum_kernel<T, 1><<<grid, block, 0, ctx->stream>>>(M, partial, v, ctx->tickets, m, n, rows_per_chunk);
     DSC_LAUNCH_CHECK(ctx);
     return DSC_OK;
 }
