@@ -202,6 +202,24 @@ int ensure_gemm_ws(Ctx* ctx, size_t bytes) {
     return DSC_OK;
 }
 
+int ensure_gemm_tickets(Ctx* ctx, size_t count) {
+    if (ctx->gemm_tickets_n >= count) return DSC_OK;
+    if (ctx->capturing || ctx->live_graphs > 0)
+        return fail(DSC_E_INVALID, "GEMM ticket array cannot grow while a CUDA graph is being captured or is alive (run the step once eagerly first)");
+    if (ctx->gemm_tickets) {
+        DSC_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->gemm_tickets);
+    }
+    ctx->gemm_tickets = nullptr;
+    ctx->gemm_tickets_n = 0;
+    size_t want = 4096;
+    while (want < count) want *= 2;
+    DSC_CUDA_CHECK(cudaMalloc(&ctx->gemm_tickets, want * sizeof(unsigned int)));
+    DSC_CUDA_CHECK(cudaMemsetAsync(ctx->gemm_tickets, 0, want * sizeof(unsigned int), ctx->stream));
+    ctx->gemm_tickets_n = want;
+    return DSC_OK;
+}
+
 template <typename T>
 __global__ void fill_kernel(T* __restrict__ p, size_t n, T v) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -321,6 +339,7 @@ int dsc_destroy(dsc_ctx_t c) {
     if (ctx->red_host) cudaFreeHost(ctx->red_host);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     if (ctx->gemm_ws) cudaFree(ctx->gemm_ws);
+    if (ctx->gemm_tickets) cudaFree(ctx->gemm_tickets);
     if (ctx->comm_stage) cudaFree(ctx->comm_stage);
     cudaEventDestroy(ctx->ev_compute);
     cudaEventDestroy(ctx->ev_comm);

@@ -303,9 +303,18 @@ __global__ void __launch_bounds__(256) skinny_cols_vec_kernel(const T* __restric
     for (int k0 = kbeg; k0 < kend; k0 += KCH) {
         const int kc = min(KCH, kend - k0);
         __syncthreads();
-        for (int idx = threadIdx.x; idx < KCH * NJ; idx += 256) {
-            const int kk = idx / NJ, j = idx % NJ;
-            Bs[kk][j] = (kk < kc && j < n) ? ldB(B, tb, k, n, k0 + kk, j) : T(0);
+        {   // thread t stages k-row t of the chunk (KCH == blockDim.x): n loads, NJ/W vector stores
+            const int kk = threadIdx.x;
+            T row[NJ];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) row[j] = (kk < kc && j < n) ? ldB(B, tb, k, n, k0 + kk, j) : T(0);
+#pragma unroll
+            for (int j = 0; j < NJ; j += W) {
+                V q;
+#pragma unroll
+                for (int l = 0; l < W; ++l) (&q.x)[l] = row[j + l];
+                *reinterpret_cast<V*>(&Bs[kk][j]) = q;
+            }
         }
         __syncthreads();
         if (col0 < m) {  // m % W == 0: a column vector is entirely inside or outside
@@ -406,48 +415,54 @@ __global__ void __launch_bounds__(256) skinny_cols_vec_kernel(const T* __restric
 }
 
 // ---- tiny K (k <= NMAX): C(m x n) = A(m x k) op(B)(k x n), output-write bound -----------------
-// (the input adjoint of the output layer: dZ (B x 10) * W3^T (10 x 1024)).  A thread keeps the k
-// B-values of its 4 (2 for double) output columns in registers and walks the rows of its CTA's slab.
-template <typename T>
+// (the input adjoint of the output layer: dZ (B x 10) * W3^T (10 x 1024)).  A thread keeps the KP
+// (= k rounded up to 4) B-values of its 4 (2 for double) output columns in registers and walks the
+// rows of its CTA's slab; the slab's A rows are staged in shared memory and read back as 16-byte
+// broadcasts.
+template <typename T, int KP>
 __global__ void __launch_bounds__(256) tiny_k_kernel(const T* __restrict__ A, const T* __restrict__ B, const T* __restrict__ bias,
                                                       T* __restrict__ C, int m, int n, int k, int ta, int tb, int rows_per_cta) {
-    constexpr int W = 16 / (int)sizeof(T);
+    using V = typename V16<T>::type;
+    constexpr int W = V16<T>::W;
+    constexpr int RS = 64;  // rows staged per pass
     const int c0 = (blockIdx.x * 256 + threadIdx.x) * W;
     const int r0 = blockIdx.y * rows_per_cta, r1 = min(m, r0 + rows_per_cta);
-    __shared__ T As[64][NMAX];
-    T b[NMAX][W];
+    __shared__ __align__(16) T As[RS][KP];
+    T b[KP][W];
 #pragma unroll
-    for (int kk = 0; kk < NMAX; ++kk)
+    for (int kk = 0; kk < KP; ++kk)
 #pragma unroll
         for (int w = 0; w < W; ++w) b[kk][w] = (kk < k && c0 + w < n) ? (tb ? B[(size_t)(c0 + w) * k + kk] : B[(size_t)kk * n + c0 + w]) : T(0);
     const bool vec = (n % W == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-    for (int rb = r0; rb < r1; rb += 64) {
-        const int nr = min(64, r1 - rb);
+    for (int rb = r0; rb < r1; rb += RS) {
+        const int nr = min(RS, r1 - rb);
         __syncthreads();
-        for (int idx = threadIdx.x; idx < 64 * NMAX; idx += 256) {
-            const int r = idx / NMAX, kk = idx % NMAX;
+        for (int idx = threadIdx.x; idx < RS * KP; idx += 256) {
+            const int r = idx / KP, kk = idx % KP;
             As[r][kk] = (r < nr && kk < k) ? (ta ? A[(size_t)kk * m + rb + r] : A[(size_t)(rb + r) * k + kk]) : T(0);
         }
         __syncthreads();
         if (c0 >= n) continue;
+#pragma unroll 2
         for (int r = 0; r < nr; ++r) {
             T acc[W];
 #pragma unroll
             for (int w = 0; w < W; ++w) acc[w] = T(0);
 #pragma unroll
-            for (int kk = 0; kk < NMAX; ++kk) {
-                const T av = As[r][kk];  // broadcast
+            for (int kk = 0; kk < KP; kk += W) {
+                const V av = *reinterpret_cast<const V*>(&As[r][kk]);  // same address in every lane: broadcast
 #pragma unroll
-                for (int w = 0; w < W; ++w) acc[w] = fma(av, b[kk][w], acc[w]);
+                for (int l = 0; l < W; ++l)
+#pragma unroll
+                    for (int w = 0; w < W; ++w) acc[w] = fma(vget(av, l), b[kk + l][w], acc[w]);
             }
             const T bv = bias ? bias[rb + r] : T(0);
             T* dst = C + (size_t)(rb + r) * n + c0;
             if (vec) {
-                int4 raw;
-                T* o = reinterpret_cast<T*>(&raw);
+                V o;
 #pragma unroll
-                for (int w = 0; w < W; ++w) o[w] = acc[w] + bv;
-                *reinterpret_cast<int4*>(dst) = raw;
+                for (int w = 0; w < W; ++w) (&o.x)[w] = acc[w] + bv;
+                *reinterpret_cast<V*>(dst) = o;
             } else {
 #pragma unroll
                 for (int w = 0; w < W; ++w)
@@ -497,8 +512,9 @@ static int launch_cols_vec_inst(Ctx* ctx, int m, int n, int k, int tb, const T* 
     using namespace skinny;
     constexpr int W = 16 / (int)sizeof(T);
     const int gx = (m + 31) / 32;
-    // ~2 CTAs per SM; every k-lane (8W per CTA) gets at least 4 k-rows
-    int chunks = (ctx->sm_count * 2 + gx - 1) / gx;
+    // one full wave at 2 CTAs per SM (rounding the chunk count DOWN: a few CTAs more than a wave
+    // would double the run time); every k-lane (8W per CTA) gets at least 4 k-rows
+    int chunks = (ctx->sm_count * 2) / gx;
     const int max_chunks = (k + 32 * W - 1) / (32 * W);
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
@@ -531,11 +547,16 @@ int gemm_skinny(Ctx* ctx, int ta, int tb, int m, int n, int k, const T* A, const
     if (k <= NMAX && n >= 64 && (long)m * n >= 65536) {
         constexpr int W = 16 / (int)sizeof(T);
         const int gx = (n + 256 * W - 1) / (256 * W);
+        // ~4 CTAs per SM, slabs of at least 16 rows (the B registers are loaded once per CTA)
         int gy = (ctx->sm_count * 4 + gx - 1) / gx;
         int rows_per_cta = (m + gy - 1) / gy;
         rows_per_cta = (rows_per_cta + 15) / 16 * 16;
         gy = (m + rows_per_cta - 1) / rows_per_cta;
-        tiny_k_kernel<T><<<dim3(gx, gy), 256, 0, ctx->stream>>>(A, B, bias, C, m, n, k, ta, tb, rows_per_cta);
+        const dim3 grid(gx, gy);
+        if (k <= 4) tiny_k_kernel<T, 4><<<grid, 256, 0, ctx->stream>>>(A, B, bias, C, m, n, k, ta, tb, rows_per_cta);
+        else if (k <= 8) tiny_k_kernel<T, 8><<<grid, 256, 0, ctx->stream>>>(A, B, bias, C, m, n, k, ta, tb, rows_per_cta);
+        else if (k <= 12) tiny_k_kernel<T, 12><<<grid, 256, 0, ctx->stream>>>(A, B, bias, C, m, n, k, ta, tb, rows_per_cta);
+        else tiny_k_kernel<T, 16><<<grid, 256, 0, ctx->stream>>>(A, B, bias, C, m, n, k, ta, tb, rows_per_cta);
         DSC_LAUNCH_CHECK(ctx);
         ctx->stats.gemm_simt++;
         return DSC_OK;

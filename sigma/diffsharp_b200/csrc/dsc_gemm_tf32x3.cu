@@ -37,9 +37,16 @@
 // The two TMEM accumulator stages alternate per chunk, so draining chunk c overlaps the MMAs of
 // chunk c+1.
 //
-// Split-K.  When the output has fewer tiles than SMs (weight-adjoint GEMMs: small m x n, K = batch),
-// the chunks of one tile are dealt to `splits` CTAs; each writes an fp32 partial tile and a second
-// kernel adds the partials in split order (deterministic) and applies the bias.
+// Stream-K.  The work of a GEMM is the list of (tile, K-chunk) units in tile-major order; the grid is
+// one CTA per SM (or per unit if there are fewer) and CTA b takes the b-th contiguous share of the
+// list, so every SM gets the same number of chunks (+-1) whatever the tile count — no partial last
+// wave (8192x1024x1024: 256 tiles on 148 SMs = 2 waves at 86 %; stream-K: 6.92 chunks per SM), and
+// small outputs with a deep K (weight adjoints: K = batch) are cut along K automatically.  A run of
+// units of one tile inside one CTA is a SEGMENT.  A segment that covers its whole tile is stored to C
+// directly.  Otherwise the CTA stores the segment sum to its workspace slot and takes a ticket for
+// the tile; the CTA that arrives last re-reads all the tile's segments in K order, adds them with
+// IEEE adds, applies the bias and stores C — the order of the additions is fixed, only who performs
+// them varies (deterministic).
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -61,7 +68,7 @@ struct Cfg {
     static constexpr int kStageBytes = 2 * kAPlaneBytes + 2 * kBPlaneBytes;
     static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
     static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator stages; power of two
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers, TMEM base, epilogue flag*/;
 };
 
 // ---- PTX helpers ------------------------------------------------------------------------------
@@ -172,12 +179,40 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 struct Params {
     int m, n, num_kb;          // problem rows/cols, number of 32-wide k-blocks
     int tiles_m, tiles_n;
-    int splits, kb_per_split;  // split-K: k-blocks [s*kb_per_split, (s+1)*kb_per_split) belong to split s
-    float* C;                  // splits == 1: the result; splits > 1: partial planes [splits][m][n]
-    const float* bias;         // applied here only when splits == 1
+    int cpt;                   // K chunks per tile
+    // schedule: CTA b first runs dp_waves whole tiles (tile = wave * grid + b), then its share of the
+    // stream-K units of the remaining tiles [dp_tiles, tiles): base + (b < rem) units from
+    // b*base + min(b, rem), unit u = (dp_tiles + u / cpt, u % cpt)
+    int dp_waves, dp_tiles;
+    int dp_extra;              // CTAs b < dp_extra run one more whole tile (tile = dp_waves * grid + b): plain last wave
+    int perm_tiles, perm_s;    // aligned split-K: CTA b acts as logical CTA (b % perm_tiles) * perm_s + b / perm_tiles, so that
+                               // neighbouring CTAs work on neighbouring tiles of the same K range (0: identity)
+    int base, rem;
+    float* C;
+    const float* bias;
+    float* slots;              // [grid][2][BM x BN] partial segment sums
+    unsigned int* tickets;     // one arrival counter per tile (zero outside a launch)
     int vec4;                  // output rows are 16-byte aligned and n % 4 == 0
     int a_mn, b_mn;            // operand tiles are MN-major (source read in place, K index strided)
 };
+
+__device__ __forceinline__ int unit_begin(const Params& p, int b) { return b * p.base + min(b, p.rem); }
+__device__ __forceinline__ int unit_owner(const Params& p, int u) {
+    const int big = p.rem * (p.base + 1);
+    return u < big ? u / (p.base + 1) : p.rem + (u - big) / p.base;
+}
+// i-th unit of CTA b -> (tile, chunk)
+__device__ __forceinline__ void unit_at(const Params& p, int i, int dp_units, int sk_begin, int& tile, int& chunk) {
+    if (i < dp_units) {
+        tile = (i / p.cpt) * (int)gridDim.x + (int)blockIdx.x;  // whole-tile waves use the physical CTA index
+        chunk = i % p.cpt;
+    } else {
+        const int u = sk_begin + (i - dp_units);
+        tile = p.dp_tiles + u / p.cpt;
+        chunk = u % p.cpt;
+    }
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -220,19 +255,22 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
 
-    const int num_tiles = p.tiles_m * p.tiles_n;
-    const int num_units = num_tiles * p.splits;  // unit u = (split u / num_tiles, tile u % num_tiles)
+    const int lb = p.perm_tiles ? ((int)blockIdx.x % p.perm_tiles) * p.perm_s + (int)blockIdx.x / p.perm_tiles : (int)blockIdx.x;
+    const int sk_begin = unit_begin(p, lb), sk_end = unit_begin(p, lb + 1);
+    const int dp_units = (p.dp_waves + ((int)blockIdx.x < p.dp_extra ? 1 : 0)) * p.cpt;
+    const int my_units = dp_units + (sk_end - sk_begin);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-                const int tile = u % num_tiles, split = u / num_tiles;
+            for (int i = 0; i < my_units; ++i) {
+                int tile, chunk;
+                unit_at(p, i, dp_units, sk_begin, tile, chunk);
                 const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
-                const int kb0 = split * p.kb_per_split;
-                const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+                const int kb0 = chunk * kChunkKb;
+                const int kb1 = min(p.num_kb, kb0 + kChunkKb);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     const uint32_t st = smem_base + s * cfg::kStageBytes;
@@ -270,58 +308,60 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
             const uint64_t a_adv = p.a_mn ? 64u : 2u, b_adv = p.b_mn ? 64u : 2u;
             int s = 0, as = 0;
             uint32_t ph = 0, aph = 0;
-            for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-                const int split = u / num_tiles;
-                const int kb0 = split * p.kb_per_split;
-                const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
-                for (int c0 = kb0; c0 < kb1; c0 += kChunkKb) {
-                    const int c1 = min(kb1, c0 + kChunkKb);
-                    mbar_wait(tempty_bar(as), aph ^ 1u);  // the epilogue has drained this accumulator stage
+            for (int i = 0; i < my_units; ++i) {
+                int tile, chunk;
+                unit_at(p, i, dp_units, sk_begin, tile, chunk);
+                const int c0 = chunk * kChunkKb;
+                const int c1 = min(p.num_kb, c0 + kChunkKb);
+                mbar_wait(tempty_bar(as), aph ^ 1u);  // the epilogue has drained this accumulator stage
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                for (int kb = c0; kb < c1; ++kb) {
+                    mbar_wait(full_bar(s), ph);        // TMA bytes have landed
                     tcgen05_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-                    for (int kb = c0; kb < c1; ++kb) {
-                        mbar_wait(full_bar(s), ph);        // TMA bytes have landed
-                        tcgen05_fence_after();
-                        const uint32_t st = smem_base + s * cfg::kStageBytes;
-                        const uint64_t ahi = p.a_mn ? make_mnmajor_sw128_desc(st) : make_kmajor_sw128_desc(st);
-                        const uint64_t alo = p.a_mn ? make_mnmajor_sw128_desc(st + kAPlaneBytes) : make_kmajor_sw128_desc(st + kAPlaneBytes);
-                        const uint64_t bhi = p.b_mn ? make_mnmajor_sw128_desc(st + 2 * kAPlaneBytes) : make_kmajor_sw128_desc(st + 2 * kAPlaneBytes);
-                        const uint64_t blo = p.b_mn ? make_mnmajor_sw128_desc(st + 2 * kAPlaneBytes + cfg::kBPlaneBytes)
-                                                    : make_kmajor_sw128_desc(st + 2 * kAPlaneBytes + cfg::kBPlaneBytes);
+                    const uint32_t st = smem_base + s * cfg::kStageBytes;
+                    const uint64_t ahi = p.a_mn ? make_mnmajor_sw128_desc(st) : make_kmajor_sw128_desc(st);
+                    const uint64_t alo = p.a_mn ? make_mnmajor_sw128_desc(st + kAPlaneBytes) : make_kmajor_sw128_desc(st + kAPlaneBytes);
+                    const uint64_t bhi = p.b_mn ? make_mnmajor_sw128_desc(st + 2 * kAPlaneBytes) : make_kmajor_sw128_desc(st + 2 * kAPlaneBytes);
+                    const uint64_t blo = p.b_mn ? make_mnmajor_sw128_desc(st + 2 * kAPlaneBytes + cfg::kBPlaneBytes)
+                                                : make_kmajor_sw128_desc(st + 2 * kAPlaneBytes + cfg::kBPlaneBytes);
 #pragma unroll
-                        for (int k = 0; k < BK / 8; ++k) {
-                            const uint64_t aa = a_adv * (uint64_t)k, ba = b_adv * (uint64_t)k;
-                            umma_tf32(d_tmem, alo + aa, bhi + ba, idesc, (uint32_t)((kb != c0) | (k != 0)));
-                            umma_tf32(d_tmem, ahi + aa, blo + ba, idesc, 1u);
-                            umma_tf32(d_tmem, ahi + aa, bhi + ba, idesc, 1u);
-                        }
-                        tcgen05_commit(empty_bar(s));      // smem stage is free once these MMAs retire
-                        if (++s == cfg::kStages) { s = 0; ph ^= 1u; }
+                    for (int k = 0; k < BK / 8; ++k) {
+                        const uint64_t aa = a_adv * (uint64_t)k, ba = b_adv * (uint64_t)k;
+                        umma_tf32(d_tmem, alo + aa, bhi + ba, idesc, (uint32_t)((kb != c0) | (k != 0)));
+                        umma_tf32(d_tmem, ahi + aa, blo + ba, idesc, 1u);
+                        umma_tf32(d_tmem, ahi + aa, bhi + ba, idesc, 1u);
                     }
-                    tcgen05_commit(tfull_bar(as));         // chunk accumulator complete
-                    if (++as == 2) { as = 0; aph ^= 1u; }
+                    tcgen05_commit(empty_bar(s));      // smem stage is free once these MMAs retire
+                    if (++s == cfg::kStages) { s = 0; ph ^= 1u; }
                 }
+                tcgen05_commit(tfull_bar(as));         // chunk accumulator complete
+                if (++as == 2) { as = 0; aph ^= 1u; }
             }
         }
     } else {
         // ===================== epilogue warps 2..9 =====================
         // warp w may touch the TMEM lanes of quadrant (w & 3); the two warps of a quadrant split the
         // BN columns in halves.  Each thread owns ONE output row and HALF = BN/2 consecutive columns,
-        // and keeps their running sum over the K chunks in registers.
+        // and keeps their running sum over the K chunks of a segment in registers.
         constexpr int HALF = BN / 2;
         const int quad = warp & 3;
         const int half = (warp - 2) >> 2;
+        const int trow = quad * 32 + lane;          // row inside the tile
+        int* s_flag = reinterpret_cast<int*>(smem_gen + cfg::kStages * cfg::kStageBytes + 8 * (2 * cfg::kStages + 4) + 8);
         int as = 0;
         uint32_t aph = 0;
-        for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-            const int tile = u % num_tiles, split = u / num_tiles;
+        int i = 0;
+        while (i < my_units) {
+            int tile, ch0;
+            unit_at(p, i, dp_units, sk_begin, tile, ch0);
+            // the segment: this CTA's consecutive units of `tile`
+            const int seg_len = i < dp_units ? p.cpt : min(p.cpt - ch0, my_units - i);
             const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
-            const int kb0 = split * p.kb_per_split;
-            const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
             float acc[HALF];
 #pragma unroll
             for (int j = 0; j < HALF; ++j) acc[j] = 0.f;
-            for (int c0 = kb0; c0 < kb1; c0 += kChunkKb) {
+            for (int e = i + seg_len; i < e; ++i) {
                 mbar_wait(tfull_bar(as), aph);
                 tcgen05_fence_after();
 #pragma unroll
@@ -338,21 +378,95 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                 if (lane == 0) mbar_arrive(tempty_bar(as));
                 if (++as == 2) { as = 0; aph ^= 1u; }
             }
-            const int row = m0 + quad * 32 + lane;
-            if (row < p.m) {
-                const float bv = (p.bias != nullptr) ? p.bias[row] : 0.f;
-                float* crow = p.C + (size_t)split * p.m * p.n + (size_t)row * p.n;
+            if (seg_len == p.cpt) {
+                // the segment is the whole tile: add the bias and store
+                const int row = m0 + trow;
                 const int col0 = n0 + half * HALF;
+                if (row < p.m) {
+                    const float bv = (p.bias != nullptr) ? p.bias[row] : 0.f;
+                    float* crow = p.C + (size_t)row * p.n;
 #pragma unroll
-                for (int c = 0; c < HALF; c += 4) {
-                    const int col = col0 + c;
-                    if (p.vec4 && col + 4 <= p.n) {
-                        *reinterpret_cast<float4*>(crow + col) = make_float4(acc[c] + bv, acc[c + 1] + bv, acc[c + 2] + bv, acc[c + 3] + bv);
-                    } else {
+                    for (int c = 0; c < HALF; c += 4) {
+                        const int col = col0 + c;
+                        if (p.vec4 && col + 4 <= p.n) {
+                            *reinterpret_cast<float4*>(crow + col) = make_float4(acc[c] + bv, acc[c + 1] + bv, acc[c + 2] + bv, acc[c + 3] + bv);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (col + j < p.n) crow[col + j] = acc[c + j] + bv;
+                            for (int j = 0; j < 4; ++j)
+                                if (col + j < p.n) crow[col + j] = acc[c + j] + bv;
+                        }
                     }
+                }
+            } else {
+                // partial segment: park it in this CTA's slot (0 = the segment that starts the CTA's range)
+                const int sk_tile = tile - p.dp_tiles;
+                const int which = (sk_tile == sk_begin / p.cpt) ? 0 : 1;
+                {
+                    float* slot = p.slots + ((size_t)lb * 2 + which) * (BM * BN) + (size_t)trow * BN + half * HALF;
+#pragma unroll
+                    for (int c = 0; c < HALF; c += 4) *reinterpret_cast<float4*>(slot + c) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+                }
+                __threadfence();
+                epi_bar();
+                const int b_first = unit_owner(p, sk_tile * p.cpt), b_last = unit_owner(p, (sk_tile + 1) * p.cpt - 1);
+                if (threadIdx.x == 64) *s_flag = (atomicAdd(&p.tickets[tile], 1u) == (unsigned)(b_last - b_first));
+                epi_bar();
+                const bool last = (*s_flag != 0);
+                epi_bar();   // everyone has read the flag before the next segment overwrites it
+                if (last) {
+                    // last arriver: C tile = sum of the tile's segments in K order (+ bias).  The
+                    // register accumulators are dead here; the tile is walked as float4 index
+                    // f = it * 256 + t (fully coalesced), 8 float4 per thread per pass with the loads
+                    // of 2 segments in flight together.
+                    __threadfence();
+                    const int t = threadIdx.x - 64;
+                    constexpr int F4_PER_ROW = BN / 4;
+                    constexpr int PASSES = BM * BN / 4 / 256 / 8;
+                    for (int pass = 0; pass < PASSES; ++pass) {
+                        float4 sum[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) sum[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int b0 = b_first; b0 <= b_last; b0 += 2) {
+                            float4 v[2][8];
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const int b = b0 + j;
+                                if (b <= b_last) {
+                                    const int w = (sk_tile == unit_begin(p, b) / p.cpt) ? 0 : 1;
+                                    const float4* src = reinterpret_cast<const float4*>(p.slots + ((size_t)b * 2 + w) * (BM * BN));
+#pragma unroll
+                                    for (int q = 0; q < 8; ++q) v[j][q] = __ldcg(src + (pass * 8 + q) * 256 + t);
+                                } else {
+#pragma unroll
+                                    for (int q = 0; q < 8; ++q) v[j][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) {
+                                    sum[q].x += v[j][q].x; sum[q].y += v[j][q].y; sum[q].z += v[j][q].z; sum[q].w += v[j][q].w;
+                                }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const int f = (pass * 8 + q) * 256 + t;
+                            const int r = m0 + f / F4_PER_ROW, cc = n0 + (f % F4_PER_ROW) * 4;
+                            if (r < p.m) {
+                                const float bv = (p.bias != nullptr) ? p.bias[r] : 0.f;
+                                float* dst = p.C + (size_t)r * p.n + cc;
+                                if (p.vec4 && cc + 4 <= p.n) {
+                                    *reinterpret_cast<float4*>(dst) = make_float4(sum[q].x + bv, sum[q].y + bv, sum[q].z + bv, sum[q].w + bv);
+                                } else {
+                                    if (cc < p.n) dst[0] = sum[q].x + bv;
+                                    if (cc + 1 < p.n) dst[1] = sum[q].y + bv;
+                                    if (cc + 2 < p.n) dst[2] = sum[q].z + bv;
+                                    if (cc + 3 < p.n) dst[3] = sum[q].w + bv;
+                                }
+                            }
+                        }
+                    }
+                    if (threadIdx.x == 64) p.tickets[tile] = 0;
                 }
             }
         }
@@ -363,34 +477,6 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)cfg::kTmemCols) : "memory");
-    }
-}
-
-// C = sum_s P[s] (+ bias[row]) in split order (deterministic)
-__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ P, const float* __restrict__ bias, float* __restrict__ C,
-                                                             int m, int n, int splits, int vec4) {
-    const size_t total = (size_t)m * n;
-    if (vec4) {
-        const size_t nv = total / 4;
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x * blockDim.x) {
-            float4 a = reinterpret_cast<const float4*>(P)[i];
-            for (int s = 1; s < splits; ++s) {
-                const float4 b = reinterpret_cast<const float4*>(P + (size_t)s * total)[i];
-                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-            }
-            if (bias) {
-                const float bv = bias[(i * 4) / n];
-                a.x += bv; a.y += bv; a.z += bv; a.w += bv;
-            }
-            reinterpret_cast<float4*>(C)[i] = a;
-        }
-    } else {
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-            float a = P[i];
-            for (int s = 1; s < splits; ++s) a += P[(size_t)s * total + i];
-            if (bias) a += bias[i / n];
-            C[i] = a;
-        }
     }
 }
 
@@ -531,15 +617,13 @@ static int make_map(CUtensorMap* map, const float* base, int inner, int outer, s
 }
 
 template <int BN>
-static int launch(Ctx* ctx, const CUtensorMap* maps, const Params& p) {
+static int launch(Ctx* ctx, const CUtensorMap* maps, const Params& p, int grid) {
     using cfg = Cfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
         DSC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::kSmemBytes));
         attr_set = true;
     }
-    const int units = p.tiles_m * p.tiles_n * p.splits;
-    const int grid = units < ctx->sm_count ? units : ctx->sm_count;
     gemm_tf32x3_kernel<BN><<<grid, kThreads, cfg::kSmemBytes, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], p);
     DSC_LAUNCH_CHECK(ctx);
     return DSC_OK;
@@ -581,55 +665,98 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
     DSC_TRY(load_encode());
     const int kp = (k + BK - 1) / BK * BK;
 
-    // ---- plan: tile width, split-K, workspace (all decided before anything is launched) ----
+    // ---- plan: tile width, grid and schedule (all decided before anything is launched) ----
     // Cycle model per CTA and 32-wide k-block (B300_MICROARCH.md pacing law, measured here):
     //   tensor pipe  : 4 k-slices x 3 MMAs x (BN/256 x 128) = 6 BN cycles
     //   smem fill    : (BM + BN) rows x 128 B x 2 planes at 128 B/cycle       = 2 (BM + BN) cycles
     //   L2 -> SM     : the same bytes from every active CTA through ~10 KB/cycle of L2 bandwidth
-    // plus ~4000 cycles of prologue / epilogue per unit.  Wide tiles win on big problems (less operand
-    // traffic), narrow tiles and split-K win when the output has fewer tiles than the machine has SMs.
+    // Schedules (one kernel, see Params):
+    //   tiles >= SMs : whole-tile waves (neighbouring CTAs walk K in lockstep over neighbouring tiles,
+    //                  so operand panels are shared in L2) + stream-K over the tiles of the last,
+    //                  partial wave, whose operands fit in L2 whatever the order
+    //   tiles <  SMs : aligned split-K — every tile is cut into `s` equal K ranges (grid = tiles * s);
+    //                  CTAs of the same range stay in lockstep.  Unaligned stream-K ranges would keep
+    //                  all SMs busy but every CTA would stream its own operand slice from HBM
+    //                  (measured: 1024 x 1024 x 8192 ran 50 % slower that way).
     const int num_kb = kp / BK;
-    const int chunks = (num_kb + kChunkKb - 1) / kChunkKb;
+    const int cpt = (num_kb + kChunkKb - 1) / kChunkKb;
     const int tiles_m = (m + BM - 1) / BM;
-    int bn = 256, splits = 1;
+    const double kb_per_chunk = (double)num_kb / cpt;
+    int bn = 256, grid = 1, dp_waves = 0, dp_extra = 0, sk_units_total = 0, perm_s = 0;
     {
         double best = -1.0;
         const int cands[3] = {256, 128, 64};
         for (int c : cands) {
-            const int tn = (n + c - 1) / c, tiles = tiles_m * tn;
-            int max_split = chunks / 2 > 0 ? chunks / 2 : 1;   // every split keeps >= 2 chunks of K
-            if (max_split > 16) max_split = 16;
-            for (int sp = 1; sp <= max_split; sp *= 2) {
-                const int cps = (chunks + sp - 1) / sp;
-                const int real_sp = (chunks + cps - 1) / cps;
-                const long units = (long)tiles * real_sp;
-                const long waves = (units + ctx->sm_count - 1) / ctx->sm_count;
-                const double active = units < ctx->sm_count ? (double)units : (double)ctx->sm_count;
-                const double bytes_kb = (double)(BM + c) * 256.0;
-                double per_kb = 6.0 * c;
-                if (2.0 * (BM + c) > per_kb) per_kb = 2.0 * (BM + c);
-                if (bytes_kb * active / 10000.0 > per_kb) per_kb = bytes_kb * active / 10000.0;
-                double cost = (double)waves * ((double)cps * kChunkKb * per_kb + 4000.0);
-                if (real_sp > 1) cost += 3000.0 + (double)real_sp * m * n * 8.0 / 3500.0;  // partial planes written + reduced
-                if (best < 0 || cost < best) { best = cost; bn = c; splits = real_sp; }
+            const long tiles = (long)tiles_m * ((n + c - 1) / c);
+            if (tiles * cpt > 0x3fffffff) continue;
+            const double bytes_kb = (double)(BM + c) * 256.0;
+            auto per_kb = [&](double active) {
+                double t = 6.0 * c;
+                if (2.0 * (BM + c) > t) t = 2.0 * (BM + c);
+                if (bytes_kb * active / 10000.0 > t) t = bytes_kb * active / 10000.0;
+                return t;
+            };
+            if (tiles >= ctx->sm_count) {
+                const int g = ctx->sm_count;
+                const int waves = (int)(tiles / g);
+                const int r = (int)(tiles % g);
+                const double chunk_t = kb_per_chunk * per_kb(g);
+                // (a) plain last wave: r CTAs run one more whole tile
+                double cost = ((double)waves + (r ? 1.0 : 0.0)) * cpt * chunk_t + 4000.0;
+                if (best < 0 || cost < best) { best = cost; bn = c; grid = g; dp_waves = waves; dp_extra = r; sk_units_total = 0; perm_s = 0; }
+                // (b) stream-K over the last wave.  Nearly every CTA parks two segments and re-reads
+                // two or three: ~1 MB of extra L2 traffic per CTA, all at the same time (measured:
+                // ~15 us for 148 CTAs with 128 x 256 tiles) — pays only when K is deep.
+                if (r) {
+                    const long sk = (long)r * cpt;
+                    const long sk_per_cta = (sk + g - 1) / g;
+                    cost = ((double)waves * cpt + (double)sk_per_cta) * chunk_t + 4000.0 + 30000.0 * c / 256.0;
+                    if (cost < best) { best = cost; bn = c; grid = g; dp_waves = waves; dp_extra = 0; sk_units_total = (int)sk; perm_s = 0; }
+                }
+            } else {
+                const int smax = cpt < 16 ? cpt : 16;
+                for (int sp = 1; sp <= smax; ++sp) {
+                    if (tiles * sp > ctx->sm_count) break;
+                    const int g = (int)tiles * sp;
+                    const long per_cta = (cpt + sp - 1) / sp;
+                    // park + ticket + the last arriver's pass over sp segments (a serial tail)
+                    double cost = (double)per_cta * kb_per_chunk * per_kb(g) + 4000.0 + (sp > 1 ? (6000.0 + 2500.0 * sp) * c / 256.0 : 0.0);
+                    if (cpt % sp != 0) cost *= 1.15;  // ranges cross tile boundaries: lockstep is lost
+                    if (best < 0 || cost < best) {
+                        best = cost; bn = c; grid = g; dp_waves = 0; dp_extra = 0; sk_units_total = (int)(tiles * cpt);
+                        perm_s = (sp > 1 && cpt % sp == 0) ? sp : 0;
+                    }
+                }
             }
         }
+        if (best < 0) return 1;
     }
     Params p;
     p.m = m; p.n = n; p.num_kb = num_kb;
     p.tiles_m = tiles_m;
     p.tiles_n = (n + bn - 1) / bn;
-    const int chunks_per_split = (chunks + splits - 1) / splits;
-    splits = (chunks + chunks_per_split - 1) / chunks_per_split;
-    p.splits = splits;
-    p.kb_per_split = chunks_per_split * kChunkKb;
+    p.cpt = cpt;
+    const long tiles = (long)p.tiles_m * p.tiles_n;
+    p.dp_waves = dp_waves;
+    p.dp_tiles = dp_waves * grid;
+    p.dp_extra = dp_extra;
+    p.perm_s = perm_s;
+    p.perm_tiles = perm_s ? (int)tiles : 0;
+    p.base = sk_units_total / grid;
+    p.rem = sk_units_total % grid;
+    static const bool debug_plan = [] { const char* e = getenv("DSC_GEMM_DEBUG"); return e && *e == '1'; }();
+    if (debug_plan)
+        fprintf(stderr, "[dsc gemm] m=%d n=%d k=%d ta=%d tb=%d: BN=%d grid=%d cpt=%d dp_waves=%d dp_extra=%d sk_units=%d perm_s=%d\n", m, n, k, ta, tb, bn,
+                grid, cpt, dp_waves, dp_extra, sk_units_total, perm_s);
+    DSC_TRY(ensure_gemm_tickets(ctx, (size_t)tiles));
+    p.tickets = ctx->gemm_tickets;
 
     // op(A)(m x k): stored m x k (K contiguous) unless ta; op(B)(k x n): stored n x k (K contiguous) only if tb
     const OperandPlan pa = plan_operand(A, !ta, m, k, kp), pb = plan_operand(B, tb != 0, n, k, kp);
     const size_t a_floats = (pa.ws_floats + 255) & ~size_t(255), b_floats = (pb.ws_floats + 255) & ~size_t(255);
     const size_t planes_bytes = (a_floats + b_floats) * sizeof(float);
-    const size_t partial_bytes = splits > 1 ? (size_t)splits * m * n * sizeof(float) : 0;
-    DSC_TRY(ensure_gemm_ws(ctx, planes_bytes + partial_bytes + 2048));
+    const size_t slot_bytes = (size_t)grid * 2 * BM * bn * sizeof(float);
+    DSC_TRY(ensure_gemm_ws(ctx, planes_bytes + slot_bytes + 2048));
     char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ctx->gemm_ws) + 1023) & ~uintptr_t(1023));
     float* ws = reinterpret_cast<float*>(base);
     // direct: [lo]; planes: [hi | lo]
@@ -637,7 +764,7 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
     float* b_lo = pb.direct ? ws + a_floats : ws + a_floats + (size_t)n * kp;
     const float* a_hi = pa.direct ? A : ws;
     const float* b_hi = pb.direct ? B : ws + a_floats;
-    float* partial = splits > 1 ? reinterpret_cast<float*>(base + planes_bytes) : nullptr;
+    p.slots = reinterpret_cast<float*>(base + planes_bytes);
 
     // ---- (1) split pre-pass ----
     {
@@ -648,9 +775,9 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
     }
 
     // ---- (2) tensor-core kernel ----
-    p.C = splits > 1 ? partial : C;
-    p.bias = splits > 1 ? nullptr : bias;
-    p.vec4 = ((n % 4) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    p.C = C;
+    p.bias = bias;
+    p.vec4 = ((n % 4) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
     p.a_mn = pa.mn_major ? 1 : 0;
     p.b_mn = pb.mn_major ? 1 : 0;
     CUtensorMap maps[4];
@@ -671,18 +798,10 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
         DSC_TRY(make_map(&maps[3], b_lo, kk, n, (size_t)kk, bn));
     }
     int s;
-    if (bn == 256) s = launch<256>(ctx, maps, p);
-    else if (bn == 128) s = launch<128>(ctx, maps, p);
-    else s = launch<64>(ctx, maps, p);
+    if (bn == 256) s = launch<256>(ctx, maps, p, grid);
+    else if (bn == 128) s = launch<128>(ctx, maps, p, grid);
+    else s = launch<64>(ctx, maps, p, grid);
     if (s != DSC_OK) return s;
-
-    // ---- (3) split-K reduction in split order ----
-    if (splits > 1) {
-        const int v4 = ((n % 4) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-        const int grid = grid_for((size_t)m * n / (v4 ? 4 : 1), 256 * 2, ctx->sm_count * 8);
-        splitk_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(partial, bias, C, m, n, splits, v4);
-        DSC_LAUNCH_CHECK(ctx);
-    }
     ctx->stats.gemm_tcgen05++;
     return DSC_OK;
 }

@@ -91,6 +91,8 @@ struct Ctx {
     // GEMM operand-split workspace (3xTF32 hi/lo planes)
     void* gemm_ws = nullptr;
     size_t gemm_ws_bytes = 0;
+    unsigned int* gemm_tickets = nullptr;   // one arrival counter per output tile (stream-K fix-up), zero between launches
+    size_t gemm_tickets_n = 0;
     // NCCL
     void* nccl_comm = nullptr;
     void* comm_stage = nullptr;    // contiguous staging buffer for packed all-reduces
@@ -165,6 +167,7 @@ int in_buf(Ctx* ctx, int dtype, dsc_buf_t h, Buf** res, const char* what);
 int buf_writable(Ctx* ctx, Buf* b);
 int ensure_red_scratch(Ctx* ctx, size_t bytes);
 int ensure_gemm_ws(Ctx* ctx, size_t bytes);
+int ensure_gemm_tickets(Ctx* ctx, size_t count);
 
 inline int grid_for(size_t work_items, int per_block, int max_blocks) {
     size_t b = (work_items + per_block - 1) / per_block;

@@ -270,10 +270,14 @@ int colsum_launch(Ctx* ctx, const T* M, T* v, int m, int n) {
     bool vec = (n % W == 0) && al16(M);
     int cols_per_block = vec ? 32 * W : 32;
     int gx = (n + cols_per_block - 1) / cols_per_block;
-    // 64-row slabs (every thread issues its 8 loads at once) unless that leaves the machine idle or
-    // makes more than 512 partial rows
+    // slabs of 64 rows (every thread issues its 8 loads at once), more when a slab would hold less
+    // than 16 KB (narrow matrices: the fence + ticket per CTA costs more than its loads) or when
+    // there would be more than 512 partial rows
     int rows_per_chunk = 64;
-    while (rows_per_chunk > 8 && (long)gx * ((m + rows_per_chunk - 1) / rows_per_chunk) < ctx->sm_count * 2) rows_per_chunk /= 2;
+    {
+        const size_t row_bytes = (size_t)(n < cols_per_block ? n : cols_per_block) * sizeof(T);
+        while ((size_t)rows_per_chunk * row_bytes < 16384 && rows_per_chunk < m) rows_per_chunk *= 2;
+    }
     while ((m + rows_per_chunk - 1) / rows_per_chunk > 512) rows_per_chunk *= 2;
     int chunks = (m + rows_per_chunk - 1) / rows_per_chunk;
     if (gx > kNumTickets) return fail(DSC_E_SHAPE, "Add_M_Colwise_V_InPlace: %d columns exceed the supported maximum", n);
