@@ -113,6 +113,8 @@ typedef struct dsc_stats {
     uint64_t gemm_tcgen05;        /* f32 GEMMs served by the tcgen05/TMEM/TMA 3xTF32 kernel         */
     uint64_t gemm_dmma;           /* f64 GEMMs served by the DMMA kernel                            */
     uint64_t gemm_simt;           /* GEMMs served by the CUDA-core kernels                          */
+    uint64_t allreduce_p2p;       /* all-reduces served by the peer-memory (NVLink P2P) kernel      */
+    uint64_t allreduce_nccl;      /* all-reduces served by NCCL                                     */
 } dsc_stats;
 
 /* ---------------------------------------------------------------- lifecycle ---------------- */
@@ -248,7 +250,7 @@ DSC_API int dsc_host_free_pinned(void* p);
     DSC_API int dsc_##P##getri(dsc_ctx_t ctx, int32_t n, dsc_buf_t A, dsc_buf_t* Ainv);                           \
     /* Inverse_M (Backend.fs:125)                                                                              */ \
     DSC_API int dsc_##P##det(dsc_ctx_t ctx, int32_t n, dsc_buf_t A, T* out);    /* Det_M       Backend.fs:126 */ \
-    /* ---- collectives (new; NCCL over NVLink, on the context's communication stream) ----                    */ \
+    /* ---- collectives (new): all-reduce = one peer-memory kernel over NVLink (NCCL when P2P is unavailable) ---- */ \
     DSC_API int dsc_##P##allreduce_sum(dsc_ctx_t ctx, int32_t count, const dsc_buf_t* bufs);                      \
     DSC_API int dsc_##P##allgather(dsc_ctx_t ctx, dsc_buf_t send, dsc_buf_t recv);
 

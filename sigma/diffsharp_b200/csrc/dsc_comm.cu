@@ -1,12 +1,31 @@
-// C1: NCCL glue.  New surface (the reference has no collective): one communicator per
-// context (= per process = per GPU).  Collectives run on the context's communication stream, ordered
-// after the producing kernels by an event, so the all-reduce of one layer's weight adjoints overlaps
-// the rest of the reverse sweep; dsc_comm_join() orders the compute stream after them.
+// C1: collectives.  New surface (the reference has no collective): one communicator per
+// context (= per process = per GPU).
+//
+// Sum of the weight adjoints (dsc_?allreduce_sum), up to 8 GPUs of one NVSwitch node: ONE kernel over
+// peer memory.  Every rank owns a symmetric buffer (flags | region A | region B) that all peers map
+// through CUDA IPC at dsc_comm_init.  The kernel (64 CTAs on the compute stream, captured in the
+// step's CUDA graph like any other kernel)
+//   0. packs the rank's adjoint buffers into its region A,
+//   1. barrier (flags written into every peer's memory with release stores, acquire spins),
+//   2. reduce-scatter + all-gather in one pass: rank r adds slice r of all N regions A — P2P loads
+//      over NVLink, peers added in rank order 0..N-1, so the sum is bit-identical on every rank and
+//      from run to run — and stores the result into region B of EVERY rank (P2P stores),
+//   3. barrier,
+//   4. unpacks region B into the adjoint buffers.
+// 7.45 MB over 8 GPUs: ~6.5 MB in and out per GPU instead of NCCL's pack -> ring/tree -> unpack
+// (measured 110 us); no staging copies on the NCCL stream, no event hand-offs.
+// NCCL remains for the bootstrap (exchange of the IPC handles), for the Jacobian all-gather, and
+// as the all-reduce path when peer access is not available (more than 8 ranks, no P2P, payload
+// larger than the symmetric buffer).  Collectives issued through NCCL run on the context's
+// communication stream, ordered after the producing kernels by an event; dsc_comm_join() orders
+// the compute stream after them.
 //
 // NCCL is resolved with dlopen at dsc_comm_init time so that the library loads (and every
 // single-GPU path runs) on machines without libnccl, and so that a process that already carries
 // torch's bundled libnccl.so.2 shares that one copy instead of loading a second one.
 #include <dlfcn.h>
+
+#include <type_traits>
 
 #include "dsc_internal.cuh"
 
@@ -15,8 +34,8 @@ namespace dsc {
 typedef struct { char internal[128]; } nccl_unique_id;
 typedef void* nccl_comm_t;
 enum { NCCL_SUCCESS = 0 };
-enum { NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8 };  // ncclDataType_t values (nccl.h)
-enum { NCCL_SUM = 0 };
+enum { NCCL_UINT8 = 1, NCCL_INT32 = 2, NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8 };  // ncclDataType_t values (nccl.h)
+enum { NCCL_SUM = 0, NCCL_MIN = 3 };
 
 struct NcclApi {
     void* lib = nullptr;
@@ -94,6 +113,145 @@ __global__ void pack_kernel(PackTable<T> t, T* __restrict__ stage) {
     }
 }
 
+// ---- peer-memory all-reduce ---------------------------------------------------------------------
+constexpr int kP2PMaxRanks = 8;
+constexpr int kP2PMaxCtas = 148;
+constexpr int kP2PThreads = 512;
+constexpr size_t kP2PHeaderBytes = 4096;              // flags[8] at 0, sync words at 256: [0] CTA counter, [1] epoch, [2] error
+constexpr size_t kP2PRegionBytes = size_t(32) << 20;  // region A and region B: 32 MB each
+
+struct P2PArgs {
+    char* peer[kP2PMaxRanks];  // every rank's symmetric buffer as mapped here
+    int nranks, rank;
+    size_t region_bytes;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// All CTAs of this rank have finished the phase -> tell every peer (flag[rank] = value in the peer's
+// header) -> wait until every peer has told us.  `arrivals` is the cumulative CTA count expected at
+// the local counter.  A 4 s timeout turns a lost peer into an error word instead of a hung GPU.
+__device__ __forceinline__ void p2p_barrier(const P2PArgs& a, unsigned int value, unsigned int arrivals, bool reset_counter) {
+    unsigned int* flags = reinterpret_cast<unsigned int*>(a.peer[a.rank]);
+    unsigned int* sync = reinterpret_cast<unsigned int*>(a.peer[a.rank] + 256);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (atomicAdd(&sync[0], 1u) == arrivals - 1u) {
+            if (reset_counter) sync[0] = 0;
+            for (int q = 0; q < a.nranks; ++q) st_release_sys(reinterpret_cast<unsigned int*>(a.peer[q]) + a.rank, value);
+        }
+    }
+    if (threadIdx.x < (unsigned)a.nranks) {
+        const unsigned long long t0 = globaltimer_ns();
+        while ((int)(ld_acquire_sys(flags + threadIdx.x) - value) < 0) {
+            if (globaltimer_ns() - t0 > 4000000000ull) {
+                sync[2] = 1;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// The buffers of one call laid out in the symmetric regions: every segment starts on a 16-byte
+// boundary (the gaps stay zero: regions are zeroed once and gaps are never written with anything but
+// sums of zeros), so an aligned source buffer is moved with 128-bit accesses.
+template <typename T>
+struct P2PTable {
+    T* ptr[kMaxPack];
+    long long start[kMaxPack + 1];  // element offset of each segment in the region; multiples of 16 / sizeof(T)
+    int len[kMaxPack];
+    int count;
+};
+
+// buffers <-> region (PACK: buffers -> region).  Grid-stride per segment, 128-bit when the buffer is aligned.
+template <typename T, bool PACK>
+__device__ __forceinline__ void p2p_move(const P2PTable<T>& t, T* __restrict__ region, long long gtid, long long gsize) {
+    using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+    constexpr int W = 16 / (int)sizeof(T);
+    for (int s = 0; s < t.count; ++s) {
+        T* p = t.ptr[s];
+        T* r = region + t.start[s];
+        const long long n = t.len[s];
+        long long done = 0;
+        if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+            const long long nv = n / W;
+            V* pv = reinterpret_cast<V*>(p);
+            V* rv = reinterpret_cast<V*>(r);
+#pragma unroll 4
+            for (long long i = gtid; i < nv; i += gsize) {
+                if (PACK) rv[i] = pv[i];
+                else pv[i] = __ldcg(rv + i);
+            }
+            done = nv * W;
+        }
+        for (long long i = done + gtid; i < n; i += gsize) {
+            if (PACK) r[i] = p[i];
+            else p[i] = __ldcg(r + i);
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kP2PThreads) allreduce_p2p_kernel(P2PTable<T> t, P2PArgs a) {
+    using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+    constexpr int W = 16 / (int)sizeof(T);
+    char* local = a.peer[a.rank];
+    unsigned int* sync = reinterpret_cast<unsigned int*>(local + 256);
+    const unsigned int epoch = sync[1];   // bumped by CTA 0 after the second barrier: every CTA has read it by then
+    const long long total = t.start[t.count];   // multiple of W
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x, gsize = (long long)gridDim.x * blockDim.x;
+    T* regA = reinterpret_cast<T*>(local + kP2PHeaderBytes);
+    T* regB = reinterpret_cast<T*>(local + kP2PHeaderBytes + a.region_bytes);
+    // 0. pack
+    p2p_move<T, true>(t, regA, gtid, gsize);
+    // 1. every rank has packed
+    p2p_barrier(a, 2u * epoch + 1u, gridDim.x, false);
+    // 2. slice `rank` of the sum: all peer loads of a vector are in flight together (one NVLink round
+    //    trip per vector, not one per peer), added in rank order; the result goes to region B of every rank
+    const long long nvec = total / W;
+    const long long per = (nvec + a.nranks - 1) / a.nranks;
+    const long long v0 = per * a.rank, v1 = min(nvec, v0 + per);
+    for (long long v = v0 + gtid; v < v1; v += gsize) {
+        V x[kP2PMaxRanks];
+#pragma unroll
+        for (int p = 0; p < kP2PMaxRanks; ++p)
+            if (p < a.nranks) x[p] = __ldcg(reinterpret_cast<const V*>(a.peer[p] + kP2PHeaderBytes) + v);
+        V acc = x[0];
+#pragma unroll
+        for (int p = 1; p < kP2PMaxRanks; ++p)
+            if (p < a.nranks) {
+                acc.x += x[p].x; acc.y += x[p].y;
+                if constexpr (W == 4) { acc.z += x[p].z; acc.w += x[p].w; }
+            }
+#pragma unroll
+        for (int q = 0; q < kP2PMaxRanks; ++q)
+            if (q < a.nranks) reinterpret_cast<V*>(a.peer[q] + kP2PHeaderBytes + a.region_bytes)[v] = acc;
+    }
+    // 3. every slice has landed everywhere
+    p2p_barrier(a, 2u * epoch + 2u, 2u * gridDim.x, true);
+    // 4. unpack
+    p2p_move<T, false>(t, regB, gtid, gsize);
+    // the CTA counter was reset by the last arriver of barrier 3; the epoch is bumped by CTA 0 after
+    // ITS threads left that barrier (all CTAs read the epoch before arriving at barrier 1)
+    if (blockIdx.x == 0 && threadIdx.x == 0) sync[1] = epoch + 1u;
+}
+
+static int p2p_setup(Ctx* ctx);
+
 template <typename T>
 static int allreduce_impl(dsc_ctx_t c, int32_t count, const dsc_buf_t* bufs) {
     if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
@@ -117,6 +275,34 @@ static int allreduce_impl(dsc_ctx_t c, int32_t count, const dsc_buf_t* bufs) {
     if (t.count == 0) return DSC_OK;
     const int dt = sizeof(T) == 4 ? NCCL_FLOAT32 : NCCL_FLOAT64;
     const long long total = t.start[t.count];
+    if (ctx->p2p_ok && (size_t)(total + 4 * t.count) * sizeof(T) <= ctx->p2p_region_bytes) {
+        // one kernel over peer memory on the compute stream (ordered after the producers by stream order)
+        if (ctx->comm_pending) {   // a collective issued through NCCL may still be writing these buffers
+            DSC_CUDA_CHECK(cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
+            DSC_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
+        }
+        constexpr long long W = 16 / (long long)sizeof(T);
+        P2PTable<T> pt;
+        pt.count = t.count;
+        pt.start[0] = 0;
+        for (int i = 0; i < t.count; ++i) {
+            pt.ptr[i] = t.ptr[i];
+            pt.len[i] = (int)(t.start[i + 1] - t.start[i]);
+            pt.start[i + 1] = pt.start[i] + (pt.len[i] + W - 1) / W * W;
+        }
+        P2PArgs a;
+        for (int r = 0; r < kP2PMaxRanks; ++r) a.peer[r] = reinterpret_cast<char*>(ctx->p2p_peer[r]);
+        a.nranks = ctx->nranks;
+        a.rank = ctx->rank;
+        a.region_bytes = ctx->p2p_region_bytes;
+        // one CTA per SM: all CTAs must be resident at once (they meet at two grid-wide barriers)
+        const int ctas = ctx->sm_count < kP2PMaxCtas ? ctx->sm_count : kP2PMaxCtas;
+        allreduce_p2p_kernel<T><<<ctas, kP2PThreads, 0, ctx->stream>>>(pt, a);
+        DSC_LAUNCH_CHECK(ctx);
+        ctx->stats.allreduce_p2p++;
+        return DSC_OK;
+    }
+    ctx->stats.allreduce_nccl++;
     if (t.count == 1) {
         DSC_TRY(comm_fork(ctx));
         DSC_NCCL_CHECK(g_nccl.AllReduce(t.ptr[0], t.ptr[0], (size_t)total, dt, NCCL_SUM, ctx->nccl_comm, ctx->comm_stream));
@@ -173,6 +359,71 @@ static int allgather_impl(dsc_ctx_t c, dsc_buf_t sendh, dsc_buf_t recvh) {
     return DSC_OK;
 }
 
+// Map every rank's symmetric buffer into this process.  Collective: every rank must call it; the
+// outcome (p2p_ok) is agreed with a MIN all-reduce so that no rank takes the peer path alone.
+static int p2p_setup(Ctx* ctx) {
+    ctx->p2p_ok = false;
+    const char* off = getenv("DSC_P2P");
+    int ok = (ctx->nranks >= 2 && ctx->nranks <= kP2PMaxRanks && !(off && *off == '0')) ? 1 : 0;
+    int ndev = 0;
+    if (ok && (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < ctx->nranks)) ok = 0;
+    const size_t bytes = kP2PHeaderBytes + 2 * kP2PRegionBytes;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (ok) {
+        if (cudaMalloc(&ctx->p2p_local, bytes) != cudaSuccess) { cudaGetLastError(); ctx->p2p_local = nullptr; ok = 0; }
+    }
+    if (ok) {
+        if (cudaMemset(ctx->p2p_local, 0, bytes) != cudaSuccess || cudaIpcGetMemHandle(&mine, ctx->p2p_local) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    }
+    // exchange (handle, ok) through NCCL: 64-byte handle + 4-byte flag per rank
+    constexpr int kRec = 128;
+    unsigned char* dev = nullptr;
+    DSC_CUDA_CHECK(cudaMalloc(&dev, (size_t)kRec * (ctx->nranks + 1)));
+    unsigned char host[kRec * (kP2PMaxRanks + 64)];
+    if (ctx->nranks > kP2PMaxRanks + 63) { cudaFree(dev); return DSC_OK; }
+    memset(host, 0, sizeof(host));
+    memcpy(host, &mine, sizeof(mine));
+    host[64] = (unsigned char)ok;
+    DSC_CUDA_CHECK(cudaMemcpyAsync(dev, host, kRec, cudaMemcpyHostToDevice, ctx->comm_stream));
+    DSC_NCCL_CHECK(g_nccl.AllGather(dev, dev + kRec, kRec, NCCL_UINT8, ctx->nccl_comm, ctx->comm_stream));
+    DSC_CUDA_CHECK(cudaMemcpyAsync(host, dev + kRec, (size_t)kRec * ctx->nranks, cudaMemcpyDeviceToHost, ctx->comm_stream));
+    DSC_CUDA_CHECK(cudaStreamSynchronize(ctx->comm_stream));
+    for (int r = 0; r < ctx->nranks; ++r) ok = ok && host[r * kRec + 64];
+    if (ok) {
+        for (int r = 0; r < ctx->nranks && ok; ++r) {
+            if (r == ctx->rank) { ctx->p2p_peer[r] = ctx->p2p_local; continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, host + r * kRec, sizeof(h));
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+            ctx->p2p_peer[r] = ptr;
+        }
+    }
+    // second agreement round: did every rank manage to open every peer?
+    host[0] = (unsigned char)ok;
+    DSC_CUDA_CHECK(cudaMemcpyAsync(dev, host, kRec, cudaMemcpyHostToDevice, ctx->comm_stream));
+    DSC_NCCL_CHECK(g_nccl.AllGather(dev, dev + kRec, kRec, NCCL_UINT8, ctx->nccl_comm, ctx->comm_stream));
+    DSC_CUDA_CHECK(cudaMemcpyAsync(host, dev + kRec, (size_t)kRec * ctx->nranks, cudaMemcpyDeviceToHost, ctx->comm_stream));
+    DSC_CUDA_CHECK(cudaStreamSynchronize(ctx->comm_stream));
+    for (int r = 0; r < ctx->nranks; ++r) ok = ok && host[r * kRec];
+    cudaFree(dev);
+    ctx->p2p_ok = ok != 0;
+    ctx->p2p_region_bytes = ok ? kP2PRegionBytes : 0;
+    return DSC_OK;
+}
+
+static void p2p_teardown(Ctx* ctx) {
+    for (int r = 0; r < kP2PMaxRanks; ++r) {
+        if (ctx->p2p_peer[r] && ctx->p2p_peer[r] != ctx->p2p_local) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
+        ctx->p2p_peer[r] = nullptr;
+    }
+    if (ctx->p2p_local) cudaFree(ctx->p2p_local);
+    ctx->p2p_local = nullptr;
+    ctx->p2p_ok = false;
+    ctx->p2p_region_bytes = 0;
+}
+
 }  // namespace dsc
 
 using namespace dsc;
@@ -204,7 +455,7 @@ int dsc_comm_init(dsc_ctx_t c, int nranks, int rank, const uint8_t idbytes[128])
     nccl_comm_t comm = nullptr;
     DSC_NCCL_CHECK(g_nccl.CommInitRank(&comm, nranks, id, rank));
     ctx->nccl_comm = comm;
-    return DSC_OK;
+    return p2p_setup(ctx);
 }
 
 int dsc_comm_join(dsc_ctx_t c) {
@@ -220,13 +471,18 @@ int dsc_comm_join(dsc_ctx_t c) {
 int dsc_comm_destroy(dsc_ctx_t c) {
     if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
     Ctx* ctx = as_ctx(c);
+    unsigned int p2p_err = 0;
     if (ctx->nccl_comm) {
+        cudaStreamSynchronize(ctx->stream);
         cudaStreamSynchronize(ctx->comm_stream);
+        if (ctx->p2p_local) cudaMemcpy(&p2p_err, reinterpret_cast<char*>(ctx->p2p_local) + 256 + 8, 4, cudaMemcpyDeviceToHost);
+        p2p_teardown(ctx);
         g_nccl.CommDestroy(ctx->nccl_comm);
         ctx->nccl_comm = nullptr;
     }
     ctx->nranks = 1;
     ctx->rank = 0;
+    if (p2p_err) return fail(DSC_E_NCCL, "a peer-memory all-reduce timed out waiting for a peer (results of that step are invalid)");
     return DSC_OK;
 }
 

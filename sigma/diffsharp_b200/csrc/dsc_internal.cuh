@@ -98,6 +98,11 @@ struct Ctx {
     void* comm_stage = nullptr;    // contiguous staging buffer for packed all-reduces
     size_t comm_stage_bytes = 0;
     int nranks = 1, rank = 0;
+    // peer-memory all-reduce (dsc_comm.cu): one symmetric buffer per rank, opened on every peer through CUDA IPC
+    bool p2p_ok = false;
+    void* p2p_local = nullptr;          // this rank's symmetric buffer: [flags | sync words | region A | region B]
+    void* p2p_peer[8] = {nullptr};      // the same buffer of every rank as mapped into this process (p2p_peer[rank] == p2p_local)
+    size_t p2p_region_bytes = 0;        // capacity of region A (= region B)
     dsc_stats stats{};
     int sm_count = kNumSMs;
     size_t smem_optin = 0;

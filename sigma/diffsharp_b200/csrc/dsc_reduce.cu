@@ -3,8 +3,9 @@
 //
 // One launch per reduction.  The element -> thread assignment and the combine tree are functions
 // of n only (fixed grid, fixed per-thread stride, warp-shuffle tree, shared-memory tree over warps,
-// and a last-block pass over the per-block partials in block order), so the result is bit-identical
-// from run to run.  HBM-bound: 128-bit loads, 4 independent accumulators per thread.
+// then two ticketed levels over the per-block partials: groups of 32 blocks, then the groups, each
+// added in index order by whichever block arrives last), so the result is bit-identical from run
+// to run.  HBM-bound: 128-bit loads, 8 independent accumulators per thread.
 #include <float.h>
 #include <stdlib.h>
 
@@ -13,7 +14,7 @@
 namespace dsc {
 
 constexpr int kRThreads = 256;
-constexpr int kRUnroll = 4;
+constexpr int kRUnroll = 8;
 constexpr int kMaxPartials = 148 * 16;
 
 enum { R_SUM = 0, R_ASUM = 1, R_SUMSQ = 2, R_AMAX = 3, R_DOT = 4 };
@@ -54,12 +55,12 @@ __device__ __forceinline__ T block_tree(T v, T* smem) {
     return v;  // valid in thread 0
 }
 
-// scratch layout: [0] ticket (uint32), [64..) T result, [256..) partials
+// scratch layout: [64..) T result, [256..) block partials, then group partials; tickets: ctx->tickets
 // Each CTA owns a CONTIGUOUS chunk of `iters` x kRUnroll x kRThreads vectors (same finding as the
 // elementwise kernels: contiguous chunks stream faster than a grid-wide stride).
 template <int KIND, typename T, bool VEC>
 __global__ void __launch_bounds__(kRThreads) reduce_kernel(const T* __restrict__ a, const T* __restrict__ b, size_t n, int iters,
-                                                            unsigned int* ticket, T* partials, T* result) {
+                                                            unsigned int* tickets, T* partials, T* result) {
     __shared__ T smem[kRThreads / 32];
     T acc[kRUnroll];
 #pragma unroll
@@ -103,7 +104,8 @@ __global__ void __launch_bounds__(kRThreads) reduce_kernel(const T* __restrict__
             }
         }
     }
-    T v = r_comb<KIND>(r_comb<KIND>(acc[0], acc[1]), r_comb<KIND>(acc[2], acc[3]));
+    T v = r_comb<KIND>(r_comb<KIND>(r_comb<KIND>(acc[0], acc[1]), r_comb<KIND>(acc[2], acc[3])),
+                       r_comb<KIND>(r_comb<KIND>(acc[4], acc[5]), r_comb<KIND>(acc[6], acc[7])));
     v = block_tree<KIND>(v, smem);
     // Only warp 0 takes part in the grid-level hand-off: the other warps retire at once, so the round
     // trip of the ticket atomic does not hold the CTA's slots (it cost ~9 us per launch when it did).
@@ -112,23 +114,48 @@ __global__ void __launch_bounds__(kRThreads) reduce_kernel(const T* __restrict__
         if (threadIdx.x == 0) *result = v;
         return;
     }
+    // level 1: groups of 32 blocks; the last block of a group adds the group's partials (one per lane)
+    constexpr unsigned G = 32;
+    const unsigned ngroups = (gridDim.x + G - 1) / G;
+    const unsigned g = blockIdx.x / G, g_first = g * G;
+    const unsigned g_size = min(G, gridDim.x - g_first);
     unsigned int t = 0;
     if (threadIdx.x == 0) {
         partials[blockIdx.x] = v;
         __threadfence();
-        t = atomicAdd(ticket, 1u);
+        t = atomicAdd(&tickets[1 + g], 1u);
     }
     t = __shfl_sync(0xffffffffu, t, 0);
-    if (t != gridDim.x - 1) return;
+    if (t != g_size - 1) return;
     __threadfence();
-    // last CTA: warp 0 adds the partials in a fixed order (lane-strided, then the shuffle tree)
-    T w = T(0);
-    for (unsigned int i = threadIdx.x; i < gridDim.x; i += 32) w = r_comb<KIND>(w, partials[i]);
+    T w = threadIdx.x < g_size ? __ldcg(partials + g_first + threadIdx.x) : T(0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w = r_comb<KIND>(w, __shfl_xor_sync(0xffffffffu, w, o));
+    if (ngroups == 1) {
+        if (threadIdx.x == 0) {
+            *result = w;
+            tickets[1 + g] = 0;
+        }
+        return;
+    }
+    // level 2: the last group adds the group sums (lane-strided in index order, then the shuffle tree)
+    T* partials2 = partials + kMaxPartials;
+    if (threadIdx.x == 0) {
+        partials2[g] = w;
+        tickets[1 + g] = 0;
+        __threadfence();
+        t = atomicAdd(&tickets[0], 1u);
+    }
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t != ngroups - 1) return;
+    __threadfence();
+    w = T(0);
+    for (unsigned int i = threadIdx.x; i < ngroups; i += 32) w = r_comb<KIND>(w, __ldcg(partials2 + i));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) w = r_comb<KIND>(w, __shfl_xor_sync(0xffffffffu, w, o));
     if (threadIdx.x == 0) {
         *result = w;
-        *ticket = 0;
+        tickets[0] = 0;
     }
 }
 
@@ -213,7 +240,7 @@ static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) 
 // Launch a reduction leaving the scalar at `result` (device pointer).
 template <int KIND, typename T>
 static int launch_reduce(Ctx* ctx, const T* a, const T* b, size_t n, T* result) {
-    unsigned int* ticket = reinterpret_cast<unsigned int*>(ctx->red_scratch);
+    unsigned int* ticket = ctx->tickets;
     T* partials = reinterpret_cast<T*>(reinterpret_cast<char*>(ctx->red_scratch) + 256);
     bool vec = al16(a) && (KIND != R_DOT || al16(b));
     size_t items = vec ? n / RVec<T>::N : n;
@@ -221,7 +248,7 @@ static int launch_reduce(Ctx* ctx, const T* a, const T* b, size_t n, T* result) 
     // grid and per-CTA chunk are functions of n only (determinism)
     const size_t per_iter = (size_t)kRThreads * kRUnroll;
     size_t blocks1 = (items + per_iter - 1) / per_iter;
-    static const int max_partials = [] { const char* e = getenv("DSC_RED_MAXP"); int v = e ? atoi(e) : 0; return (v >= 1 && v <= 16384) ? v : kMaxPartials; }();
+    static const int max_partials = [] { const char* e = getenv("DSC_RED_MAXP"); int v = e ? atoi(e) : 0; return (v >= 1 && v <= kMaxPartials) ? v : kMaxPartials; }();
     int iters = (int)((blocks1 + max_partials - 1) / max_partials);
     if (iters < 1) iters = 1;
     int grid = (int)((items + per_iter * iters - 1) / (per_iter * iters));

@@ -1,5 +1,5 @@
-"""N > 1 on real GPUs: batch-row shards + ONE packed NCCL all-reduce of the adjoints reproduce the
-single-GPU gradient; tangent-row shards + all-gather reproduce the Jacobian.  Needs >= 2 GPUs
+"""N > 1 on real GPUs: batch-row shards + ONE all-reduce of the adjoints (peer-memory kernel over
+NVLink, NCCL when P2P is unavailable) reproduce the single-GPU gradient; tangent-row shards + all-gather reproduce the Jacobian.  Needs >= 2 GPUs
 (skipped on the 1-GPU box; the same host logic runs on CPU/gloo in test_dist_cpu.py)."""
 import ctypes as C
 import os
@@ -45,6 +45,37 @@ def _worker(rank, world, port, out):
     L, dW, db = D.sharded_mlp_grad(comm, wl.to_DM(X), wl.to_DM(Y), [wl.to_DM(w) for w in Ws], [wl.to_DV(b) for b in bs])
     comm.join()
     grads = [a.ToArray().copy() for a in dW + db]
+    # the all-reduce is deterministic and replayable: repeat it eagerly and from a CUDA graph on fresh
+    # copies of known data and compare against world * data (exact: every rank contributes the same values)
+    st = prov.ctx.stats()
+    rng = np.random.default_rng(5)
+    host = [rng.standard_normal(n).astype(np.float32) for n in (1000, 37, 4096 * 3 + 1)]
+    for use_graph in (False, True):
+        bufs = [CudaDataBuffer.from_host(prov.ctx, h) for h in host]
+        if use_graph:
+            comm.allreduce_sum(bufs); comm.join(); prov.ctx.sync()          # warm (sizes the staging buffers)
+            for b, h in zip(bufs, host):
+                b.upload(h)
+            prov.ctx.graph_begin()
+            try:
+                comm.allreduce_sum(bufs); comm.join()
+            finally:
+                g = prov.ctx.graph_end()
+            for rep in range(3):
+                for b, h in zip(bufs, host):
+                    b.upload(h)
+                prov.ctx.graph_launch(g)
+                prov.ctx.sync()
+                for b, h in zip(bufs, host):
+                    assert np.array_equal(b.SubData, h * np.float32(world)), ("graph", rep)
+            prov.ctx.graph_destroy(g)
+        else:
+            for rep in range(3):
+                comm.allreduce_sum(bufs); comm.join()
+            for b, h in zip(bufs, host):
+                assert np.array_equal(b.SubData, h * np.float32(world ** 3)), "eager"
+    st1 = prov.ctx.stats()
+    used_p2p = st1["allreduce_p2p"] - st["allreduce_p2p"]
     # config-4 shape in miniature: tangent rows sharded, all-gather at the end
     n = 64
     W1, b1, W2, b2, x = wl.jacobian_inputs(n)
@@ -55,7 +86,7 @@ def _worker(rank, world, port, out):
     comm.join()
     Jfull = full.SubData.reshape(n, n)
     if rank == 0:
-        out.put((float(L), grads, Jfull))
+        out.put((float(L), grads, Jfull, used_p2p, st1["allreduce_nccl"]))
     D.barrier()
     comm.close()
     dist.destroy_process_group()
@@ -70,7 +101,9 @@ def test_two_gpu_sharded_gradient_and_jacobian():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    L0, grads, Jfull = q.get()
+    L0, grads, Jfull, used_p2p, used_nccl = q.get()
+    print(f"all-reduces: peer-memory {used_p2p}, NCCL {used_nccl}")
+    assert used_p2p + used_nccl > 0
     for p in procs:
         p.join(180)
         assert p.exitcode == 0

@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Device time of the adjoint all-reduce of the config-3 step (six buffers, 1 863 690 f32 = 7.45 MB)
+in isolation: R all-reduces captured in one CUDA graph, max over ranks.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/allreduce_bench.py
+  DSC_P2P=0 ... (same)     # NCCL path (pack -> ncclAllReduce -> unpack) for comparison
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from sigma.diffsharp_b200 import dist as D  # noqa: E402
+from sigma.diffsharp_b200.buffers import CudaContext, CudaDataBuffer  # noqa: E402
+
+rank, world = D.init_process_group()
+ctx = CudaContext(int(os.environ.get("LOCAL_RANK", 0)))
+comm = D.NcclComm(ctx)
+sizes = (784 * 1024, 1024 * 1024, 1024 * 10, 1024, 1024, 10)
+rng = np.random.default_rng(rank)
+host = [rng.standard_normal(n).astype(np.float32) for n in sizes]
+bufs = [CudaDataBuffer.from_host(ctx, h) for h in host]
+for _ in range(3):
+    comm.allreduce_sum(bufs)
+    comm.join()
+ctx.sync()
+R = 20
+ctx.graph_begin()
+try:
+    for _ in range(R):
+        comm.allreduce_sum(bufs)
+        comm.join()
+finally:
+    g = ctx.graph_end()
+e0, e1 = ctx.event(), ctx.event()
+ctx.graph_launch(g)
+ctx.sync()
+best = 1e30
+for _ in range(5):
+    D.barrier()
+    ctx.record(e0)
+    ctx.graph_launch(g)
+    ctx.record(e1)
+    ctx.sync()
+    best = min(best, D.max_over_ranks(ctx.elapsed_ms(e0, e1)))
+st = ctx.stats()
+if rank == 0:
+    nbytes = sum(sizes) * 4
+    print(f"world {world}: all-reduce of {nbytes / 1e6:.2f} MB: {best / R * 1e3:.1f} us per call "
+          f"(peer-memory kernel calls {st['allreduce_p2p']}, NCCL calls {st['allreduce_nccl']})", flush=True)
+ctx.graph_destroy(g)
+D.barrier()
+comm.close()
