@@ -58,7 +58,7 @@ namespace tf32x3 {
 constexpr int BM = 128;
 constexpr int BK = 32;  // floats: 128 bytes = one SWIZZLE_128B row
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + 32 * kEpiWarps;  // warp0 TMA, warp1 MMA, 8 epilogue warps
+constexpr int kBaseThreads = 64 + 32 * kEpiWarps;  // warp0 TMA, warp1 MMA, 8 epilogue warps (+ converter warps, see Cfg)
 constexpr int kChunkKb = 8;                   // k-blocks per accumulation chunk (256 K-elements)
 constexpr int kAPlaneBytes = BM * BK * 4;
 
@@ -69,6 +69,11 @@ struct Cfg {
     static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
     static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator stages; power of two
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers, TMEM base, epilogue flag*/;
+    // Converter warps (in-kernel operand split): 128 x 256 tiles leave room for two smem stages only
+    // and 168 registers per epilogue thread, so that shape keeps the pre-pass; the narrower tiles
+    // compute their lo planes in shared memory.
+    static constexpr int kConvWarps = BN >= 256 ? 0 : 4;
+    static constexpr int kThreads = kBaseThreads + 32 * kConvWarps;
 };
 
 // ---- PTX helpers ------------------------------------------------------------------------------
@@ -194,6 +199,7 @@ struct Params {
     unsigned int* tickets;     // one arrival counter per tile (zero outside a launch)
     int vec4;                  // output rows are 16-byte aligned and n % 4 == 0
     int a_mn, b_mn;            // operand tiles are MN-major (source read in place, K index strided)
+    int a_fused, b_fused;      // the operand's lo tile is computed in shared memory by the converter warps (no lo plane in HBM)
 };
 
 __device__ __forceinline__ int unit_begin(const Params& p, int b) { return b * p.base + min(b, p.rem); }
@@ -214,8 +220,33 @@ __device__ __forceinline__ void unit_at(const Params& p, int i, int dp_units, in
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }
 
+// ---- in-kernel operand split ---------------------------------------------------------------------
+// lo = rna_tf32(x - trunc_tf32(x)) for one fp32 word as the tensor core will see it: x - hi is exact;
+// adding half a TF32 ulp to the bit pattern rounds the magnitude to nearest once the tensor core
+// drops the low 13 bits.  Non-finite x (x - hi = NaN) contributes through hi only.
+__device__ __forceinline__ float lo_word(float x) {
+    const float res = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    return res == res ? __uint_as_float(__float_as_uint(res) + 0x1000u) : 0.f;
+}
+// lo plane = f(hi plane), element by element (the swizzle is the same for both, so layout is irrelevant).
+// N4 float4 per plane, NT converter threads, 4 loads in flight per thread.
+template <int N4, int NT>
+__device__ __forceinline__ void convert_plane(const uint8_t* hi, uint8_t* lo, int ct) {
+    static_assert(N4 % (NT * 4) == 0 || N4 % (NT * 2) == 0, "plane size vs converter threads");
+    constexpr int U = (N4 % (NT * 4) == 0) ? 4 : 2;
+#pragma unroll
+    for (int j = 0; j < N4 / NT; j += U) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = *reinterpret_cast<const float4*>(hi + 16 * (ct + (j + u) * NT));
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            *reinterpret_cast<float4*>(lo + 16 * (ct + (j + u) * NT)) = make_float4(lo_word(v[u].x), lo_word(v[u].y), lo_word(v[u].z), lo_word(v[u].w));
+    }
+}
+
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(Cfg<BN>::kThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
                    const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, const Params p) {
     using cfg = Cfg<BN>;
@@ -223,14 +254,16 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
     // SWIZZLE_128B tiles need 1024-byte alignment
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = smem_base + cfg::kStages * cfg::kStageBytes;
-    // barrier slots (8 bytes each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then the TMEM base
+    // barrier slots (8 bytes each): full[kStages], empty[kStages], conv[kStages], tmem_full[2], tmem_empty[2], then the TMEM base
+    constexpr int kConv = cfg::kConvWarps;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (cfg::kStages + s); };
-    auto tfull_bar = [&](int a) { return bars + 8u * (2 * cfg::kStages + a); };
-    auto tempty_bar = [&](int a) { return bars + 8u * (2 * cfg::kStages + 2 + a); };
-    const uint32_t tmem_slot = bars + 8u * (2 * cfg::kStages + 4);
+    auto conv_bar = [&](int s) { return bars + 8u * (2 * cfg::kStages + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (3 * cfg::kStages + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (3 * cfg::kStages + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (3 * cfg::kStages + 4);
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + cfg::kStages * cfg::kStageBytes + 8 * (2 * cfg::kStages + 4));
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + cfg::kStages * cfg::kStageBytes + 8 * (3 * cfg::kStages + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -238,6 +271,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
         for (int s = 0; s < cfg::kStages; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
+            mbar_init(conv_bar(s), kConv > 0 ? kConv : 1);  // one arrival per converter warp
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
@@ -259,6 +293,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
     const int sk_begin = unit_begin(p, lb), sk_end = unit_begin(p, lb + 1);
     const int dp_units = (p.dp_waves + ((int)blockIdx.x < p.dp_extra ? 1 : 0)) * p.cpt;
     const int my_units = dp_units + (sk_end - sk_begin);
+    const bool a_fused = kConv > 0 && p.a_fused, b_fused = kConv > 0 && p.b_fused;
+    const uint32_t stage_tx = (uint32_t)((a_fused ? 1 : 2) * kAPlaneBytes + (b_fused ? 1 : 2) * cfg::kBPlaneBytes);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -274,25 +310,25 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     const uint32_t st = smem_base + s * cfg::kStageBytes;
-                    mbar_expect_tx(full_bar(s), cfg::kStageBytes);
+                    mbar_expect_tx(full_bar(s), stage_tx);
                     if (!p.a_mn) {
                         tma_load_2d(st, &map_ahi, full_bar(s), kb * BK, m0);
-                        tma_load_2d(st + kAPlaneBytes, &map_alo, full_bar(s), kb * BK, m0);
+                        if (!a_fused) tma_load_2d(st + kAPlaneBytes, &map_alo, full_bar(s), kb * BK, m0);
                     } else {
 #pragma unroll
                         for (int i = 0; i < BM / 32; ++i) {
                             tma_load_2d(st + i * 4096, &map_ahi, full_bar(s), m0 + 32 * i, kb * BK);
-                            tma_load_2d(st + kAPlaneBytes + i * 4096, &map_alo, full_bar(s), m0 + 32 * i, kb * BK);
+                            if (!a_fused) tma_load_2d(st + kAPlaneBytes + i * 4096, &map_alo, full_bar(s), m0 + 32 * i, kb * BK);
                         }
                     }
                     if (!p.b_mn) {
                         tma_load_2d(st + 2 * kAPlaneBytes, &map_bhi, full_bar(s), kb * BK, n0);
-                        tma_load_2d(st + 2 * kAPlaneBytes + cfg::kBPlaneBytes, &map_blo, full_bar(s), kb * BK, n0);
+                        if (!b_fused) tma_load_2d(st + 2 * kAPlaneBytes + cfg::kBPlaneBytes, &map_blo, full_bar(s), kb * BK, n0);
                     } else {
 #pragma unroll
                         for (int i = 0; i < BN / 32; ++i) {
                             tma_load_2d(st + 2 * kAPlaneBytes + i * 4096, &map_bhi, full_bar(s), n0 + 32 * i, kb * BK);
-                            tma_load_2d(st + 2 * kAPlaneBytes + cfg::kBPlaneBytes + i * 4096, &map_blo, full_bar(s), n0 + 32 * i, kb * BK);
+                            if (!b_fused) tma_load_2d(st + 2 * kAPlaneBytes + cfg::kBPlaneBytes + i * 4096, &map_blo, full_bar(s), n0 + 32 * i, kb * BK);
                         }
                     }
                     if (++s == cfg::kStages) { s = 0; ph ^= 1u; }
@@ -318,6 +354,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
                 for (int kb = c0; kb < c1; ++kb) {
                     mbar_wait(full_bar(s), ph);        // TMA bytes have landed
+                    if (kConv > 0) mbar_wait(conv_bar(s), ph);  // ... and the converter warps have written the lo tiles
                     tcgen05_fence_after();
                     const uint32_t st = smem_base + s * cfg::kStageBytes;
                     const uint64_t ahi = p.a_mn ? make_mnmajor_sw128_desc(st) : make_kmajor_sw128_desc(st);
@@ -339,6 +376,28 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                 if (++as == 2) { as = 0; aph ^= 1u; }
             }
         }
+    } else if (kConv > 0 && warp >= 2 + kEpiWarps) {
+        // ===================== converter warps: lo tiles from hi tiles, in shared memory =====================
+        constexpr int NT = 32 * (kConv > 0 ? kConv : 1);
+        const int ct = (int)threadIdx.x - 32 * (2 + kEpiWarps);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int i = 0; i < my_units; ++i) {
+            int tile, chunk;
+            unit_at(p, i, dp_units, sk_begin, tile, chunk);
+            const int kb0 = chunk * kChunkKb;
+            const int kb1 = min(p.num_kb, kb0 + kChunkKb);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(full_bar(s), ph);
+                uint8_t* st = smem_gen + s * cfg::kStageBytes;
+                if (a_fused) convert_plane<kAPlaneBytes / 16, NT>(st, st + kAPlaneBytes, ct);
+                if (b_fused) convert_plane<cfg::kBPlaneBytes / 16, NT>(st + 2 * kAPlaneBytes, st + 2 * kAPlaneBytes + cfg::kBPlaneBytes, ct);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to tcgen05.mma
+                __syncwarp();
+                if (lane == 0) mbar_arrive(conv_bar(s));
+                if (++s == cfg::kStages) { s = 0; ph ^= 1u; }
+            }
+        }
     } else {
         // ===================== epilogue warps 2..9 =====================
         // warp w may touch the TMEM lanes of quadrant (w & 3); the two warps of a quadrant split the
@@ -348,7 +407,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
         const int quad = warp & 3;
         const int half = (warp - 2) >> 2;
         const int trow = quad * 32 + lane;          // row inside the tile
-        int* s_flag = reinterpret_cast<int*>(smem_gen + cfg::kStages * cfg::kStageBytes + 8 * (2 * cfg::kStages + 4) + 8);
+        int* s_flag = reinterpret_cast<int*>(smem_gen + cfg::kStages * cfg::kStageBytes + 8 * (3 * cfg::kStages + 4) + 8);
         int as = 0;
         uint32_t aph = 0;
         int i = 0;
@@ -624,7 +683,7 @@ static int launch(Ctx* ctx, const CUtensorMap* maps, const Params& p, int grid) 
         DSC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::kSmemBytes));
         attr_set = true;
     }
-    gemm_tf32x3_kernel<BN><<<grid, kThreads, cfg::kSmemBytes, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+    gemm_tf32x3_kernel<BN><<<grid, cfg::kThreads, cfg::kSmemBytes, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], p);
     DSC_LAUNCH_CHECK(ctx);
     return DSC_OK;
 }
@@ -682,18 +741,32 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
     const int cpt = (num_kb + kChunkKb - 1) / kChunkKb;
     const int tiles_m = (m + BM - 1) / BM;
     const double kb_per_chunk = (double)num_kb / cpt;
+    // op(A)(m x k): stored m x k (K contiguous) unless ta; op(B)(k x n): stored n x k (K contiguous) only if tb
+    const OperandPlan pa = plan_operand(A, !ta, m, k, kp), pb = plan_operand(B, tb != 0, n, k, kp);
+    // In-kernel split (tiles narrower than 256): a direct operand needs no pre-pass and no lo plane;
+    // only its fp32 words cross L2 -> SM (half the bytes), and the converter warps derive the lo tile.
+    static const int fuse_env = [] { const char* e = getenv("DSC_GEMM_FUSE"); return e ? atoi(e) : 1; }();
+    static const int force_bn = [] { const char* e = getenv("DSC_GEMM_BN"); return e ? atoi(e) : 0; }();
     int bn = 256, grid = 1, dp_waves = 0, dp_extra = 0, sk_units_total = 0, perm_s = 0;
     {
         double best = -1.0;
         const int cands[3] = {256, 128, 64};
         for (int c : cands) {
+            if (force_bn && c != force_bn) continue;
             const long tiles = (long)tiles_m * ((n + c - 1) / c);
             if (tiles * cpt > 0x3fffffff) continue;
-            const double bytes_kb = (double)(BM + c) * 256.0;
+            const bool can_fuse = fuse_env && c < 256;
+            const bool fa = can_fuse && pa.direct, fb = can_fuse && pb.direct;
+            const double bytes_kb = (double)BM * (fa ? 128.0 : 256.0) + (double)c * (fb ? 128.0 : 256.0);
+            // converter warps: ~26 instructions per float4, 4 warps on 4 schedulers
+            const double conv_kb = ((fa ? BM : 0) + (fb ? c : 0)) * 8.0 * 26.0 / 32.0 / 4.0;
+            // pre-pass for the operands that are not split in the kernel: 8 bytes per element at ~5 TB/s + launch
+            const double pre = (fa && fb) ? 0.0 : 2000.0 * (3.0 + ((fa ? 0.0 : (double)m * k) + (fb ? 0.0 : (double)n * k)) * 8.0 / 5.0e6);
             auto per_kb = [&](double active) {
                 double t = 6.0 * c;
                 if (2.0 * (BM + c) > t) t = 2.0 * (BM + c);
-                if (bytes_kb * active / 10000.0 > t) t = bytes_kb * active / 10000.0;
+                if (conv_kb > t) t = conv_kb;
+                if (bytes_kb * active / 6000.0 > t) t = bytes_kb * active / 6000.0;
                 return t;
             };
             if (tiles >= ctx->sm_count) {
@@ -702,7 +775,7 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
                 const int r = (int)(tiles % g);
                 const double chunk_t = kb_per_chunk * per_kb(g);
                 // (a) plain last wave: r CTAs run one more whole tile
-                double cost = ((double)waves + (r ? 1.0 : 0.0)) * cpt * chunk_t + 4000.0;
+                double cost = ((double)waves + (r ? 1.0 : 0.0)) * cpt * chunk_t + 4000.0 + pre;
                 if (best < 0 || cost < best) { best = cost; bn = c; grid = g; dp_waves = waves; dp_extra = r; sk_units_total = 0; perm_s = 0; }
                 // (b) stream-K over the last wave.  Nearly every CTA parks two segments and re-reads
                 // two or three: ~1 MB of extra L2 traffic per CTA, all at the same time (measured:
@@ -710,7 +783,7 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
                 if (r) {
                     const long sk = (long)r * cpt;
                     const long sk_per_cta = (sk + g - 1) / g;
-                    cost = ((double)waves * cpt + (double)sk_per_cta) * chunk_t + 4000.0 + 30000.0 * c / 256.0;
+                    cost = ((double)waves * cpt + (double)sk_per_cta) * chunk_t + 4000.0 + 30000.0 * c / 256.0 + pre;
                     if (cost < best) { best = cost; bn = c; grid = g; dp_waves = waves; dp_extra = 0; sk_units_total = (int)sk; perm_s = 0; }
                 }
             } else {
@@ -720,7 +793,7 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
                     const int g = (int)tiles * sp;
                     const long per_cta = (cpt + sp - 1) / sp;
                     // park + ticket + the last arriver's pass over sp segments (a serial tail)
-                    double cost = (double)per_cta * kb_per_chunk * per_kb(g) + 4000.0 + (sp > 1 ? (6000.0 + 2500.0 * sp) * c / 256.0 : 0.0);
+                    double cost = (double)per_cta * kb_per_chunk * per_kb(g) + 4000.0 + (sp > 1 ? (6000.0 + 2500.0 * sp) * c / 256.0 : 0.0) + pre;
                     if (cpt % sp != 0) cost *= 1.15;  // ranges cross tile boundaries: lockstep is lost
                     if (best < 0 || cost < best) {
                         best = cost; bn = c; grid = g; dp_waves = 0; dp_extra = 0; sk_units_total = (int)(tiles * cpt);
@@ -745,15 +818,14 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
     p.base = sk_units_total / grid;
     p.rem = sk_units_total % grid;
     static const bool debug_plan = [] { const char* e = getenv("DSC_GEMM_DEBUG"); return e && *e == '1'; }();
+    const bool a_fused = fuse_env && bn < 256 && pa.direct, b_fused = fuse_env && bn < 256 && pb.direct;
     if (debug_plan)
-        fprintf(stderr, "[dsc gemm] m=%d n=%d k=%d ta=%d tb=%d: BN=%d grid=%d cpt=%d dp_waves=%d dp_extra=%d sk_units=%d perm_s=%d\n", m, n, k, ta, tb, bn,
-                grid, cpt, dp_waves, dp_extra, sk_units_total, perm_s);
+        fprintf(stderr, "[dsc gemm] m=%d n=%d k=%d ta=%d tb=%d: BN=%d grid=%d cpt=%d dp_waves=%d dp_extra=%d sk_units=%d perm_s=%d fused=%d%d\n", m, n, k, ta, tb, bn,
+                grid, cpt, dp_waves, dp_extra, sk_units_total, perm_s, (int)a_fused, (int)b_fused);
     DSC_TRY(ensure_gemm_tickets(ctx, (size_t)tiles));
     p.tickets = ctx->gemm_tickets;
 
-    // op(A)(m x k): stored m x k (K contiguous) unless ta; op(B)(k x n): stored n x k (K contiguous) only if tb
-    const OperandPlan pa = plan_operand(A, !ta, m, k, kp), pb = plan_operand(B, tb != 0, n, k, kp);
-    const size_t a_floats = (pa.ws_floats + 255) & ~size_t(255), b_floats = (pb.ws_floats + 255) & ~size_t(255);
+    const size_t a_floats = a_fused ? 0 : (pa.ws_floats + 255) & ~size_t(255), b_floats = b_fused ? 0 : (pb.ws_floats + 255) & ~size_t(255);
     const size_t planes_bytes = (a_floats + b_floats) * sizeof(float);
     const size_t slot_bytes = (size_t)grid * 2 * BM * bn * sizeof(float);
     DSC_TRY(ensure_gemm_ws(ctx, planes_bytes + slot_bytes + 2048));
@@ -766,10 +838,10 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
     const float* b_hi = pb.direct ? B : ws + a_floats;
     p.slots = reinterpret_cast<float*>(base + planes_bytes);
 
-    // ---- (1) split pre-pass ----
-    {
-        SplitJob ja{A, pa.direct ? nullptr : ws, a_lo, m, pa.mode, split_blocks(pa, m, k, kp)};
-        SplitJob jb{B, pb.direct ? nullptr : ws + a_floats, b_lo, n, pb.mode, split_blocks(pb, n, k, kp)};
+    // ---- (1) split pre-pass: only for the operands the kernel does not split itself ----
+    if (!a_fused || !b_fused) {
+        SplitJob ja{A, pa.direct ? nullptr : ws, a_lo, m, pa.mode, a_fused ? 0 : split_blocks(pa, m, k, kp)};
+        SplitJob jb{B, pb.direct ? nullptr : ws + a_floats, b_lo, n, pb.mode, b_fused ? 0 : split_blocks(pb, n, k, kp)};
         split_pair_kernel<<<ja.blocks + jb.blocks, 256, 0, ctx->stream>>>(ja, jb, k, kp);
         DSC_LAUNCH_CHECK(ctx);
     }
@@ -780,6 +852,10 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
     p.vec4 = ((n % 4) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
     p.a_mn = pa.mn_major ? 1 : 0;
     p.b_mn = pb.mn_major ? 1 : 0;
+    p.a_fused = a_fused ? 1 : 0;
+    p.b_fused = b_fused ? 1 : 0;
+    if (a_fused) a_lo = const_cast<float*>(A);   // the lo maps are never dereferenced for a fused operand: point them at valid memory
+    if (b_fused) b_lo = const_cast<float*>(B);
     CUtensorMap maps[4];
     if (pa.mn_major) {          // stored k x m
         DSC_TRY(make_map(&maps[0], a_hi, m, k, (size_t)m, BK, true));
