@@ -62,9 +62,17 @@ constexpr int kBaseThreads = 64 + 32 * kEpiWarps;  // warp0 TMA, warp1 MMA, 8 ep
 constexpr int kChunkKb = 8;                   // k-blocks per accumulation chunk (256 K-elements)
 constexpr int kAPlaneBytes = BM * BK * 4;
 
-template <int BN>
+// PAIR: two CTAs of a cluster (the two SMs of a TPC) run ONE tcgen05.mma.cta_group::2 on a 256 x BN
+// tile: each CTA stages its own 128 rows of A and HALF of the B tile (BN/2 rows) and the tensor cores
+// of both SMs share the B halves, so a CTA moves (128 + BN/2) rows per k-block through shared memory
+// instead of (128 + BN).  That matters because shared-memory bandwidth, not the tensor pipe, bounds
+// the single-CTA kernel: per 32-wide k-block a 128 x 256 tile takes 96 KB of TMA writes plus
+// 12 MMAs x 12 KB of operand reads = 240 KB at 128 B/cycle = 1920 cycles against 1536 cycles of MMA
+// (measured: tensor pipe 78 % active).  The pair moves 64 + 96 = 160 KB = 1280 cycles: tensor-bound.
+template <int BN, bool PAIR>
 struct Cfg {
-    static constexpr int kBPlaneBytes = BN * BK * 4;
+    static constexpr int kBRows = PAIR ? BN / 2 : BN;     // rows of the B tile staged by one CTA
+    static constexpr int kBPlaneBytes = kBRows * BK * 4;
     static constexpr int kStageBytes = 2 * kAPlaneBytes + 2 * kBPlaneBytes;
     static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
     static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator stages; power of two
@@ -72,7 +80,7 @@ struct Cfg {
     // Converter warps (in-kernel operand split): 128 x 256 tiles leave room for two smem stages only
     // and 168 registers per epilogue thread, so that shape keeps the pre-pass; the narrower tiles
     // compute their lo planes in shared memory.
-    static constexpr int kConvWarps = BN >= 256 ? 0 : 4;
+    static constexpr int kConvWarps = (PAIR || BN >= 256) ? 0 : 4;
     static constexpr int kThreads = kBaseThreads + 32 * kConvWarps;
 };
 
@@ -106,6 +114,40 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
                  "l"(map), "r"(bar), "r"(c0), "r"(c1)
                  : "memory");
+}
+// 2-CTA forms: the load lands in this CTA's shared memory, its bytes are counted on the LEADER's
+// (even CTA's) barrier: clearing bit 24 of a shared::cta address names the same offset in the even CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {    // arrive on the barrier at the same offset in cluster CTA 0
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 rem;\n\t"
+        "mapa.shared::cluster.u32 rem, %0, 0;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [rem];\n\t"
+        "}" ::"r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8, %9, %10, %11, %12}, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -208,9 +250,9 @@ __device__ __forceinline__ int unit_owner(const Params& p, int u) {
     return u < big ? u / (p.base + 1) : p.rem + (u - big) / p.base;
 }
 // i-th unit of CTA b -> (tile, chunk)
-__device__ __forceinline__ void unit_at(const Params& p, int i, int dp_units, int sk_begin, int& tile, int& chunk) {
+__device__ __forceinline__ void unit_at(const Params& p, int i, int dp_units, int sk_begin, int nb, int bid, int& tile, int& chunk) {
     if (i < dp_units) {
-        tile = (i / p.cpt) * (int)gridDim.x + (int)blockIdx.x;  // whole-tile waves use the physical CTA index
+        tile = (i / p.cpt) * nb + bid;  // whole-tile waves use the physical CTA (pair) index
         chunk = i % p.cpt;
     } else {
         const int u = sk_begin + (i - dp_units);
@@ -245,11 +287,16 @@ __device__ __forceinline__ void convert_plane(const uint8_t* hi, uint8_t* lo, in
     }
 }
 
-template <int BN>
-__global__ void __launch_bounds__(Cfg<BN>::kThreads, 1)
+template <int BN, bool PAIR>
+__global__ void __launch_bounds__(Cfg<BN, PAIR>::kThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
                    const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, const Params p) {
-    using cfg = Cfg<BN>;
+    using cfg = Cfg<BN, PAIR>;
+    constexpr int TM = PAIR ? 2 * BM : BM;          // rows of an output tile
+    uint32_t cta_rank = 0;                          // 0 = leader of the pair (issues the MMAs)
+    if constexpr (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    const int nb = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;    // workers (CTAs or CTA pairs)
+    const int bid = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -275,23 +322,29 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), kEpiWarps);  // one arrival per epilogue warp
+            mbar_init(tempty_bar(a), PAIR ? 2 * kEpiWarps : kEpiWarps);  // one arrival per epilogue warp (pair: of both CTAs, on the leader's barrier)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)cfg::kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)cfg::kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)cfg::kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
 
-    const int lb = p.perm_tiles ? ((int)blockIdx.x % p.perm_tiles) * p.perm_s + (int)blockIdx.x / p.perm_tiles : (int)blockIdx.x;
+    const int lb = p.perm_tiles ? (bid % p.perm_tiles) * p.perm_s + bid / p.perm_tiles : bid;
     const int sk_begin = unit_begin(p, lb), sk_end = unit_begin(p, lb + 1);
-    const int dp_units = (p.dp_waves + ((int)blockIdx.x < p.dp_extra ? 1 : 0)) * p.cpt;
+    const int dp_units = (p.dp_waves + (bid < p.dp_extra ? 1 : 0)) * p.cpt;
     const int my_units = dp_units + (sk_end - sk_begin);
     const bool a_fused = kConv > 0 && p.a_fused, b_fused = kConv > 0 && p.b_fused;
     const uint32_t stage_tx = (uint32_t)((a_fused ? 1 : 2) * kAPlaneBytes + (b_fused ? 1 : 2) * cfg::kBPlaneBytes);
@@ -303,32 +356,38 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
             uint32_t ph = 0;
             for (int i = 0; i < my_units; ++i) {
                 int tile, chunk;
-                unit_at(p, i, dp_units, sk_begin, tile, chunk);
-                const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
+                unit_at(p, i, dp_units, sk_begin, nb, bid, tile, chunk);
+                // this CTA's share of the tile's operands: its 128 rows of A, and (pair) its half of the B rows
+                const int m0 = (tile / p.tiles_n) * TM + (int)cta_rank * BM, n0 = (tile % p.tiles_n) * BN + (int)cta_rank * cfg::kBRows;
                 const int kb0 = chunk * kChunkKb;
                 const int kb1 = min(p.num_kb, kb0 + kChunkKb);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     const uint32_t st = smem_base + s * cfg::kStageBytes;
-                    mbar_expect_tx(full_bar(s), stage_tx);
+                    auto load = [&](uint32_t dst, const CUtensorMap* map, int c0, int c1) {
+                        if constexpr (PAIR) tma_load_2d_pair(dst, map, full_bar(s), c0, c1);
+                        else tma_load_2d(dst, map, full_bar(s), c0, c1);
+                    };
+                    // pair: the leader's barrier counts the bytes of both CTAs
+                    if (!PAIR || cta_rank == 0) mbar_expect_tx(full_bar(s), PAIR ? 2u * stage_tx : stage_tx);
                     if (!p.a_mn) {
-                        tma_load_2d(st, &map_ahi, full_bar(s), kb * BK, m0);
-                        if (!a_fused) tma_load_2d(st + kAPlaneBytes, &map_alo, full_bar(s), kb * BK, m0);
+                        load(st, &map_ahi, kb * BK, m0);
+                        if (!a_fused) load(st + kAPlaneBytes, &map_alo, kb * BK, m0);
                     } else {
 #pragma unroll
                         for (int i = 0; i < BM / 32; ++i) {
-                            tma_load_2d(st + i * 4096, &map_ahi, full_bar(s), m0 + 32 * i, kb * BK);
-                            if (!a_fused) tma_load_2d(st + kAPlaneBytes + i * 4096, &map_alo, full_bar(s), m0 + 32 * i, kb * BK);
+                            load(st + i * 4096, &map_ahi, m0 + 32 * i, kb * BK);
+                            if (!a_fused) load(st + kAPlaneBytes + i * 4096, &map_alo, m0 + 32 * i, kb * BK);
                         }
                     }
                     if (!p.b_mn) {
-                        tma_load_2d(st + 2 * kAPlaneBytes, &map_bhi, full_bar(s), kb * BK, n0);
-                        if (!b_fused) tma_load_2d(st + 2 * kAPlaneBytes + cfg::kBPlaneBytes, &map_blo, full_bar(s), kb * BK, n0);
+                        load(st + 2 * kAPlaneBytes, &map_bhi, kb * BK, n0);
+                        if (!b_fused) load(st + 2 * kAPlaneBytes + cfg::kBPlaneBytes, &map_blo, kb * BK, n0);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < BN / 32; ++i) {
-                            tma_load_2d(st + 2 * kAPlaneBytes + i * 4096, &map_bhi, full_bar(s), n0 + 32 * i, kb * BK);
-                            if (!b_fused) tma_load_2d(st + 2 * kAPlaneBytes + cfg::kBPlaneBytes + i * 4096, &map_blo, full_bar(s), n0 + 32 * i, kb * BK);
+                        for (int i = 0; i < cfg::kBRows / 32; ++i) {
+                            load(st + 2 * kAPlaneBytes + i * 4096, &map_bhi, n0 + 32 * i, kb * BK);
+                            if (!b_fused) load(st + 2 * kAPlaneBytes + cfg::kBPlaneBytes + i * 4096, &map_blo, n0 + 32 * i, kb * BK);
                         }
                     }
                     if (++s == cfg::kStages) { s = 0; ph ^= 1u; }
@@ -337,8 +396,16 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(BM, BN) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16);
+        if (lane == 0 && cta_rank == 0) {
+            const uint32_t idesc = make_idesc_tf32(TM, BN) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16);
+            auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
+                if constexpr (PAIR) umma_tf32_pair(d, a, b, idesc, acc);
+                else umma_tf32(d, a, b, idesc, acc);
+            };
+            auto commit = [&](uint32_t bar) {
+                if constexpr (PAIR) tcgen05_commit_pair(bar);
+                else tcgen05_commit(bar);
+            };
             // per 8-wide k-slice the descriptor start address moves by 32 B inside the swizzle row
             // (K-major) or by one 1024-byte group of 8 k-rows (MN-major); units of 16 B
             const uint64_t a_adv = p.a_mn ? 64u : 2u, b_adv = p.b_mn ? 64u : 2u;
@@ -346,7 +413,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
             uint32_t ph = 0, aph = 0;
             for (int i = 0; i < my_units; ++i) {
                 int tile, chunk;
-                unit_at(p, i, dp_units, sk_begin, tile, chunk);
+                unit_at(p, i, dp_units, sk_begin, nb, bid, tile, chunk);
                 const int c0 = chunk * kChunkKb;
                 const int c1 = min(p.num_kb, c0 + kChunkKb);
                 mbar_wait(tempty_bar(as), aph ^ 1u);  // the epilogue has drained this accumulator stage
@@ -365,14 +432,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
 #pragma unroll
                     for (int k = 0; k < BK / 8; ++k) {
                         const uint64_t aa = a_adv * (uint64_t)k, ba = b_adv * (uint64_t)k;
-                        umma_tf32(d_tmem, alo + aa, bhi + ba, idesc, (uint32_t)((kb != c0) | (k != 0)));
-                        umma_tf32(d_tmem, ahi + aa, blo + ba, idesc, 1u);
-                        umma_tf32(d_tmem, ahi + aa, bhi + ba, idesc, 1u);
+                        mma(d_tmem, alo + aa, bhi + ba, (uint32_t)((kb != c0) | (k != 0)));
+                        mma(d_tmem, ahi + aa, blo + ba, 1u);
+                        mma(d_tmem, ahi + aa, bhi + ba, 1u);
                     }
-                    tcgen05_commit(empty_bar(s));      // smem stage is free once these MMAs retire
+                    commit(empty_bar(s));              // smem stage is free (in both CTAs) once these MMAs retire
                     if (++s == cfg::kStages) { s = 0; ph ^= 1u; }
                 }
-                tcgen05_commit(tfull_bar(as));         // chunk accumulator complete
+                commit(tfull_bar(as));                 // chunk accumulator complete
                 if (++as == 2) { as = 0; aph ^= 1u; }
             }
         }
@@ -384,7 +451,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
         uint32_t ph = 0;
         for (int i = 0; i < my_units; ++i) {
             int tile, chunk;
-            unit_at(p, i, dp_units, sk_begin, tile, chunk);
+            unit_at(p, i, dp_units, sk_begin, nb, bid, tile, chunk);
             const int kb0 = chunk * kChunkKb;
             const int kb1 = min(p.num_kb, kb0 + kChunkKb);
             for (int kb = kb0; kb < kb1; ++kb) {
@@ -413,10 +480,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
         int i = 0;
         while (i < my_units) {
             int tile, ch0;
-            unit_at(p, i, dp_units, sk_begin, tile, ch0);
+            unit_at(p, i, dp_units, sk_begin, nb, bid, tile, ch0);
             // the segment: this CTA's consecutive units of `tile`
             const int seg_len = i < dp_units ? p.cpt : min(p.cpt - ch0, my_units - i);
-            const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
+            const int m0 = (tile / p.tiles_n) * TM + (int)cta_rank * BM, n0 = (tile % p.tiles_n) * BN;
             float acc[HALF];
 #pragma unroll
             for (int j = 0; j < HALF; ++j) acc[j] = 0.f;
@@ -434,7 +501,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                 }
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar(as));
+                if (lane == 0) {
+                    if constexpr (PAIR) mbar_arrive_leader(tempty_bar(as));
+                    else mbar_arrive(tempty_bar(as));
+                }
                 if (++as == 2) { as = 0; aph ^= 1u; }
             }
             if (seg_len == p.cpt) {
@@ -461,14 +531,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                 const int sk_tile = tile - p.dp_tiles;
                 const int which = (sk_tile == sk_begin / p.cpt) ? 0 : 1;
                 {
-                    float* slot = p.slots + ((size_t)lb * 2 + which) * (BM * BN) + (size_t)trow * BN + half * HALF;
+                    float* slot = p.slots + (((size_t)lb * 2 + which) * (PAIR ? 2 : 1) + cta_rank) * (BM * BN) + (size_t)trow * BN + half * HALF;
 #pragma unroll
                     for (int c = 0; c < HALF; c += 4) *reinterpret_cast<float4*>(slot + c) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
                 }
                 __threadfence();
                 epi_bar();
                 const int b_first = unit_owner(p, sk_tile * p.cpt), b_last = unit_owner(p, (sk_tile + 1) * p.cpt - 1);
-                if (threadIdx.x == 64) *s_flag = (atomicAdd(&p.tickets[tile], 1u) == (unsigned)(b_last - b_first));
+                unsigned int* ticket = p.tickets + (PAIR ? 2 * tile + (int)cta_rank : tile);   // the two halves of a pair's tile are finished independently
+                if (threadIdx.x == 64) *s_flag = (atomicAdd(ticket, 1u) == (unsigned)(b_last - b_first));
                 epi_bar();
                 const bool last = (*s_flag != 0);
                 epi_bar();   // everyone has read the flag before the next segment overwrites it
@@ -492,7 +563,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                                 const int b = b0 + j;
                                 if (b <= b_last) {
                                     const int w = (sk_tile == unit_begin(p, b) / p.cpt) ? 0 : 1;
-                                    const float4* src = reinterpret_cast<const float4*>(p.slots + ((size_t)b * 2 + w) * (BM * BN));
+                                    const float4* src = reinterpret_cast<const float4*>(p.slots + (((size_t)b * 2 + w) * (PAIR ? 2 : 1) + cta_rank) * (BM * BN));
 #pragma unroll
                                     for (int q = 0; q < 8; ++q) v[j][q] = __ldcg(src + (pass * 8 + q) * 256 + t);
                                 } else {
@@ -525,7 +596,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                             }
                         }
                     }
-                    if (threadIdx.x == 64) p.tickets[tile] = 0;
+                    if (threadIdx.x == 64) *ticket = 0;
                 }
             }
         }
@@ -533,9 +604,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
 
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();   // neither CTA may leave (or free TMEM) while the pair's MMAs / barrier arrivals are in flight
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)cfg::kTmemCols) : "memory");
+        if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)cfg::kTmemCols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)cfg::kTmemCols) : "memory");
     }
 }
 
@@ -675,15 +748,28 @@ static int make_map(CUtensorMap* map, const float* base, int inner, int outer, s
     return DSC_OK;
 }
 
-template <int BN>
-static int launch(Ctx* ctx, const CUtensorMap* maps, const Params& p, int grid) {
-    using cfg = Cfg<BN>;
+// `workers` = CTAs, or CTA pairs (clusters of 2: the two SMs of a TPC) when PAIR
+template <int BN, bool PAIR>
+static int launch(Ctx* ctx, const CUtensorMap* maps, const Params& p, int workers) {
+    using cfg = Cfg<BN, PAIR>;
     static bool attr_set = false;
     if (!attr_set) {
-        DSC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::kSmemBytes));
+        DSC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::kSmemBytes));
         attr_set = true;
     }
-    gemm_tf32x3_kernel<BN><<<grid, cfg::kThreads, cfg::kSmemBytes, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(PAIR ? 2 * workers : workers);
+    lc.blockDim = dim3(cfg::kThreads);
+    lc.dynamicSmemBytes = cfg::kSmemBytes;
+    lc.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    lc.attrs = at;
+    lc.numAttrs = PAIR ? 1 : 0;
+    DSC_CUDA_CHECK(cudaLaunchKernelEx(&lc, gemm_tf32x3_kernel<BN, PAIR>, maps[0], maps[1], maps[2], maps[3], p));
     DSC_LAUNCH_CHECK(ctx);
     return DSC_OK;
 }
@@ -725,10 +811,8 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
     const int kp = (k + BK - 1) / BK * BK;
 
     // ---- plan: tile width, grid and schedule (all decided before anything is launched) ----
-    // Cycle model per CTA and 32-wide k-block (B300_MICROARCH.md pacing law, measured here):
-    //   tensor pipe  : 4 k-slices x 3 MMAs x (BN/256 x 128) = 6 BN cycles
-    //   smem fill    : (BM + BN) rows x 128 B x 2 planes at 128 B/cycle       = 2 (BM + BN) cycles
-    //   L2 -> SM     : the same bytes from every active CTA through ~10 KB/cycle of L2 bandwidth
+    // Candidates: tile width 256 / 128 / 64, one CTA per tile (128 rows) or a CTA pair (256 rows); the
+    // cycle model is stated next to the candidate loop.
     // Schedules (one kernel, see Params):
     //   tiles >= SMs : whole-tile waves (neighbouring CTAs walk K in lockstep over neighbouring tiles,
     //                  so operand panels are shared in L2) + stream-K over the tiles of the last,
@@ -745,60 +829,79 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
     const OperandPlan pa = plan_operand(A, !ta, m, k, kp), pb = plan_operand(B, tb != 0, n, k, kp);
     // In-kernel split (tiles narrower than 256): a direct operand needs no pre-pass and no lo plane;
     // only its fp32 words cross L2 -> SM (half the bytes), and the converter warps derive the lo tile.
-    static const int fuse_env = [] { const char* e = getenv("DSC_GEMM_FUSE"); return e ? atoi(e) : 1; }();
-    static const int force_bn = [] { const char* e = getenv("DSC_GEMM_BN"); return e ? atoi(e) : 0; }();
+    static const int fuse_env0 = [] { const char* e = getenv("DSC_GEMM_FUSE"); return e ? atoi(e) : 1; }();
+    static const int force_bn0 = [] { const char* e = getenv("DSC_GEMM_BN"); return e ? atoi(e) : 0; }();
+    const int fuse_env = ctx->gemm_force_fuse >= 0 ? ctx->gemm_force_fuse : fuse_env0;
+    const int force_bn = ctx->gemm_force_bn > 0 ? ctx->gemm_force_bn : force_bn0;
+    static const int force_pair0 = [] { const char* e = getenv("DSC_GEMM_PAIR"); return e ? atoi(e) : -1; }();   // -1: planner decides
+    const int force_pair = ctx->gemm_force_pair >= 0 ? ctx->gemm_force_pair : force_pair0;
+    const int force_split = ctx->gemm_force_split;
     int bn = 256, grid = 1, dp_waves = 0, dp_extra = 0, sk_units_total = 0, perm_s = 0;
+    bool pair = false;
     {
+        // Per worker (CTA, or CTA pair) and 32-wide k-block, in cycles:
+        //   tensor pipe : 4 k-slices x 3 MMAs x (BN/256 x 128)                               = 6 BN
+        //   smem        : TMA writes + MMA operand reads (3 MMAs re-read both operands) [+ converter read/write],
+        //                 over the rows one CTA stages (128 + BN, pair: 128 + BN/2), 128 B/cycle  = 5 (6) x rows
+        //   L2 -> SM    : the TMA bytes of every active CTA through ~6 KB/cycle
         double best = -1.0;
-        const int cands[3] = {256, 128, 64};
-        for (int c : cands) {
+        for (int cand = 0; cand < 6; ++cand) {
+            const int c = cand % 3 == 0 ? 256 : (cand % 3 == 1 ? 128 : 64);
+            const bool pr = cand >= 3;
             if (force_bn && c != force_bn) continue;
-            const long tiles = (long)tiles_m * ((n + c - 1) / c);
+            if (force_pair >= 0 && (int)pr != force_pair) continue;
+            const int tm = pr ? 2 * BM : BM;
+            const int tiles_m_c = (m + tm - 1) / tm;
+            const long tiles = (long)tiles_m_c * ((n + c - 1) / c);
             if (tiles * cpt > 0x3fffffff) continue;
-            const bool can_fuse = fuse_env && c < 256;
+            const int workers = pr ? ctx->sm_count / 2 : ctx->sm_count;
+            const int ctas_per_worker = pr ? 2 : 1;
+            const int brows = pr ? c / 2 : c;
+            const bool can_fuse = fuse_env && !pr && c < 256;
             const bool fa = can_fuse && pa.direct, fb = can_fuse && pb.direct;
-            const double bytes_kb = (double)BM * (fa ? 128.0 : 256.0) + (double)c * (fb ? 128.0 : 256.0);
-            // converter warps: ~26 instructions per float4, 4 warps on 4 schedulers
-            const double conv_kb = ((fa ? BM : 0) + (fb ? c : 0)) * 8.0 * 26.0 / 32.0 / 4.0;
+            const double bytes_kb = (double)BM * (fa ? 128.0 : 256.0) + (double)brows * (fb ? 128.0 : 256.0);
+            const double smem_kb = (double)BM * (fa ? 6.0 : 5.0) + (double)brows * (fb ? 6.0 : 5.0);
             // pre-pass for the operands that are not split in the kernel: 8 bytes per element at ~5 TB/s + launch
             const double pre = (fa && fb) ? 0.0 : 2000.0 * (3.0 + ((fa ? 0.0 : (double)m * k) + (fb ? 0.0 : (double)n * k)) * 8.0 / 5.0e6);
-            auto per_kb = [&](double active) {
+            auto per_kb = [&](double active_workers) {
                 double t = 6.0 * c;
-                if (2.0 * (BM + c) > t) t = 2.0 * (BM + c);
-                if (conv_kb > t) t = conv_kb;
-                if (bytes_kb * active / 6000.0 > t) t = bytes_kb * active / 6000.0;
+                if (smem_kb > t) t = smem_kb;
+                const double l2 = bytes_kb * active_workers * ctas_per_worker / 6000.0;
+                if (l2 > t) t = l2;
                 return t;
             };
-            if (tiles >= ctx->sm_count) {
-                const int g = ctx->sm_count;
+            const double fix_scale = (double)c / 256.0;   // cost of parking / re-reading partial tiles scales with the tile width
+            auto take = [&](double cost, int g, int waves, int extra, long sk, int ps) {
+                if (best < 0 || cost < best) {
+                    best = cost; bn = c; pair = pr; grid = g; dp_waves = waves; dp_extra = extra; sk_units_total = (int)sk; perm_s = ps;
+                }
+            };
+            if (tiles >= workers) {
+                const int g = workers;
                 const int waves = (int)(tiles / g);
                 const int r = (int)(tiles % g);
                 const double chunk_t = kb_per_chunk * per_kb(g);
-                // (a) plain last wave: r CTAs run one more whole tile
-                double cost = ((double)waves + (r ? 1.0 : 0.0)) * cpt * chunk_t + 4000.0 + pre;
-                if (best < 0 || cost < best) { best = cost; bn = c; grid = g; dp_waves = waves; dp_extra = r; sk_units_total = 0; perm_s = 0; }
-                // (b) stream-K over the last wave.  Nearly every CTA parks two segments and re-reads
-                // two or three: ~1 MB of extra L2 traffic per CTA, all at the same time (measured:
-                // ~15 us for 148 CTAs with 128 x 256 tiles) — pays only when K is deep.
+                // (a) plain last wave: r workers run one more whole tile
+                take(((double)waves + (r ? 1.0 : 0.0)) * cpt * chunk_t + 4000.0 + pre, g, waves, r, 0, 0);
+                // (b) stream-K over the last wave.  Nearly every worker parks two segments and re-reads
+                // two or three: extra L2 traffic, all at the same time (measured: ~15 us for 148 CTAs
+                // with 128 x 256 tiles) — pays only when K is deep.
                 if (r) {
                     const long sk = (long)r * cpt;
-                    const long sk_per_cta = (sk + g - 1) / g;
-                    cost = ((double)waves * cpt + (double)sk_per_cta) * chunk_t + 4000.0 + 30000.0 * c / 256.0 + pre;
-                    if (cost < best) { best = cost; bn = c; grid = g; dp_waves = waves; dp_extra = 0; sk_units_total = (int)sk; perm_s = 0; }
+                    const long sk_per = (sk + g - 1) / g;
+                    take(((double)waves * cpt + (double)sk_per) * chunk_t + 4000.0 + 30000.0 * fix_scale + pre, g, waves, 0, sk, 0);
                 }
             } else {
                 const int smax = cpt < 16 ? cpt : 16;
                 for (int sp = 1; sp <= smax; ++sp) {
-                    if (tiles * sp > ctx->sm_count) break;
+                    if (tiles * sp > workers) break;
+                    if (force_split > 0 && sp != force_split && !(sp == smax && force_split > smax)) continue;
                     const int g = (int)tiles * sp;
-                    const long per_cta = (cpt + sp - 1) / sp;
+                    const long per_w = (cpt + sp - 1) / sp;
                     // park + ticket + the last arriver's pass over sp segments (a serial tail)
-                    double cost = (double)per_cta * kb_per_chunk * per_kb(g) + 4000.0 + (sp > 1 ? (6000.0 + 2500.0 * sp) * c / 256.0 : 0.0) + pre;
+                    double cost = (double)per_w * kb_per_chunk * per_kb(g) + 4000.0 + (sp > 1 ? (6000.0 + 2500.0 * sp) * fix_scale : 0.0) + pre;
                     if (cpt % sp != 0) cost *= 1.15;  // ranges cross tile boundaries: lockstep is lost
-                    if (best < 0 || cost < best) {
-                        best = cost; bn = c; grid = g; dp_waves = 0; dp_extra = 0; sk_units_total = (int)(tiles * cpt);
-                        perm_s = (sp > 1 && cpt % sp == 0) ? sp : 0;
-                    }
+                    take(cost, g, 0, 0, tiles * cpt, (sp > 1 && cpt % sp == 0) ? sp : 0);
                 }
             }
         }
@@ -806,7 +909,7 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
     }
     Params p;
     p.m = m; p.n = n; p.num_kb = num_kb;
-    p.tiles_m = tiles_m;
+    p.tiles_m = pair ? (m + 2 * BM - 1) / (2 * BM) : tiles_m;
     p.tiles_n = (n + bn - 1) / bn;
     p.cpt = cpt;
     const long tiles = (long)p.tiles_m * p.tiles_n;
@@ -818,16 +921,16 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
     p.base = sk_units_total / grid;
     p.rem = sk_units_total % grid;
     static const bool debug_plan = [] { const char* e = getenv("DSC_GEMM_DEBUG"); return e && *e == '1'; }();
-    const bool a_fused = fuse_env && bn < 256 && pa.direct, b_fused = fuse_env && bn < 256 && pb.direct;
+    const bool a_fused = fuse_env && !pair && bn < 256 && pa.direct, b_fused = fuse_env && !pair && bn < 256 && pb.direct;
     if (debug_plan)
-        fprintf(stderr, "[dsc gemm] m=%d n=%d k=%d ta=%d tb=%d: BN=%d grid=%d cpt=%d dp_waves=%d dp_extra=%d sk_units=%d perm_s=%d fused=%d%d\n", m, n, k, ta, tb, bn,
-                grid, cpt, dp_waves, dp_extra, sk_units_total, perm_s, (int)a_fused, (int)b_fused);
-    DSC_TRY(ensure_gemm_tickets(ctx, (size_t)tiles));
+        fprintf(stderr, "[dsc gemm] m=%d n=%d k=%d ta=%d tb=%d: BN=%d pair=%d grid=%d cpt=%d dp_waves=%d dp_extra=%d sk_units=%d perm_s=%d fused=%d%d\n", m, n, k, ta, tb, bn,
+                (int)pair, grid, cpt, dp_waves, dp_extra, sk_units_total, perm_s, (int)a_fused, (int)b_fused);
+    DSC_TRY(ensure_gemm_tickets(ctx, (size_t)tiles * (pair ? 2 : 1)));
     p.tickets = ctx->gemm_tickets;
 
     const size_t a_floats = a_fused ? 0 : (pa.ws_floats + 255) & ~size_t(255), b_floats = b_fused ? 0 : (pb.ws_floats + 255) & ~size_t(255);
     const size_t planes_bytes = (a_floats + b_floats) * sizeof(float);
-    const size_t slot_bytes = (size_t)grid * 2 * BM * bn * sizeof(float);
+    const size_t slot_bytes = (size_t)grid * (pair ? 2 : 1) * 2 * BM * bn * sizeof(float);
     DSC_TRY(ensure_gemm_ws(ctx, planes_bytes + slot_bytes + 2048));
     char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ctx->gemm_ws) + 1023) & ~uintptr_t(1023));
     float* ws = reinterpret_cast<float*>(base);
@@ -870,16 +973,34 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
         DSC_TRY(make_map(&maps[3], b_lo, n, k, (size_t)n, BK, true));
     } else {
         const int kk = pb.direct ? k : kp;
-        DSC_TRY(make_map(&maps[2], b_hi, kk, n, (size_t)kk, bn));
-        DSC_TRY(make_map(&maps[3], b_lo, kk, n, (size_t)kk, bn));
+        DSC_TRY(make_map(&maps[2], b_hi, kk, n, (size_t)kk, pair ? bn / 2 : bn));
+        DSC_TRY(make_map(&maps[3], b_lo, kk, n, (size_t)kk, pair ? bn / 2 : bn));
     }
     int s;
-    if (bn == 256) s = launch<256>(ctx, maps, p, grid);
-    else if (bn == 128) s = launch<128>(ctx, maps, p, grid);
-    else s = launch<64>(ctx, maps, p, grid);
+    if (pair) {
+        if (bn == 256) s = launch<256, true>(ctx, maps, p, grid);
+        else if (bn == 128) s = launch<128, true>(ctx, maps, p, grid);
+        else s = launch<64, true>(ctx, maps, p, grid);
+    } else {
+        if (bn == 256) s = launch<256, false>(ctx, maps, p, grid);
+        else if (bn == 128) s = launch<128, false>(ctx, maps, p, grid);
+        else s = launch<64, false>(ctx, maps, p, grid);
+    }
     if (s != DSC_OK) return s;
     ctx->stats.gemm_tcgen05++;
     return DSC_OK;
 }
 
 }  // namespace dsc
+
+extern "C" int dsc_gemm_tune(dsc_ctx_t c, int bn, int pair, int split, int fuse) {
+    using namespace dsc;
+    if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
+    if (!(bn == -1 || bn == 256 || bn == 128 || bn == 64)) return fail(DSC_E_INVALID, "dsc_gemm_tune: bn must be -1, 256, 128 or 64");
+    Ctx* ctx = as_ctx(c);
+    ctx->gemm_force_bn = bn;
+    ctx->gemm_force_pair = pair < 0 ? -1 : (pair != 0);
+    ctx->gemm_force_split = split;
+    ctx->gemm_force_fuse = fuse < 0 ? -1 : (fuse != 0);
+    return DSC_OK;
+}

@@ -91,6 +91,7 @@ struct Ctx {
     // GEMM operand-split workspace (3xTF32 hi/lo planes)
     void* gemm_ws = nullptr;
     size_t gemm_ws_bytes = 0;
+    int gemm_force_bn = -1, gemm_force_pair = -1, gemm_force_split = -1, gemm_force_fuse = -1;   // dsc_gemm_tune; -1 = planner decides
     unsigned int* gemm_tickets = nullptr;   // one arrival counter per output tile (stream-K fix-up), zero between launches
     size_t gemm_tickets_n = 0;
     // NCCL
