@@ -147,7 +147,8 @@ DSC_API int dsc_graph_destroy(dsc_ctx_t ctx, dsc_graph_t graph);
 DSC_API int dsc_flush_l2(dsc_ctx_t ctx);
 /* Pin the plan of the float32 tensor-core GEMM (tests force every kernel variant; tools sweep them):
  * tile width bn in {256,128,64}, pair = 1 for the 2-CTA (cta_group::2) kernel, split = K ranges per
- * tile when the tiles do not fill the GPU, fuse = in-kernel operand split.  -1 = planner decides. */
+ * tile when the tiles do not fill the GPU, fuse = in-kernel operand split (0 off, 1 single-CTA
+ * kernels, 2 also the 2-CTA 256 x 256 kernel).  -1 = planner decides. */
 DSC_API int dsc_gemm_tune(dsc_ctx_t ctx, int bn, int pair, int split, int fuse);
 
 /* ---------------------------------------------------------------- buffers ------------------ */

@@ -69,19 +69,36 @@ constexpr int kAPlaneBytes = BM * BK * 4;
 // the single-CTA kernel: per 32-wide k-block a 128 x 256 tile takes 96 KB of TMA writes plus
 // 12 MMAs x 12 KB of operand reads = 240 KB at 128 B/cycle = 1920 cycles against 1536 cycles of MMA
 // (measured: tensor pipe 78 % active).  The pair moves 64 + 96 = 160 KB = 1280 cycles: tensor-bound.
-template <int BN, bool PAIR>
+//
+// WIDE (256 x 256 pair tiles whose operands are both directly addressable): the operand split moves
+// into the kernel.  TMA fetches only the fp32 words (the hi tiles: half the L2 -> SM bytes, no lo
+// planes in HBM, no pre-pass launch) into a 4-deep ring; six converter warps derive the lo tiles into a
+// separate 3-deep ring (7 x 32 KB of shared memory), so that the extra hop TMA -> converters -> MMA
+// is hidden: the fetch of k-block i+3 and the conversion of k-blocks i+1, i+2 overlap the MMAs of
+// k-block i.  16 warps in four warpgroups — {TMA, MMA, converter, converter}, 2 x epilogue,
+// 4 x converter — with the register file re-divided by setmaxnreg (epilogue threads hold 128
+// accumulators: 200 registers; the other warpgroups run on 56).  Per k-block a CTA moves 32 KB of TMA
+// writes + 64 KB of converter traffic + 96 KB of MMA operand reads = 192 KB = 1536 cycles of shared-memory
+// bandwidth, below the ~2400 cycles the tensor pipe needs for the 12 TF32 MMAs of a 256 x 256 x 32 block.
+template <int BN, bool PAIR, bool WIDE>
 struct Cfg {
+    static_assert(!WIDE || (PAIR && BN == 256), "the in-kernel split of the pair kernel is built for 256 x 256 tiles");
+    static constexpr bool kWide = WIDE;
     static constexpr int kBRows = PAIR ? BN / 2 : BN;     // rows of the B tile staged by one CTA
     static constexpr int kBPlaneBytes = kBRows * BK * 4;
-    static constexpr int kStageBytes = 2 * kAPlaneBytes + 2 * kBPlaneBytes;
-    static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
+    // not WIDE: a stage holds [A_hi | A_lo | B_hi | B_lo];  WIDE: hi ring of [A_hi | B_hi] stages, then the lo ring of [A_lo | B_lo]
+    static constexpr int kStageBytes = WIDE ? kAPlaneBytes + kBPlaneBytes : 2 * kAPlaneBytes + 2 * kBPlaneBytes;
+    static constexpr int kStages = WIDE ? 4 : ((196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes));
+    static constexpr int kLoStages = WIDE ? 3 : kStages;
+    static constexpr int kTileBytes = WIDE ? (kStages + kLoStages) * kStageBytes : kStages * kStageBytes;
     static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator stages; power of two
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers, TMEM base, epilogue flag*/;
-    // Converter warps (in-kernel operand split): 128 x 256 tiles leave room for two smem stages only
-    // and 168 registers per epilogue thread, so that shape keeps the pre-pass; the narrower tiles
-    // compute their lo planes in shared memory.
-    static constexpr int kConvWarps = (PAIR || BN >= 256) ? 0 : 4;
-    static constexpr int kThreads = kBaseThreads + 32 * kConvWarps;
+    static constexpr int kSmemBytes = kTileBytes + 1024 /*align*/ + 256 /*barriers, TMEM base, epilogue flag*/;
+    // Converter warps (in-kernel operand split).  Single-CTA 128 x 256 tiles leave room for two smem
+    // stages only and need 168 registers per epilogue thread: that shape keeps the pre-pass, and so do
+    // the narrower pair tiles; single-CTA 128 x 128 / 128 x 64 tiles convert inside their stages.
+    static constexpr int kConvWarps = WIDE ? 6 : ((PAIR || BN >= 256) ? 0 : 4);
+    static constexpr int kEpi0 = WIDE ? 4 : 2;   // first epilogue warp
+    static constexpr int kThreads = WIDE ? 512 : kBaseThreads + 32 * kConvWarps;
 };
 
 // ---- PTX helpers ------------------------------------------------------------------------------
@@ -125,6 +142,29 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
 __device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
                  : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope: the arrivals come from both CTAs
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive_leader_release(uint32_t bar) {   // release at cluster scope on cluster CTA 0's barrier
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 rem;\n\t"
+        "mapa.shared::cluster.u32 rem, %0, 0;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [rem];\n\t"
+        "}" ::"r"(bar)
+        : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {    // arrive on the barrier at the same offset in cluster CTA 0
     asm volatile(
@@ -274,24 +314,30 @@ __device__ __forceinline__ float lo_word(float x) {
 // N4 float4 per plane, NT converter threads, 4 loads in flight per thread.
 template <int N4, int NT>
 __device__ __forceinline__ void convert_plane(const uint8_t* hi, uint8_t* lo, int ct) {
-    static_assert(N4 % (NT * 4) == 0 || N4 % (NT * 2) == 0, "plane size vs converter threads");
-    constexpr int U = (N4 % (NT * 4) == 0) ? 4 : 2;
+    constexpr int PER = (N4 + NT - 1) / NT;   // float4 per thread (the last round may be partial)
+    constexpr int U = 4;
 #pragma unroll
-    for (int j = 0; j < N4 / NT; j += U) {
+    for (int j = 0; j < PER; j += U) {
         float4 v[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) v[u] = *reinterpret_cast<const float4*>(hi + 16 * (ct + (j + u) * NT));
+        for (int u = 0; u < U; ++u) {
+            const int idx = ct + (j + u) * NT;
+            if (j + u < PER && ((j + u + 1) * NT <= N4 || idx < N4)) v[u] = *reinterpret_cast<const float4*>(hi + 16 * idx);
+        }
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-            *reinterpret_cast<float4*>(lo + 16 * (ct + (j + u) * NT)) = make_float4(lo_word(v[u].x), lo_word(v[u].y), lo_word(v[u].z), lo_word(v[u].w));
+        for (int u = 0; u < U; ++u) {
+            const int idx = ct + (j + u) * NT;
+            if (j + u < PER && ((j + u + 1) * NT <= N4 || idx < N4))
+                *reinterpret_cast<float4*>(lo + 16 * idx) = make_float4(lo_word(v[u].x), lo_word(v[u].y), lo_word(v[u].z), lo_word(v[u].w));
+        }
     }
 }
 
-template <int BN, bool PAIR>
-__global__ void __launch_bounds__(Cfg<BN, PAIR>::kThreads, 1)
+template <int BN, bool PAIR, bool WIDE>
+__global__ void __launch_bounds__(Cfg<BN, PAIR, WIDE>::kThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
                    const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, const Params p) {
-    using cfg = Cfg<BN, PAIR>;
+    using cfg = Cfg<BN, PAIR, WIDE>;
     constexpr int TM = PAIR ? 2 * BM : BM;          // rows of an output tile
     uint32_t cta_rank = 0;                          // 0 = leader of the pair (issues the MMAs)
     if constexpr (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
@@ -300,25 +346,41 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bars = smem_base + cfg::kStages * cfg::kStageBytes;
-    // barrier slots (8 bytes each): full[kStages], empty[kStages], conv[kStages], tmem_full[2], tmem_empty[2], then the TMEM base
+    const uint32_t bars = smem_base + cfg::kTileBytes;
+    // barrier slots (8 bytes each): full[kStages], empty[kStages], conv[kLoStages], lo_empty[kLoStages], tmem_full[2],
+    // tmem_empty[2], then the TMEM base and the epilogue flag
     constexpr int kConv = cfg::kConvWarps;
+    constexpr int kEpi0 = cfg::kEpi0;
+    constexpr int kS = cfg::kStages, kL = cfg::kLoStages;
     auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto empty_bar = [&](int s) { return bars + 8u * (cfg::kStages + s); };
-    auto conv_bar = [&](int s) { return bars + 8u * (2 * cfg::kStages + s); };
-    auto tfull_bar = [&](int a) { return bars + 8u * (3 * cfg::kStages + a); };
-    auto tempty_bar = [&](int a) { return bars + 8u * (3 * cfg::kStages + 2 + a); };
-    const uint32_t tmem_slot = bars + 8u * (3 * cfg::kStages + 4);
+    auto empty_bar = [&](int s) { return bars + 8u * (kS + s); };
+    auto conv_bar = [&](int l) { return bars + 8u * (2 * kS + l); };
+    auto loempty_bar = [&](int l) { return bars + 8u * (2 * kS + kL + l); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * kS + 2 * kL + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * kS + 2 * kL + 2 + a); };
+    constexpr int kSlotOff = 8 * (2 * kS + 2 * kL + 4);
+    static_assert(kSlotOff + 16 <= 256, "barrier block");
+    const uint32_t tmem_slot = bars + kSlotOff;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + cfg::kStages * cfg::kStageBytes + 8 * (3 * cfg::kStages + 4));
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + cfg::kTileBytes + kSlotOff);
+    // tile addresses (byte offsets from smem_base): s = fetch stage, l = lo-ring stage (not WIDE: the lo tiles live in stage s)
+    auto a_hi_off = [&](int s) { return (uint32_t)(s * cfg::kStageBytes); };
+    auto b_hi_off = [&](int s) { return (uint32_t)(s * cfg::kStageBytes + (WIDE ? kAPlaneBytes : 2 * kAPlaneBytes)); };
+    auto a_lo_off = [&](int s, int l) { return (uint32_t)(WIDE ? (kS + l) * cfg::kStageBytes : s * cfg::kStageBytes + kAPlaneBytes); };
+    auto b_lo_off = [&](int s, int l) {
+        return (uint32_t)(WIDE ? (kS + l) * cfg::kStageBytes + kAPlaneBytes : s * cfg::kStageBytes + 2 * kAPlaneBytes + cfg::kBPlaneBytes);
+    };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < cfg::kStages; ++s) {
+        for (int s = 0; s < kS; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
-            mbar_init(conv_bar(s), kConv > 0 ? kConv : 1);  // one arrival per converter warp
+        }
+        for (int l = 0; l < kL; ++l) {
+            mbar_init(conv_bar(l), kConv > 0 ? (PAIR ? 2 * kConv : kConv) : 1);  // one arrival per converter warp (pair: of both CTAs, on the leader's barrier)
+            mbar_init(loempty_bar(l), 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
@@ -346,9 +408,44 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
     const int sk_begin = unit_begin(p, lb), sk_end = unit_begin(p, lb + 1);
     const int dp_units = (p.dp_waves + (bid < p.dp_extra ? 1 : 0)) * p.cpt;
     const int my_units = dp_units + (sk_end - sk_begin);
-    const bool a_fused = kConv > 0 && p.a_fused, b_fused = kConv > 0 && p.b_fused;
+    const bool a_fused = WIDE || (kConv > 0 && p.a_fused), b_fused = WIDE || (kConv > 0 && p.b_fused);   // WIDE is launched for two fused operands only
     const uint32_t stage_tx = (uint32_t)((a_fused ? 1 : 2) * kAPlaneBytes + (b_fused ? 1 : 2) * cfg::kBPlaneBytes);
 
+    // ===================== converter warps: lo tiles from hi tiles, in shared memory =====================
+    auto run_converter = [&]() {
+        constexpr int NT = 32 * (kConv > 0 ? kConv : 1);
+        // converter thread index: the warps before the epilogue block (from warp 2), then the warps after it
+        const int ct = warp < kEpi0 ? (int)threadIdx.x - 64 : (int)threadIdx.x - 32 * (kEpi0 + kEpiWarps) + 32 * (kEpi0 - 2);
+        int s = 0, l = 0;
+        uint32_t ph = 0, lph = 0;
+        for (int i = 0; i < my_units; ++i) {
+            int tile, chunk;
+            unit_at(p, i, dp_units, sk_begin, nb, bid, tile, chunk);
+            const int kb0 = chunk * kChunkKb;
+            const int kb1 = min(p.num_kb, kb0 + kChunkKb);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(full_bar(s), ph);                              // this CTA's fp32 tiles have landed
+                if constexpr (WIDE) mbar_wait(loempty_bar(l), lph ^ 1u); // the MMAs that read this lo-ring stage have retired
+                if (a_fused) convert_plane<kAPlaneBytes / 16, NT>(smem_gen + a_hi_off(s), smem_gen + a_lo_off(s, l), ct);
+                if (b_fused) convert_plane<cfg::kBPlaneBytes / 16, NT>(smem_gen + b_hi_off(s), smem_gen + b_lo_off(s, l), ct);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to tcgen05.mma
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (PAIR) mbar_arrive_leader_release(conv_bar(l));
+                    else mbar_arrive(conv_bar(l));
+                }
+                if (++s == kS) { s = 0; ph ^= 1u; }
+                if (++l == kL) { l = 0; lph ^= 1u; }
+            }
+        }
+    };
+
+    // WIDE: the register file is re-divided per warpgroup; every warp of a warpgroup executes the SAME
+    // setmaxnreg instruction (warpgroup 0 here, warpgroups 1-2 at the top of the epilogue branch,
+    // warpgroup 3 at the top of the converter branch), and ptxas sizes each region accordingly.
+    if constexpr (cfg::kWide) {
+        if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    }
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
@@ -363,34 +460,39 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                 const int kb1 = min(p.num_kb, kb0 + kChunkKb);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty_bar(s), ph ^ 1u);
-                    const uint32_t st = smem_base + s * cfg::kStageBytes;
+                    const uint32_t a_hi = smem_base + a_hi_off(s), a_lo = smem_base + a_lo_off(s, s);
+                    const uint32_t b_hi = smem_base + b_hi_off(s), b_lo = smem_base + b_lo_off(s, s);   // lo tiles are fetched only when not fused (never WIDE)
+                    // Pair without converters: the bytes of both CTAs are counted on the LEADER's barrier (the
+                    // MMA issuer waits there).  With converters every CTA counts its own bytes on its own
+                    // barrier: its converter warps wait for them, and the leader's MMA issuer waits for the
+                    // converter warps of both CTAs.
+                    constexpr bool kLeaderFull = PAIR && kConv == 0;
                     auto load = [&](uint32_t dst, const CUtensorMap* map, int c0, int c1) {
-                        if constexpr (PAIR) tma_load_2d_pair(dst, map, full_bar(s), c0, c1);
+                        if constexpr (kLeaderFull) tma_load_2d_pair(dst, map, full_bar(s), c0, c1);
                         else tma_load_2d(dst, map, full_bar(s), c0, c1);
                     };
-                    // pair: the leader's barrier counts the bytes of both CTAs
-                    if (!PAIR || cta_rank == 0) mbar_expect_tx(full_bar(s), PAIR ? 2u * stage_tx : stage_tx);
+                    if (!kLeaderFull || cta_rank == 0) mbar_expect_tx(full_bar(s), kLeaderFull ? 2u * stage_tx : stage_tx);
                     if (!p.a_mn) {
-                        load(st, &map_ahi, kb * BK, m0);
-                        if (!a_fused) load(st + kAPlaneBytes, &map_alo, kb * BK, m0);
+                        load(a_hi, &map_ahi, kb * BK, m0);
+                        if (!a_fused) load(a_lo, &map_alo, kb * BK, m0);
                     } else {
 #pragma unroll
                         for (int i = 0; i < BM / 32; ++i) {
-                            load(st + i * 4096, &map_ahi, m0 + 32 * i, kb * BK);
-                            if (!a_fused) load(st + kAPlaneBytes + i * 4096, &map_alo, m0 + 32 * i, kb * BK);
+                            load(a_hi + i * 4096, &map_ahi, m0 + 32 * i, kb * BK);
+                            if (!a_fused) load(a_lo + i * 4096, &map_alo, m0 + 32 * i, kb * BK);
                         }
                     }
                     if (!p.b_mn) {
-                        load(st + 2 * kAPlaneBytes, &map_bhi, kb * BK, n0);
-                        if (!b_fused) load(st + 2 * kAPlaneBytes + cfg::kBPlaneBytes, &map_blo, kb * BK, n0);
+                        load(b_hi, &map_bhi, kb * BK, n0);
+                        if (!b_fused) load(b_lo, &map_blo, kb * BK, n0);
                     } else {
 #pragma unroll
                         for (int i = 0; i < cfg::kBRows / 32; ++i) {
-                            load(st + 2 * kAPlaneBytes + i * 4096, &map_bhi, n0 + 32 * i, kb * BK);
-                            if (!b_fused) load(st + 2 * kAPlaneBytes + cfg::kBPlaneBytes + i * 4096, &map_blo, n0 + 32 * i, kb * BK);
+                            load(b_hi + i * 4096, &map_bhi, n0 + 32 * i, kb * BK);
+                            if (!b_fused) load(b_lo + i * 4096, &map_blo, n0 + 32 * i, kb * BK);
                         }
                     }
-                    if (++s == cfg::kStages) { s = 0; ph ^= 1u; }
+                    if (++s == kS) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -409,8 +511,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
             // per 8-wide k-slice the descriptor start address moves by 32 B inside the swizzle row
             // (K-major) or by one 1024-byte group of 8 k-rows (MN-major); units of 16 B
             const uint64_t a_adv = p.a_mn ? 64u : 2u, b_adv = p.b_mn ? 64u : 2u;
-            int s = 0, as = 0;
-            uint32_t ph = 0, aph = 0;
+            int s = 0, l = 0, as = 0;
+            uint32_t ph = 0, lph = 0, aph = 0;
             for (int i = 0; i < my_units; ++i) {
                 int tile, chunk;
                 unit_at(p, i, dp_units, sk_begin, nb, bid, tile, chunk);
@@ -420,15 +522,19 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
                 for (int kb = c0; kb < c1; ++kb) {
-                    mbar_wait(full_bar(s), ph);        // TMA bytes have landed
-                    if (kConv > 0) mbar_wait(conv_bar(s), ph);  // ... and the converter warps have written the lo tiles
+                    if constexpr (PAIR && kConv > 0) {
+                        mbar_wait_cluster(conv_bar(l), lph);    // the converter warps of BOTH CTAs have seen their TMA bytes and written the lo tiles
+                    } else {
+                        mbar_wait(full_bar(s), ph);             // TMA bytes have landed
+                        if (kConv > 0) mbar_wait(conv_bar(l), lph);  // ... and the converter warps have written the lo tiles
+                    }
                     tcgen05_fence_after();
-                    const uint32_t st = smem_base + s * cfg::kStageBytes;
-                    const uint64_t ahi = p.a_mn ? make_mnmajor_sw128_desc(st) : make_kmajor_sw128_desc(st);
-                    const uint64_t alo = p.a_mn ? make_mnmajor_sw128_desc(st + kAPlaneBytes) : make_kmajor_sw128_desc(st + kAPlaneBytes);
-                    const uint64_t bhi = p.b_mn ? make_mnmajor_sw128_desc(st + 2 * kAPlaneBytes) : make_kmajor_sw128_desc(st + 2 * kAPlaneBytes);
-                    const uint64_t blo = p.b_mn ? make_mnmajor_sw128_desc(st + 2 * kAPlaneBytes + cfg::kBPlaneBytes)
-                                                : make_kmajor_sw128_desc(st + 2 * kAPlaneBytes + cfg::kBPlaneBytes);
+                    const uint32_t a_hi = smem_base + a_hi_off(s), a_lo = smem_base + a_lo_off(s, l);
+                    const uint32_t b_hi = smem_base + b_hi_off(s), b_lo = smem_base + b_lo_off(s, l);
+                    const uint64_t ahi = p.a_mn ? make_mnmajor_sw128_desc(a_hi) : make_kmajor_sw128_desc(a_hi);
+                    const uint64_t alo = p.a_mn ? make_mnmajor_sw128_desc(a_lo) : make_kmajor_sw128_desc(a_lo);
+                    const uint64_t bhi = p.b_mn ? make_mnmajor_sw128_desc(b_hi) : make_kmajor_sw128_desc(b_hi);
+                    const uint64_t blo = p.b_mn ? make_mnmajor_sw128_desc(b_lo) : make_kmajor_sw128_desc(b_lo);
 #pragma unroll
                     for (int k = 0; k < BK / 8; ++k) {
                         const uint64_t aa = a_adv * (uint64_t)k, ba = b_adv * (uint64_t)k;
@@ -437,44 +543,31 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                         mma(d_tmem, ahi + aa, bhi + ba, 1u);
                     }
                     commit(empty_bar(s));              // smem stage is free (in both CTAs) once these MMAs retire
-                    if (++s == cfg::kStages) { s = 0; ph ^= 1u; }
+                    if constexpr (WIDE) commit(loempty_bar(l));
+                    if (++s == kS) { s = 0; ph ^= 1u; }
+                    if (++l == kL) { l = 0; lph ^= 1u; }
                 }
                 commit(tfull_bar(as));                 // chunk accumulator complete
                 if (++as == 2) { as = 0; aph ^= 1u; }
             }
         }
-    } else if (kConv > 0 && warp >= 2 + kEpiWarps) {
-        // ===================== converter warps: lo tiles from hi tiles, in shared memory =====================
-        constexpr int NT = 32 * (kConv > 0 ? kConv : 1);
-        const int ct = (int)threadIdx.x - 32 * (2 + kEpiWarps);
-        int s = 0;
-        uint32_t ph = 0;
-        for (int i = 0; i < my_units; ++i) {
-            int tile, chunk;
-            unit_at(p, i, dp_units, sk_begin, nb, bid, tile, chunk);
-            const int kb0 = chunk * kChunkKb;
-            const int kb1 = min(p.num_kb, kb0 + kChunkKb);
-            for (int kb = kb0; kb < kb1; ++kb) {
-                mbar_wait(full_bar(s), ph);
-                uint8_t* st = smem_gen + s * cfg::kStageBytes;
-                if (a_fused) convert_plane<kAPlaneBytes / 16, NT>(st, st + kAPlaneBytes, ct);
-                if (b_fused) convert_plane<cfg::kBPlaneBytes / 16, NT>(st + 2 * kAPlaneBytes, st + 2 * kAPlaneBytes + cfg::kBPlaneBytes, ct);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to tcgen05.mma
-                __syncwarp();
-                if (lane == 0) mbar_arrive(conv_bar(s));
-                if (++s == cfg::kStages) { s = 0; ph ^= 1u; }
-            }
+    } else if (kConv > 0 && (warp < kEpi0 || warp >= kEpi0 + kEpiWarps)) {
+        // converter warps (in the WIDE layout: warps 2-3 of warpgroup 0 and the whole of warpgroup 3)
+        if constexpr (cfg::kWide) {
+            if (warp >= kEpi0 + kEpiWarps) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");   // warpgroup 3
         }
+        run_converter();
     } else {
         // ===================== epilogue warps 2..9 =====================
         // warp w may touch the TMEM lanes of quadrant (w & 3); the two warps of a quadrant split the
         // BN columns in halves.  Each thread owns ONE output row and HALF = BN/2 consecutive columns,
         // and keeps their running sum over the K chunks of a segment in registers.
+        if constexpr (cfg::kWide) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
         constexpr int HALF = BN / 2;
         const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int half = (warp - kEpi0) >> 2;
         const int trow = quad * 32 + lane;          // row inside the tile
-        int* s_flag = reinterpret_cast<int*>(smem_gen + cfg::kStages * cfg::kStageBytes + 8 * (3 * cfg::kStages + 4) + 8);
+        int* s_flag = reinterpret_cast<int*>(smem_gen + cfg::kTileBytes + kSlotOff + 8);
         int as = 0;
         uint32_t aph = 0;
         int i = 0;
@@ -539,7 +632,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                 epi_bar();
                 const int b_first = unit_owner(p, sk_tile * p.cpt), b_last = unit_owner(p, (sk_tile + 1) * p.cpt - 1);
                 unsigned int* ticket = p.tickets + (PAIR ? 2 * tile + (int)cta_rank : tile);   // the two halves of a pair's tile are finished independently
-                if (threadIdx.x == 64) *s_flag = (atomicAdd(ticket, 1u) == (unsigned)(b_last - b_first));
+                if (threadIdx.x == 32 * kEpi0) *s_flag = (atomicAdd(ticket, 1u) == (unsigned)(b_last - b_first));
                 epi_bar();
                 const bool last = (*s_flag != 0);
                 epi_bar();   // everyone has read the flag before the next segment overwrites it
@@ -549,7 +642,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                     // f = it * 256 + t (fully coalesced), 8 float4 per thread per pass with the loads
                     // of 2 segments in flight together.
                     __threadfence();
-                    const int t = threadIdx.x - 64;
+                    const int t = threadIdx.x - 32 * kEpi0;
                     constexpr int F4_PER_ROW = BN / 4;
                     constexpr int PASSES = BM * BN / 4 / 256 / 8;
                     for (int pass = 0; pass < PASSES; ++pass) {
@@ -596,7 +689,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                             }
                         }
                     }
-                    if (threadIdx.x == 64) *ticket = 0;
+                    if (threadIdx.x == 32 * kEpi0) *ticket = 0;
                 }
             }
         }
@@ -749,12 +842,12 @@ static int make_map(CUtensorMap* map, const float* base, int inner, int outer, s
 }
 
 // `workers` = CTAs, or CTA pairs (clusters of 2: the two SMs of a TPC) when PAIR
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, bool WIDE = false>
 static int launch(Ctx* ctx, const CUtensorMap* maps, const Params& p, int workers) {
-    using cfg = Cfg<BN, PAIR>;
+    using cfg = Cfg<BN, PAIR, WIDE>;
     static bool attr_set = false;
     if (!attr_set) {
-        DSC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::kSmemBytes));
+        DSC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, PAIR, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::kSmemBytes));
         attr_set = true;
     }
     cudaLaunchConfig_t lc = {};
@@ -769,7 +862,7 @@ static int launch(Ctx* ctx, const CUtensorMap* maps, const Params& p, int worker
     at[0].val.clusterDim.z = 1;
     lc.attrs = at;
     lc.numAttrs = PAIR ? 1 : 0;
-    DSC_CUDA_CHECK(cudaLaunchKernelEx(&lc, gemm_tf32x3_kernel<BN, PAIR>, maps[0], maps[1], maps[2], maps[3], p));
+    DSC_CUDA_CHECK(cudaLaunchKernelEx(&lc, gemm_tf32x3_kernel<BN, PAIR, WIDE>, maps[0], maps[1], maps[2], maps[3], p));
     DSC_LAUNCH_CHECK(ctx);
     return DSC_OK;
 }
@@ -836,6 +929,14 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
     static const int force_pair0 = [] { const char* e = getenv("DSC_GEMM_PAIR"); return e ? atoi(e) : -1; }();   // -1: planner decides
     const int force_pair = ctx->gemm_force_pair >= 0 ? ctx->gemm_force_pair : force_pair0;
     const int force_split = ctx->gemm_force_split;
+    // Kernel variants with converter warps (Cfg::kConvWarps > 0).  The WIDE pair kernel is correct but
+    // measured slower than pre-pass + plain pair kernel on every shape tried (8192 x 1024 x 1024:
+    // 91.5 us against 80.6 us including the pre-pass): the in-kernel split repeats the conversion for
+    // every tile that re-reads an operand and its 64 KB of converter traffic per k-block competes with
+    // the MMA operand fetch for shared-memory bandwidth.  It is only planned when asked for
+    // (dsc_gemm_tune fuse = 2), which is how the parity tests and tools/gemm_sweep.py reach it.
+    const bool allow_wide = ctx->gemm_force_fuse == 2;
+    auto has_converters = [allow_wide](int c, bool pr) { return pr ? (allow_wide && c == 256) : c < 256; };
     int bn = 256, grid = 1, dp_waves = 0, dp_extra = 0, sk_units_total = 0, perm_s = 0;
     bool pair = false;
     {
@@ -857,8 +958,9 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
             const int workers = pr ? ctx->sm_count / 2 : ctx->sm_count;
             const int ctas_per_worker = pr ? 2 : 1;
             const int brows = pr ? c / 2 : c;
-            const bool can_fuse = fuse_env && !pr && c < 256;
-            const bool fa = can_fuse && pa.direct, fb = can_fuse && pb.direct;
+            const bool can_fuse = fuse_env && has_converters(c, pr);
+            bool fa = can_fuse && pa.direct, fb = can_fuse && pb.direct;
+            if (pr) fa = fb = (fa && fb);   // the pair kernel splits both operands in the kernel or neither
             const double bytes_kb = (double)BM * (fa ? 128.0 : 256.0) + (double)brows * (fb ? 128.0 : 256.0);
             const double smem_kb = (double)BM * (fa ? 6.0 : 5.0) + (double)brows * (fb ? 6.0 : 5.0);
             // pre-pass for the operands that are not split in the kernel: 8 bytes per element at ~5 TB/s + launch
@@ -921,7 +1023,8 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
     p.base = sk_units_total / grid;
     p.rem = sk_units_total % grid;
     static const bool debug_plan = [] { const char* e = getenv("DSC_GEMM_DEBUG"); return e && *e == '1'; }();
-    const bool a_fused = fuse_env && !pair && bn < 256 && pa.direct, b_fused = fuse_env && !pair && bn < 256 && pb.direct;
+    bool a_fused = fuse_env && has_converters(bn, pair) && pa.direct, b_fused = fuse_env && has_converters(bn, pair) && pb.direct;
+    if (pair) a_fused = b_fused = (a_fused && b_fused);
     if (debug_plan)
         fprintf(stderr, "[dsc gemm] m=%d n=%d k=%d ta=%d tb=%d: BN=%d pair=%d grid=%d cpt=%d dp_waves=%d dp_extra=%d sk_units=%d perm_s=%d fused=%d%d\n", m, n, k, ta, tb, bn,
                 (int)pair, grid, cpt, dp_waves, dp_extra, sk_units_total, perm_s, (int)a_fused, (int)b_fused);
@@ -978,7 +1081,8 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
     }
     int s;
     if (pair) {
-        if (bn == 256) s = launch<256, true>(ctx, maps, p, grid);
+        if (bn == 256 && a_fused && b_fused) s = launch<256, true, true>(ctx, maps, p, grid);
+        else if (bn == 256) s = launch<256, true>(ctx, maps, p, grid);
         else if (bn == 128) s = launch<128, true>(ctx, maps, p, grid);
         else s = launch<64, true>(ctx, maps, p, grid);
     } else {
@@ -1001,6 +1105,6 @@ extern "C" int dsc_gemm_tune(dsc_ctx_t c, int bn, int pair, int split, int fuse)
     ctx->gemm_force_bn = bn;
     ctx->gemm_force_pair = pair < 0 ? -1 : (pair != 0);
     ctx->gemm_force_split = split;
-    ctx->gemm_force_fuse = fuse < 0 ? -1 : (fuse != 0);
+    ctx->gemm_force_fuse = fuse < 0 ? -1 : (fuse > 2 ? 2 : fuse);
     return DSC_OK;
 }

@@ -150,6 +150,38 @@ def test_gemm_all_transposes_against_openblas(cuda_provider, dtype, m, k, n):
             assert np.all(np.abs(got - exact) <= bound + RTOL[np.dtype(dtype)] * np.abs(bias).max())
 
 
+@pytest.mark.parametrize("bn,pair,split,fuse", [(256, 0, -1, 0), (128, 0, -1, 0), (128, 0, -1, 1), (64, 0, -1, 1), (64, 0, 2, 1),
+                                                (256, 1, -1, 0), (256, 1, 2, 0), (128, 1, -1, 0), (64, 1, -1, 0), (256, 1, -1, 2), (256, 1, 4, 2)])
+@pytest.mark.parametrize("m,k,n", [(512, 1024, 512), (300, 520, 260), (1024, 96, 2048)])
+def test_f32_tensor_core_gemm_variants(cuda_provider, bn, pair, split, fuse, m, k, n):
+    """Every plan of the tcgen05 kernel (tile width, 1-CTA / 2-CTA cta_group::2, split-K, in-kernel operand
+    split) pinned with dsc_gemm_tune, all four operand layouts, against OpenBLAS sgemm; the same plan twice
+    gives the same bits (deterministic fix-up order)."""
+    from sigma.diffsharp_b200._lib import check, lib
+    b, o = backend(cuda_provider, np.float32), OracleBackend(np.float32)
+    rng = np.random.default_rng(m + n + bn)
+    A = (rng.random((m, k)) * 2 - 1).astype(np.float32)
+    B = (rng.random((k, n)) * 2 - 1).astype(np.float32)
+    bias = rng.standard_normal(m).astype(np.float32)
+    bound = RTOL[np.dtype(np.float32)] * (np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64))
+    st0 = cuda_provider.ctx.stats()
+    check(lib.dsc_gemm_tune(cuda_provider.ctx.handle, bn, pair, split, fuse))
+    try:
+        for ta in (0, 1):
+            for tb in (0, 1):
+                As = np.ascontiguousarray(A.T if ta else A)
+                Bs = np.ascontiguousarray(B.T if tb else B)
+                ref = o.gemm(ta, tb, m, n, k, As.reshape(-1), Bs.reshape(-1), bias).reshape(m, n).astype(np.float64)
+                dA, dB, dbias = b.CreateDataBuffer(As.reshape(-1)), b.CreateDataBuffer(Bs.reshape(-1)), b.CreateDataBuffer(bias)
+                got = [b._out(b._f["gemm"], m * n, ta, tb, m, n, k, dA.handle, dB.handle, dbias.handle).SubData.reshape(m, n) for _ in range(2)]
+                assert np.array_equal(got[0], got[1])
+                assert np.all(np.abs(got[0].astype(np.float64) - ref) <= bound + 1e-30), (ta, tb, float(np.abs(got[0] - ref).max()))
+    finally:
+        check(lib.dsc_gemm_tune(cuda_provider.ctx.handle, -1, -1, -1, -1))
+    st1 = cuda_provider.ctx.stats()
+    assert st1["gemm_tcgen05"] - st0["gemm_tcgen05"] == 8     # none of the calls fell back to the CUDA-core kernel
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_gemv_ger_colsum_larger(cuda_provider, dtype):
     b, o = backend(cuda_provider, dtype), OracleBackend(dtype)
