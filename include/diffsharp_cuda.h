@@ -266,6 +266,9 @@ DSC_DECLARE_TYPED(d, double)
 DSC_API int dsc_comm_unique_id(uint8_t out[128]);
 DSC_API int dsc_comm_init(dsc_ctx_t ctx, int nranks, int rank, const uint8_t id[128]);
 DSC_API int dsc_comm_join(dsc_ctx_t ctx); /* compute stream waits for everything queued on the comm stream */
+/* %globaltimer (ns) at the phase boundaries of the last peer-memory all-reduce as CTA 0 saw them:
+ * start, packed, barrier 1, reduced + broadcast, barrier 2, unpacked (tools/allreduce_bench.py). */
+DSC_API int dsc_comm_debug_stamps(dsc_ctx_t ctx, uint64_t out[6]);
 DSC_API int dsc_comm_destroy(dsc_ctx_t ctx);
 
 #ifdef __cplusplus

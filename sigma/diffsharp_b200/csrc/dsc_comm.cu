@@ -3,17 +3,17 @@
 //
 // Sum of the weight adjoints (dsc_?allreduce_sum), up to 8 GPUs of one NVSwitch node: ONE kernel over
 // peer memory.  Every rank owns a symmetric buffer (flags | region A | region B) that all peers map
-// through CUDA IPC at dsc_comm_init.  The kernel (64 CTAs on the compute stream, captured in the
-// step's CUDA graph like any other kernel)
-//   0. packs the rank's adjoint buffers into its region A,
-//   1. barrier (flags written into every peer's memory with release stores, acquire spins),
-//   2. reduce-scatter + all-gather in one pass: rank r adds slice r of all N regions A — P2P loads
-//      over NVLink, peers added in rank order 0..N-1, so the sum is bit-identical on every rank and
-//      from run to run — and stores the result into region B of EVERY rank (P2P stores),
+// through CUDA IPC at dsc_comm_init.  The kernel (one CTA per SM on the compute stream, captured in
+// the step's CUDA graph like any other kernel) pushes: every byte that crosses NVLink is a store.
+//   0. scatter: slice q of the rank's (packed) adjoint buffers -> region A of rank q, slot [rank],
+//   1. barrier (one flag per peer, written into the peer's memory; relaxed stores and polls between
+//      two system fences),
+//   2. rank r adds the N slots of its region A (local) in rank order 0..N-1, so the sum is bit-identical
+//      on every rank and from run to run, and stores the result slice into region B of EVERY rank,
 //   3. barrier,
 //   4. unpacks region B into the adjoint buffers.
-// 7.45 MB over 8 GPUs: ~6.5 MB in and out per GPU instead of NCCL's pack -> ring/tree -> unpack
-// (measured 110 us); no staging copies on the NCCL stream, no event hand-offs.
+// No staging copies on a second stream, no event hand-offs, deterministic.  Measured (7.45 MB,
+// tools/allreduce_bench.py): see profiles/README.md.
 // NCCL remains for the bootstrap (exchange of the IPC handles), for the Jacobian all-gather, and
 // as the all-reduce path when peer access is not available (more than 8 ranks, no P2P, payload
 // larger than the symmetric buffer).  Collectives issued through NCCL run on the context's
@@ -140,28 +140,53 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 
+__device__ __forceinline__ void st_relaxed_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_relaxed_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // All CTAs of this rank have finished the phase -> tell every peer (flag[rank] = value in the peer's
 // header) -> wait until every peer has told us.  `arrivals` is the cumulative CTA count expected at
 // the local counter.  A 4 s timeout turns a lost peer into an error word instead of a hung GPU.
+// Cost matters here (two barriers per all-reduce): ONE system fence per CTA on the way in, the flags of
+// all peers written in parallel by the lanes of one warp with relaxed stores (a release store per peer
+// is a system fence per peer: measured 78 us per all-reduce at 8 ranks against 37 us at 2), relaxed
+// polling, one system fence on the way out.
 __device__ __forceinline__ void p2p_barrier(const P2PArgs& a, unsigned int value, unsigned int arrivals, bool reset_counter) {
     unsigned int* flags = reinterpret_cast<unsigned int*>(a.peer[a.rank]);
     unsigned int* sync = reinterpret_cast<unsigned int*>(a.peer[a.rank] + 256);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        if (atomicAdd(&sync[0], 1u) == arrivals - 1u) {
-            if (reset_counter) sync[0] = 0;
-            for (int q = 0; q < a.nranks; ++q) st_release_sys(reinterpret_cast<unsigned int*>(a.peer[q]) + a.rank, value);
-        }
-    }
-    if (threadIdx.x < (unsigned)a.nranks) {
-        const unsigned long long t0 = globaltimer_ns();
-        while ((int)(ld_acquire_sys(flags + threadIdx.x) - value) < 0) {
-            if (globaltimer_ns() - t0 > 4000000000ull) {
-                sync[2] = 1;
-                break;
+    if (threadIdx.x < 32) {
+        const unsigned lane = threadIdx.x;
+        unsigned int last = 0;
+        if (lane == 0) {
+            // release pattern at GPU scope per CTA; the CTA that arrives last issues the ONE system fence,
+            // which is cumulative over everything it observed (the other CTAs' stores, local and peer)
+            __threadfence();
+            last = atomicAdd(&sync[0], 1u) == arrivals - 1u;
+            if (last) {
+                if (reset_counter) sync[0] = 0;
+                __threadfence_system();
             }
         }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last && lane < (unsigned)a.nranks) st_relaxed_sys(reinterpret_cast<unsigned int*>(a.peer[lane]) + a.rank, value);
+        if (lane < (unsigned)a.nranks) {
+            const unsigned long long t0 = globaltimer_ns();
+            unsigned int spins = 0;
+            while ((int)(ld_relaxed_sys(flags + lane) - value) < 0) {
+                if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
+                    sync[2] = 1;
+                    break;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) __threadfence_system();            // acquire side: peers' data written before their flags is visible
     }
     __syncthreads();
 }
@@ -177,34 +202,39 @@ struct P2PTable {
     int count;
 };
 
-// buffers <-> region (PACK: buffers -> region).  Grid-stride per segment, 128-bit when the buffer is aligned.
-template <typename T, bool PACK>
-__device__ __forceinline__ void p2p_move(const P2PTable<T>& t, T* __restrict__ region, long long gtid, long long gsize) {
+// Region B -> buffers.  Grid-stride per segment, 128-bit when the buffer is aligned.
+template <typename T>
+__device__ __forceinline__ void p2p_unpack(const P2PTable<T>& t, const T* __restrict__ region, long long gtid, long long gsize) {
     using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
     constexpr int W = 16 / (int)sizeof(T);
     for (int s = 0; s < t.count; ++s) {
         T* p = t.ptr[s];
-        T* r = region + t.start[s];
+        const T* r = region + t.start[s];
         const long long n = t.len[s];
         long long done = 0;
         if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
             const long long nv = n / W;
             V* pv = reinterpret_cast<V*>(p);
-            V* rv = reinterpret_cast<V*>(r);
+            const V* rv = reinterpret_cast<const V*>(r);
 #pragma unroll 4
-            for (long long i = gtid; i < nv; i += gsize) {
-                if (PACK) rv[i] = pv[i];
-                else pv[i] = __ldcg(rv + i);
-            }
+            for (long long i = gtid; i < nv; i += gsize) pv[i] = __ldcg(rv + i);
             done = nv * W;
         }
-        for (long long i = done + gtid; i < n; i += gsize) {
-            if (PACK) r[i] = p[i];
-            else p[i] = __ldcg(r + i);
-        }
+        for (long long i = done + gtid; i < n; i += gsize) p[i] = __ldcg(r + i);
     }
 }
 
+// Push design: every byte that crosses NVLink is a STORE (fire and forget; the system fence of the
+// following barrier waits for them), never a load whose round trip a thread would have to sit out.
+//   0. scatter: element e of the packed (16-byte aligned) concatenation of this rank's buffers belongs
+//      to slice q = e / slice_len; it is written into region A of rank q, slot [rank] — the buffers
+//      are read once, locally, with 128-bit loads, and pack + reduce-scatter exchange are one pass,
+//   1. barrier,
+//   2. rank r adds the N slots of its region A (local reads) in rank order 0..N-1 — the sum is
+//      bit-identical on every rank and from run to run — and stores the result slice into region B of
+//      EVERY rank (all-gather by stores),
+//   3. barrier,
+//   4. region B (local) -> buffers.
 template <typename T>
 __global__ void __launch_bounds__(kP2PThreads) allreduce_p2p_kernel(P2PTable<T> t, P2PArgs a) {
     using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
@@ -214,37 +244,69 @@ __global__ void __launch_bounds__(kP2PThreads) allreduce_p2p_kernel(P2PTable<T> 
     const unsigned int epoch = sync[1];   // bumped by CTA 0 after the second barrier: every CTA has read it by then
     const long long total = t.start[t.count];   // multiple of W
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x, gsize = (long long)gridDim.x * blockDim.x;
-    T* regA = reinterpret_cast<T*>(local + kP2PHeaderBytes);
-    T* regB = reinterpret_cast<T*>(local + kP2PHeaderBytes + a.region_bytes);
-    // 0. pack
-    p2p_move<T, true>(t, regA, gtid, gsize);
-    // 1. every rank has packed
-    p2p_barrier(a, 2u * epoch + 1u, gridDim.x, false);
-    // 2. slice `rank` of the sum: all peer loads of a vector are in flight together (one NVLink round
-    //    trip per vector, not one per peer), added in rank order; the result goes to region B of every rank
     const long long nvec = total / W;
-    const long long per = (nvec + a.nranks - 1) / a.nranks;
-    const long long v0 = per * a.rank, v1 = min(nvec, v0 + per);
-    for (long long v = v0 + gtid; v < v1; v += gsize) {
-        V x[kP2PMaxRanks];
-#pragma unroll
-        for (int p = 0; p < kP2PMaxRanks; ++p)
-            if (p < a.nranks) x[p] = __ldcg(reinterpret_cast<const V*>(a.peer[p] + kP2PHeaderBytes) + v);
-        V acc = x[0];
-#pragma unroll
-        for (int p = 1; p < kP2PMaxRanks; ++p)
-            if (p < a.nranks) {
-                acc.x += x[p].x; acc.y += x[p].y;
-                if constexpr (W == 4) { acc.z += x[p].z; acc.w += x[p].w; }
+    const long long per = (nvec + a.nranks - 1) / a.nranks;   // vectors per slice (the last slice may be short)
+    unsigned long long* stamps = reinterpret_cast<unsigned long long*>(local + 512);   // phase boundaries as CTA 0 sees them (dsc_comm_debug_stamps)
+    const bool stamp = blockIdx.x == 0 && threadIdx.x == 0;
+    if (stamp) stamps[0] = globaltimer_ns();
+    // 0. scatter this rank's contribution: slice q -> rank q, region A, slot [rank]
+    for (int s = 0; s < t.count; ++s) {
+        const T* p = t.ptr[s];
+        const long long v_seg = t.start[s] / W;   // first vector of the segment in the packed space
+        const long long n = t.len[s];
+        long long done = 0;
+        if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+            const long long nv = n / W;
+            const V* pv = reinterpret_cast<const V*>(p);
+#pragma unroll 4
+            for (long long i = gtid; i < nv; i += gsize) {
+                const V x = pv[i];
+                const long long v = v_seg + i;
+                const int q = (int)(v / per);
+                reinterpret_cast<V*>(a.peer[q] + kP2PHeaderBytes)[(long long)a.rank * per + (v - q * per)] = x;
             }
-#pragma unroll
-        for (int q = 0; q < kP2PMaxRanks; ++q)
-            if (q < a.nranks) reinterpret_cast<V*>(a.peer[q] + kP2PHeaderBytes + a.region_bytes)[v] = acc;
+            done = nv * W;
+        }
+        for (long long i = done + gtid; i < n; i += gsize) {   // unaligned buffer, or the tail of a segment
+            const long long e = t.start[s] + i;
+            const long long v = e / W;
+            const int q = (int)(v / per);
+            reinterpret_cast<T*>(a.peer[q] + kP2PHeaderBytes)[((long long)a.rank * per + (v - q * per)) * W + (e - v * W)] = p[i];
+        }
     }
+    if (stamp) stamps[1] = globaltimer_ns();
+    // 1. every rank's contribution to our slice has landed
+    p2p_barrier(a, 2u * epoch + 1u, gridDim.x, false);
+    if (stamp) stamps[2] = globaltimer_ns();
+    // 2. our slice of the sum (slots added in rank order), stored into region B of every rank
+    {
+        const V* slots = reinterpret_cast<const V*>(local + kP2PHeaderBytes);
+        const long long v0 = per * a.rank;
+        const long long mine = max(0ll, min(per, nvec - v0));
+        for (long long i = gtid; i < mine; i += gsize) {
+            V x[kP2PMaxRanks];
+#pragma unroll
+            for (int r = 0; r < kP2PMaxRanks; ++r)
+                if (r < a.nranks) x[r] = __ldcg(slots + (long long)r * per + i);
+            V acc = x[0];
+#pragma unroll
+            for (int r = 1; r < kP2PMaxRanks; ++r)
+                if (r < a.nranks) {
+                    acc.x += x[r].x; acc.y += x[r].y;
+                    if constexpr (W == 4) { acc.z += x[r].z; acc.w += x[r].w; }
+                }
+#pragma unroll
+            for (int q = 0; q < kP2PMaxRanks; ++q)
+                if (q < a.nranks) reinterpret_cast<V*>(a.peer[q] + kP2PHeaderBytes + a.region_bytes)[v0 + i] = acc;
+        }
+    }
+    if (stamp) stamps[3] = globaltimer_ns();
     // 3. every slice has landed everywhere
     p2p_barrier(a, 2u * epoch + 2u, 2u * gridDim.x, true);
+    if (stamp) stamps[4] = globaltimer_ns();
     // 4. unpack
-    p2p_move<T, false>(t, regB, gtid, gsize);
+    p2p_unpack<T>(t, reinterpret_cast<const T*>(local + kP2PHeaderBytes + a.region_bytes), gtid, gsize);
+    if (stamp) stamps[5] = globaltimer_ns();
     // the CTA counter was reset by the last arriver of barrier 3; the epoch is bumped by CTA 0 after
     // ITS threads left that barrier (all CTAs read the epoch before arriving at barrier 1)
     if (blockIdx.x == 0 && threadIdx.x == 0) sync[1] = epoch + 1u;
@@ -275,7 +337,7 @@ static int allreduce_impl(dsc_ctx_t c, int32_t count, const dsc_buf_t* bufs) {
     if (t.count == 0) return DSC_OK;
     const int dt = sizeof(T) == 4 ? NCCL_FLOAT32 : NCCL_FLOAT64;
     const long long total = t.start[t.count];
-    if (ctx->p2p_ok && (size_t)(total + 4 * t.count) * sizeof(T) <= ctx->p2p_region_bytes) {
+    if (ctx->p2p_ok && (size_t)(total + 4 * t.count) * sizeof(T) + 16 * kP2PMaxRanks <= ctx->p2p_region_bytes) {
         // one kernel over peer memory on the compute stream (ordered after the producers by stream order)
         if (ctx->comm_pending) {   // a collective issued through NCCL may still be writing these buffers
             DSC_CUDA_CHECK(cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
@@ -456,6 +518,15 @@ int dsc_comm_init(dsc_ctx_t c, int nranks, int rank, const uint8_t idbytes[128])
     DSC_NCCL_CHECK(g_nccl.CommInitRank(&comm, nranks, id, rank));
     ctx->nccl_comm = comm;
     return p2p_setup(ctx);
+}
+
+int dsc_comm_debug_stamps(dsc_ctx_t c, uint64_t out[6]) {
+    if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
+    Ctx* ctx = as_ctx(c);
+    if (!ctx->p2p_local) return fail(DSC_E_NCCL, "the peer-memory all-reduce is not set up");
+    DSC_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    DSC_CUDA_CHECK(cudaMemcpy(out, reinterpret_cast<char*>(ctx->p2p_local) + 512, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return DSC_OK;
 }
 
 int dsc_comm_join(dsc_ctx_t c) {

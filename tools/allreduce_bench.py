@@ -45,6 +45,14 @@ for _ in range(5):
     ctx.sync()
     best = min(best, D.max_over_ranks(ctx.elapsed_ms(e0, e1)))
 st = ctx.stats()
+if st["allreduce_p2p"]:
+    import ctypes as C
+    from sigma.diffsharp_b200._lib import check, lib
+    stamps = (C.c_uint64 * 6)()
+    check(lib.dsc_comm_debug_stamps(ctx.handle, stamps))
+    d = [(stamps[i + 1] - stamps[i]) / 1e3 for i in range(5)]
+    print(f"rank {rank}: last call, CTA 0: pack {d[0]:.1f} us | barrier {d[1]:.1f} | reduce+broadcast {d[2]:.1f} | barrier {d[3]:.1f} | unpack {d[4]:.1f}", flush=True)
+D.barrier()
 if rank == 0:
     nbytes = sum(sizes) * 4
     print(f"world {world}: all-reduce of {nbytes / 1e6:.2f} MB: {best / R * 1e3:.1f} us per call "
