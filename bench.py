@@ -435,7 +435,10 @@ def run_ours(args):
     hY[...] = Y
     n_params = sum(w.size for w in Ws) + sum(b.size for b in bs)
     h2d = (X.size + Y.size) * 4
-    d2h = n_params * 4 + 4
+    # The all-reduced adjoints are identical on every rank: the job reads them back to the host ONCE
+    # (rank 0); every rank reads back the loss of its own rows.  d2h_bytes_per_step is rank 0's count.
+    read_grads = rank == 0
+    d2h = (n_params * 4 if read_grads else 0) + 4
     sets = []
     for s_ in range(2):
         bX = CudaDataBuffer.empty(ctx, np.float32, X.size)
@@ -450,7 +453,7 @@ def run_ours(args):
         L, dW, db = D.sharded_mlp_grad(comm, st["eX"], st["eY"], dWs, dbs)   # Sum_M inside returns the loss to the host
         comm.join()
         off = 0
-        for a in [w.Buffer.DataBuffer for w in dW] + [v.Buffer for v in db]:
+        for a in ([w.Buffer.DataBuffer for w in dW] + [v.Buffer for v in db]) if read_grads else []:
             check(lib.dsc_buf_download_async(a.handle, 0, st["hG"].ctypes.data + 4 * off, a.Length))
             off += a.Length
         ctx.sync()
@@ -476,7 +479,8 @@ def run_ours(args):
         finally:
             st["graph"] = ctx.graph_end()
             st["loss"], backend.capture_scalars = backend.capture_scalars[0], None
-        st["outs"] = [w.Buffer.DataBuffer for w in cW] + [v.Buffer for v in cb]
+        st["outs"] = ([w.Buffer.DataBuffer for w in cW] + [v.Buffer for v in cb]) if read_grads else []
+        st["keep"] = (cW, cb)
 
     def queue_upload(st):
         check(lib.dsc_copy_upload(st["bX"].handle, 0, hX.ctypes.data, X.size))
@@ -488,7 +492,7 @@ def run_ours(args):
         for a in st["outs"]:
             check(lib.dsc_copy_download(a.handle, 0, st["hG"].ctypes.data + 4 * off, a.Length))
             off += a.Length
-        check(lib.dsc_copy_download(st["loss"].handle, 0, st["hG"].ctypes.data + 4 * off, 1))
+        check(lib.dsc_copy_download(st["loss"].handle, 0, st["hG"].ctypes.data + 4 * n_params, 1))
         check(lib.dsc_event_record_copy(ctx.handle, st["ev"]))
 
     def e2e_loop(nsteps):
@@ -519,6 +523,7 @@ def run_ours(args):
     loss_e2e = losses[-1]
     for st in sets:
         st["outs"] = None
+        st["keep"] = None
         st["loss"] = None
         ctx.graph_destroy(st["graph"])
 
@@ -555,15 +560,18 @@ def run_ours(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(graph_ms, 4), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "C3: reverse-mode grad of 784-1024-1024-10 tanh MLP loss, global batch 8192, float32",
-                   "global_batch": GLOBAL_BATCH, "rows_per_gpu": rows, "parallelism": f"batch-row shards x{world} + NCCL all-reduce of adjoints ({ALLREDUCE_MB} MB)",
+                   "global_batch": GLOBAL_BATCH, "rows_per_gpu": rows,
+                   "parallelism": f"batch-row shards x{world} + one all-reduce of the adjoints ({ALLREDUCE_MB} MB; peer-memory kernel over NVLink: "
+                                  f"{st['allreduce_p2p']} calls, NCCL: {st['allreduce_nccl']} calls)",
                    "mode": "CUDA-graph replay of the captured Backend<'T> call sequence",
                    "l2": f"no flush between steps: per-rank working set {st['pool_bytes_reserved'] / 1e6:.0f} MB streams through the 126 MB L2"},
         "eager": {"value": round(1e3 / eager_ms, 3), "unit": "steps/s", "ms_per_step": round(eager_ms, 4),
                   "note": "same step driven op by op from Python through the C ABI (host-bound)"},
         "e2e": {"value": round(1e3 / e2e_ms, 3), "unit": "steps/s", "ms_per_step": round(e2e_ms, 4),
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "mode": "host X/Y rows -> device every step, loss + all adjoints -> host every step; the step is a CUDA-graph replay of the "
-                        "captured call sequence; copies of steps i+2 / i ride the copy stream while step i+1 computes (2 input sets)"},
+                "mode": "every rank: its X/Y rows host -> device every step and its loss -> host every step; rank 0 also reads all (all-reduced) "
+                        "adjoints back every step; the step is a CUDA-graph replay of the captured call sequence; copies of steps i+2 / i ride "
+                        "the copy stream while step i+1 computes (2 input sets)"},
         "e2e_eager": {"value": round(1e3 / e2e_eager_ms, 3), "unit": "steps/s", "ms_per_step": round(e2e_eager_ms, 4),
                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                       "mode": "the same, but the step is driven op by op through the plugin interface (no graph, no copy/compute overlap)"},
