@@ -493,7 +493,7 @@ def run_ours(args):
             check(lib.dsc_copy_download(a.handle, 0, st["hG"].ctypes.data + 4 * off, a.Length))
             off += a.Length
         check(lib.dsc_copy_download(st["loss"].handle, 0, st["hG"].ctypes.data + 4 * n_params, 1))
-        check(lib.dsc_event_record_copy(ctx.handle, st["ev"]))
+        check(lib.dsc_event_record_copy_down(ctx.handle, st["ev"]))   # downloads ride their own stream: PCIe is full duplex
 
     def e2e_loop(nsteps):
         queue_upload(sets[0])
@@ -501,7 +501,9 @@ def run_ours(args):
         losses = []
         for i in range(nsteps):
             st = sets[i % 2]
-            check(lib.dsc_compute_wait_event(ctx.handle, st["ev_up"]))  # step i's inputs have landed (and step i-2's results were read)
+            check(lib.dsc_compute_wait_event(ctx.handle, st["ev_up"]))  # step i's inputs have landed
+            if i >= 2:
+                check(lib.dsc_compute_wait_event(ctx.handle, st["ev"]))  # ... and step i-2's results (same output buffers) were read
             ctx.graph_launch(st["graph"])
             check(lib.dsc_copy_wait_compute(ctx.handle))   # copies queued from here on wait for step i
             queue_download(st)                             # D2H: loss + all adjoints of step i

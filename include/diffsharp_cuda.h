@@ -133,7 +133,8 @@ DSC_API int dsc_event_create(dsc_ctx_t ctx, dsc_event_t* ev);
 DSC_API int dsc_event_record(dsc_ctx_t ctx, dsc_event_t ev);
 DSC_API int dsc_event_elapsed_ms(dsc_ctx_t ctx, dsc_event_t start, dsc_event_t stop, float* ms);
 DSC_API int dsc_event_destroy(dsc_ctx_t ctx, dsc_event_t ev);
-DSC_API int dsc_event_record_copy(dsc_ctx_t ctx, dsc_event_t ev); /* record on the copy stream           */
+DSC_API int dsc_event_record_copy(dsc_ctx_t ctx, dsc_event_t ev); /* record on the upload copy stream    */
+DSC_API int dsc_event_record_copy_down(dsc_ctx_t ctx, dsc_event_t ev); /* record on the download copy stream */
 DSC_API int dsc_event_sync(dsc_ctx_t ctx, dsc_event_t ev);        /* host waits for a recorded event      */
 DSC_API int dsc_compute_wait_event(dsc_ctx_t ctx, dsc_event_t ev);/* compute stream waits for the event   */
 /* CUDA-graph capture of a replayed call sequence (static shapes): begin, issue the calls once,
@@ -161,10 +162,12 @@ DSC_API int dsc_buf_upload(dsc_buf_t h, int32_t off, const void* host, int32_t n
 DSC_API int dsc_buf_download(dsc_buf_t h, int32_t off, void* host, int32_t n);                /* .Data / .SubData    */
 DSC_API int dsc_buf_upload_async(dsc_buf_t h, int32_t off, const void* pinned_host, int32_t n);
 DSC_API int dsc_buf_download_async(dsc_buf_t h, int32_t off, void* pinned_host, int32_t n);
-/* The same copies on the context's COPY stream, so that the host<->device traffic of minibatch i+1 / i-1
- * overlaps the kernels of minibatch i.  dsc_copy_wait_compute: copies queued after this call start only
- * when the compute work queued so far has finished; dsc_compute_wait_copy: the converse;
- * dsc_copy_sync: the host waits for the copy stream. */
+/* The same copies on the context's COPY streams (one per direction: PCIe is full duplex), so that the
+ * host<->device traffic of minibatch i+1 / i-1 overlaps the kernels of minibatch i.  Uploads are
+ * ordered among themselves, downloads among themselves; an upload and a download are ordered only
+ * through events (dsc_event_record_copy / dsc_event_record_copy_down + dsc_compute_wait_event).
+ * dsc_copy_wait_compute: copies queued after this call start only when the compute work queued so far
+ * has finished; dsc_compute_wait_copy: the converse; dsc_copy_sync: the host waits for both streams. */
 DSC_API int dsc_copy_upload(dsc_buf_t h, int32_t off, const void* pinned_host, int32_t n);
 DSC_API int dsc_copy_download(dsc_buf_t h, int32_t off, void* pinned_host, int32_t n);
 DSC_API int dsc_copy_wait_compute(dsc_ctx_t ctx);

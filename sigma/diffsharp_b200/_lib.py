@@ -116,6 +116,7 @@ _sig("dsc_event_record", ctx_t, C.c_uint64)
 _sig("dsc_event_elapsed_ms", ctx_t, C.c_uint64, C.c_uint64, P(C.c_float))
 _sig("dsc_event_destroy", ctx_t, C.c_uint64)
 _sig("dsc_event_record_copy", ctx_t, C.c_uint64)
+_sig("dsc_event_record_copy_down", ctx_t, C.c_uint64)
 _sig("dsc_event_sync", ctx_t, C.c_uint64)
 _sig("dsc_compute_wait_event", ctx_t, C.c_uint64)
 _sig("dsc_graph_begin", ctx_t)

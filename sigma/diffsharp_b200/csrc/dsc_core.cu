@@ -306,8 +306,10 @@ int dsc_create(int device, uint32_t flags, dsc_ctx_t* out) {
     DSC_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     DSC_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
     DSC_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    DSC_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream_down, cudaStreamNonBlocking));
     DSC_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_copy_a, cudaEventDisableTiming));
     DSC_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_copy_b, cudaEventDisableTiming));
+    DSC_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_copy_c, cudaEventDisableTiming));
     DSC_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming));
     DSC_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
     DSC_CUDA_CHECK(cudaMallocHost(&ctx->red_host, 256));
@@ -328,9 +330,12 @@ int dsc_destroy(dsc_ctx_t c) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->comm_stream);
     cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamSynchronize(ctx->copy_stream_down);
     cudaEventDestroy(ctx->ev_copy_a);
     cudaEventDestroy(ctx->ev_copy_b);
+    cudaEventDestroy(ctx->ev_copy_c);
     cudaStreamDestroy(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream_down);
     if (ctx->nccl_comm) dsc_comm_destroy(c);
     for (auto& kv : ctx->pool.free_blocks) cudaFree(kv.second);
     ctx->pool.free_blocks.clear();
@@ -419,6 +424,11 @@ int dsc_event_destroy(dsc_ctx_t c, dsc_event_t ev) {
 int dsc_event_record_copy(dsc_ctx_t c, dsc_event_t ev) {
     if (!ctx_ok(c) || !ev) return fail(DSC_E_INVALID, "bad context or event");
     DSC_CUDA_CHECK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev), as_ctx(c)->copy_stream));
+    return DSC_OK;
+}
+int dsc_event_record_copy_down(dsc_ctx_t c, dsc_event_t ev) {
+    if (!ctx_ok(c) || !ev) return fail(DSC_E_INVALID, "bad context or event");
+    DSC_CUDA_CHECK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev), as_ctx(c)->copy_stream_down));
     return DSC_OK;
 }
 int dsc_event_sync(dsc_ctx_t c, dsc_event_t ev) {
@@ -661,7 +671,7 @@ int dsc_copy_download(dsc_buf_t h, int32_t off, void* host, int32_t n) {
     if (ctx->capturing) return fail(DSC_E_INVALID, "copy-stream transfers cannot be captured");
     size_t es = dtype_size(b->dtype);
     const char* src = reinterpret_cast<const char*>(b->block->ptr) + (b->off + off) * es;
-    DSC_CUDA_CHECK(cudaMemcpyAsync(host, src, (size_t)n * es, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    DSC_CUDA_CHECK(cudaMemcpyAsync(host, src, (size_t)n * es, cudaMemcpyDeviceToHost, ctx->copy_stream_down));
     ctx->stats.memcpy_d2h_bytes += (size_t)n * es;
     return DSC_OK;
 }
@@ -672,6 +682,7 @@ int dsc_copy_wait_compute(dsc_ctx_t c) {
     DSC_TRY(dsc_comm_join(c));
     DSC_CUDA_CHECK(cudaEventRecord(ctx->ev_copy_a, ctx->stream));
     DSC_CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy_a, 0));
+    DSC_CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream_down, ctx->ev_copy_a, 0));
     return DSC_OK;
 }
 
@@ -680,12 +691,15 @@ int dsc_compute_wait_copy(dsc_ctx_t c) {
     Ctx* ctx = as_ctx(c);
     DSC_CUDA_CHECK(cudaEventRecord(ctx->ev_copy_b, ctx->copy_stream));
     DSC_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_b, 0));
+    DSC_CUDA_CHECK(cudaEventRecord(ctx->ev_copy_c, ctx->copy_stream_down));
+    DSC_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_c, 0));
     return DSC_OK;
 }
 
 int dsc_copy_sync(dsc_ctx_t c) {
     if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
     DSC_CUDA_CHECK(cudaStreamSynchronize(as_ctx(c)->copy_stream));
+    DSC_CUDA_CHECK(cudaStreamSynchronize(as_ctx(c)->copy_stream_down));
     return DSC_OK;
 }
 

@@ -67,8 +67,9 @@ struct Ctx {
     uint32_t flags = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t comm_stream = nullptr;
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_copy_a = nullptr, ev_copy_b = nullptr;
+    cudaStream_t copy_stream = nullptr;       // host -> device transfers of the copy-stream API
+    cudaStream_t copy_stream_down = nullptr;  // device -> host transfers: PCIe is full duplex, the two directions overlap
+    cudaEvent_t ev_copy_a = nullptr, ev_copy_b = nullptr, ev_copy_c = nullptr;
     cudaEvent_t ev_compute = nullptr, ev_comm = nullptr;
     bool comm_pending = false;
     Pool pool;
