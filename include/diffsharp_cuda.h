@@ -151,6 +151,11 @@ DSC_API int dsc_flush_l2(dsc_ctx_t ctx);
  * tile when the tiles do not fill the GPU, fuse = in-kernel operand split (0 off, 1 single-CTA
  * kernels, 2 also the 2-CTA 256 x 256 kernel).  -1 = planner decides. */
 DSC_API int dsc_gemm_tune(dsc_ctx_t ctx, int bn, int pair, int split, int fuse);
+/* With DSC_GEMM_STAMPS=1 in the environment: %globaltimer (ns) as CTA 0 of the last float32 tensor-core GEMM
+ * saw it at kernel entry, after the prologue (barriers, TMEM), when the first operand tiles had landed, when
+ * the last MMA was issued, when the last accumulator chunk was drained, and when the epilogue was done;
+ * [6], [7] (aligned split-K only): segment parked, all segments of the tile parked. */
+DSC_API int dsc_gemm_debug_stamps(dsc_ctx_t ctx, uint64_t out[8]);
 
 /* ---------------------------------------------------------------- buffers ------------------ */
 /* CreateDataBuffer / CreateZeroArray / CreateValueArray / CreateUninitialisedArray

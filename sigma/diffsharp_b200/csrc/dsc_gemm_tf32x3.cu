@@ -282,7 +282,15 @@ struct Params {
     int vec4;                  // output rows are 16-byte aligned and n % 4 == 0
     int a_mn, b_mn;            // operand tiles are MN-major (source read in place, K index strided)
     int a_fused, b_fused;      // the operand's lo tile is computed in shared memory by the converter warps (no lo plane in HBM)
+    unsigned long long* stamps; // null, or 8 slots for %globaltimer at the phase boundaries as CTA 0 sees them (dsc_gemm_debug_stamps)
 };
+__device__ __forceinline__ void stamp(const Params& p, int slot) {
+    if (p.stamps != nullptr && blockIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.stamps[slot] = t;
+    }
+}
 
 __device__ __forceinline__ int unit_begin(const Params& p, int b) { return b * p.base + min(b, p.rem); }
 __device__ __forceinline__ int unit_owner(const Params& p, int u) {
@@ -372,6 +380,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
     };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) stamp(p, 0);   // kernel entry
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kS; ++s) {
@@ -403,6 +412,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
     if constexpr (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
+    if (threadIdx.x == 0) stamp(p, 1);   // barriers initialised, TMEM allocated
 
     const int lb = p.perm_tiles ? (bid % p.perm_tiles) * p.perm_s + bid / p.perm_tiles : bid;
     const int sk_begin = unit_begin(p, lb), sk_end = unit_begin(p, lb + 1);
@@ -529,6 +539,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                         if (kConv > 0) mbar_wait(conv_bar(l), lph);  // ... and the converter warps have written the lo tiles
                     }
                     tcgen05_fence_after();
+                    if (i == 0 && kb == c0) stamp(p, 2);   // first operand tiles have landed
                     const uint32_t a_hi = smem_base + a_hi_off(s), a_lo = smem_base + a_lo_off(s, l);
                     const uint32_t b_hi = smem_base + b_hi_off(s), b_lo = smem_base + b_lo_off(s, l);
                     const uint64_t ahi = p.a_mn ? make_mnmajor_sw128_desc(a_hi) : make_kmajor_sw128_desc(a_hi);
@@ -550,6 +561,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                 commit(tfull_bar(as));                 // chunk accumulator complete
                 if (++as == 2) { as = 0; aph ^= 1u; }
             }
+            stamp(p, 3);                               // last MMA issued
         }
     } else if (kConv > 0 && (warp < kEpi0 || warp >= kEpi0 + kEpiWarps)) {
         // converter warps (in the WIDE layout: warps 2-3 of warpgroup 0 and the whole of warpgroup 3)
@@ -571,6 +583,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
         int as = 0;
         uint32_t aph = 0;
         int i = 0;
+        const bool stamper = threadIdx.x == 32 * kEpi0;
         while (i < my_units) {
             int tile, ch0;
             unit_at(p, i, dp_units, sk_begin, nb, bid, tile, ch0);
@@ -600,6 +613,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                 }
                 if (++as == 2) { as = 0; aph ^= 1u; }
             }
+            if (stamper && i == my_units) stamp(p, 4);   // last accumulator chunk drained
             if (seg_len == p.cpt) {
                 // the segment is the whole tile: add the bias and store
                 const int row = m0 + trow;
@@ -623,7 +637,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                 // partial segment: park it in this CTA's slot (0 = the segment that starts the CTA's range)
                 const int sk_tile = tile - p.dp_tiles;
                 const int which = (sk_tile == sk_begin / p.cpt) ? 0 : 1;
-                {
+                if (p.perm_s > 1) {
+                    // aligned split-K: plane-major slot, float4 index = (c / 4) * 256 + epilogue thread — every store
+                    // instruction of a warp writes 512 contiguous bytes (the row-major slot below writes 16 bytes to
+                    // each of 32 rows: parking 64 KB took 3.4 us that way)
+                    float4* slot = reinterpret_cast<float4*>(p.slots + (((size_t)lb * 2 + which) * (PAIR ? 2 : 1) + cta_rank) * (BM * BN)) + (threadIdx.x - 32 * kEpi0);
+#pragma unroll
+                    for (int c = 0; c < HALF; c += 4) slot[(c / 4) * 256] = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+                } else {
                     float* slot = p.slots + (((size_t)lb * 2 + which) * (PAIR ? 2 : 1) + cta_rank) * (BM * BN) + (size_t)trow * BN + half * HALF;
 #pragma unroll
                     for (int c = 0; c < HALF; c += 4) *reinterpret_cast<float4*>(slot + c) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
@@ -632,6 +653,74 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                 epi_bar();
                 const int b_first = unit_owner(p, sk_tile * p.cpt), b_last = unit_owner(p, (sk_tile + 1) * p.cpt - 1);
                 unsigned int* ticket = p.tickets + (PAIR ? 2 * tile + (int)cta_rank : tile);   // the two halves of a pair's tile are finished independently
+                if (p.perm_s > 1) {
+                    // Aligned split-K: every worker of the tile holds exactly ONE segment and all of them
+                    // finish together (one CTA per SM, grid <= SMs: co-resident), so instead of leaving
+                    // the whole tile to the last arriver (a serial tail of nseg + 1 tile-sized passes on
+                    // one SM: measured 6.8 us for 4 x 128 x 256, 15.9 us when the slots miss L2) the CTAs wait for
+                    // each other and each adds 1/nseg of the rows: segments in K order (deterministic).
+                    const unsigned nseg = (unsigned)(b_last - b_first + 1);
+                    if (threadIdx.x == 32 * kEpi0) {
+                        stamp(p, 6);   // segment parked
+                        atomicAdd(ticket, 1u);
+                        unsigned int seen;
+                        do {
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ticket) : "memory");
+                        } while (seen < nseg);
+                        stamp(p, 7);   // all segments of the tile parked
+                    }
+                    epi_bar();
+                    __threadfence();
+                    const int t = threadIdx.x - 32 * kEpi0;
+                    constexpr int NC4 = HALF / 4;                                  // float4 planes of a slot
+                    const int mine = lb - b_first;                                 // this worker's position among the tile's segments
+                    const int c4_0 = (int)((unsigned)mine * NC4 / nseg), c4_1 = (int)((unsigned)(mine + 1) * NC4 / nseg);
+                    const float4* seg0 = reinterpret_cast<const float4*>(p.slots + (((size_t)b_first * 2) * (PAIR ? 2 : 1) + cta_rank) * (BM * BN)) + t;
+                    const size_t seg_stride = (size_t)2 * (PAIR ? 2 : 1) * (BM * BN) / 4;   // float4 between the slots of consecutive workers
+                    // thread t reduces what thread t of every segment parked: its own row, columns half * HALF + 4 c4 ...
+                    const int row = m0 + trow;
+                    const float bv = (p.bias != nullptr && row < p.m) ? p.bias[row] : 0.f;
+                    float* crow = p.C + (size_t)row * p.n + n0 + half * HALF;
+                    for (int c4 = c4_0; c4 < c4_1; c4 += 8) {
+                        float4 sum[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) sum[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (unsigned j0 = 0; j0 < nseg; j0 += 2) {     // 2 segments x 8 planes in flight
+                            float4 v[2][8];
+#pragma unroll
+                            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                                for (int q = 0; q < 8; ++q)
+                                    v[jj][q] = (j0 + jj < nseg && c4 + q < c4_1) ? __ldcg(seg0 + (j0 + jj) * seg_stride + (size_t)(c4 + q) * 256)
+                                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) {
+                                    if (j0 + jj < nseg) { sum[q].x += v[jj][q].x; sum[q].y += v[jj][q].y; sum[q].z += v[jj][q].z; sum[q].w += v[jj][q].w; }
+                                }
+                        }
+                        if (row < p.m) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                if (c4 + q >= c4_1) continue;
+                                const int cc = n0 + half * HALF + (c4 + q) * 4;
+                                float* dst = crow + (c4 + q) * 4;
+                                if (p.vec4 && cc + 4 <= p.n) {
+                                    *reinterpret_cast<float4*>(dst) = make_float4(sum[q].x + bv, sum[q].y + bv, sum[q].z + bv, sum[q].w + bv);
+                                } else {
+                                    if (cc < p.n) dst[0] = sum[q].x + bv;
+                                    if (cc + 1 < p.n) dst[1] = sum[q].y + bv;
+                                    if (cc + 2 < p.n) dst[2] = sum[q].z + bv;
+                                    if (cc + 3 < p.n) dst[3] = sum[q].w + bv;
+                                }
+                            }
+                        }
+                    }
+                    epi_bar();   // every thread has read the segments
+                    if (threadIdx.x == 32 * kEpi0 && atomicAdd(ticket, 1u) == 2u * nseg - 1u) *ticket = 0;   // the last reader re-arms the counter
+                    continue;
+                }
                 if (threadIdx.x == 32 * kEpi0) *s_flag = (atomicAdd(ticket, 1u) == (unsigned)(b_last - b_first));
                 epi_bar();
                 const bool last = (*s_flag != 0);
@@ -695,6 +784,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
         }
     }
 
+    if (threadIdx.x == 32 * kEpi0) stamp(p, 5);          // epilogue done (stores, fix-up)
     tcgen05_fence_before();
     __syncthreads();
     if constexpr (PAIR) cluster_sync_all();   // neither CTA may leave (or free TMEM) while the pair's MMAs / barrier arrivals are in flight
@@ -1060,6 +1150,12 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
     p.b_mn = pb.mn_major ? 1 : 0;
     p.a_fused = a_fused ? 1 : 0;
     p.b_fused = b_fused ? 1 : 0;
+    static const bool want_stamps = [] { const char* e = getenv("DSC_GEMM_STAMPS"); return e && *e == '1'; }();
+    if (want_stamps && !ctx->gemm_stamps && !ctx->capturing) {
+        DSC_CUDA_CHECK(cudaMalloc(&ctx->gemm_stamps, 8 * sizeof(unsigned long long)));
+        DSC_CUDA_CHECK(cudaMemset(ctx->gemm_stamps, 0, 8 * sizeof(unsigned long long)));
+    }
+    p.stamps = ctx->gemm_stamps;
     if (a_fused) a_lo = const_cast<float*>(A);   // the lo maps are never dereferenced for a fused operand: point them at valid memory
     if (b_fused) b_lo = const_cast<float*>(B);
     CUtensorMap maps[4];
@@ -1096,6 +1192,16 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
 }
 
 }  // namespace dsc
+
+extern "C" int dsc_gemm_debug_stamps(dsc_ctx_t c, uint64_t out[8]) {
+    using namespace dsc;
+    if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
+    Ctx* ctx = as_ctx(c);
+    if (!ctx->gemm_stamps) return fail(DSC_E_INVALID, "no GEMM time stamps: set DSC_GEMM_STAMPS=1 before the first product");
+    DSC_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    DSC_CUDA_CHECK(cudaMemcpy(out, ctx->gemm_stamps, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return DSC_OK;
+}
 
 extern "C" int dsc_gemm_tune(dsc_ctx_t c, int bn, int pair, int split, int fuse) {
     using namespace dsc;

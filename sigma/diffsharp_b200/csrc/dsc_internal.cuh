@@ -93,6 +93,7 @@ struct Ctx {
     void* gemm_ws = nullptr;
     size_t gemm_ws_bytes = 0;
     int gemm_force_bn = -1, gemm_force_pair = -1, gemm_force_split = -1, gemm_force_fuse = -1;   // dsc_gemm_tune; -1 = planner decides
+    unsigned long long* gemm_stamps = nullptr;   // %globaltimer at the phase boundaries of the last tensor-core GEMM (DSC_GEMM_STAMPS=1)
     unsigned int* gemm_tickets = nullptr;   // one arrival counter per output tile (stream-K fix-up), zero between launches
     size_t gemm_tickets_n = 0;
     // NCCL
