@@ -95,7 +95,9 @@ struct Cfg {
     static constexpr int kSmemBytes = kTileBytes + 1024 /*align*/ + 256 /*barriers, TMEM base, epilogue flag*/;
     // Converter warps (in-kernel operand split).  Single-CTA 128 x 256 tiles leave room for two smem
     // stages only and need 168 registers per epilogue thread: that shape keeps the pre-pass, and so do
-    // the narrower pair tiles; single-CTA 128 x 128 / 128 x 64 tiles convert inside their stages.
+    // the narrower pair tiles (measured: with converter warps and the extra TMA -> converter -> MMA hop
+    // the 256 x 128 pair kernel loses 2-3 us on a 1024^3 product even when nothing is converted);
+    // single-CTA 128 x 128 / 128 x 64 tiles convert inside their stages.
     static constexpr int kConvWarps = WIDE ? 6 : ((PAIR || BN >= 256) ? 0 : 4);
     static constexpr int kEpi0 = WIDE ? 4 : 2;   // first epilogue warp
     static constexpr int kThreads = WIDE ? 512 : kBaseThreads + 32 * kConvWarps;
@@ -381,6 +383,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) stamp(p, 0);   // kernel entry
+    if (threadIdx.x == 32) {             // descriptor fetches overlap the barrier / TMEM prologue
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ahi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_bhi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_alo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_blo) : "memory");
+    }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kS; ++s) {

@@ -76,9 +76,9 @@ def main():
     for R in rows_list:
         print(f"===== rows = {R} =====")
         big = [(-1, -1, -1, -1), (256, 1, -1, 0), (256, 1, -1, 1), (128, 1, -1, 0), (256, 0, -1, 0), (128, 0, -1, 0), (128, 0, -1, 1), (64, 0, -1, 1), (64, 1, -1, 0)]
-        deep = [(-1, -1, -1, -1)] + [(256, 1, s, 0) for s in (1, 2, 4)] + [(256, 1, s, 1) for s in (2, 4)] + [(128, 1, s, 0) for s in (1, 2, 4)] + [(256, 0, s, 0) for s in (4, 8)] + \
-               [(128, 0, s, 1) for s in (2, 4)] + [(64, 1, s, 0) for s in (1, 2)]
-        small = R <= 2048
+        deep = [(-1, -1, -1, -1)] + [(256, 1, s, 0) for s in (1, 2, 4)] + [(128, 1, s, 0) for s in (1, 2)] + \
+               [(128, 0, s, 1) for s in (1, 2)] + [(128, 0, 2, 0)] + [(256, 0, s, 0) for s in (1, 2, 4)]
+        small = R <= 4096
         sweep("fwd1  X*W1", R, 1024, 784, 0, 0, deep if small else big)
         sweep("fwd2  H*W2", R, 1024, 1024, 0, 0, deep if small else big)
         sweep("dH1   dZ*W2^T", R, 1024, 1024, 0, 1, deep if small else big)
