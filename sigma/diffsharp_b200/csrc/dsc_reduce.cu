@@ -59,25 +59,29 @@ __device__ __forceinline__ T block_tree(T v, T* smem) {
 // Each CTA owns a CONTIGUOUS chunk of `iters` x kRUnroll x kRThreads vectors (same finding as the
 // elementwise kernels: contiguous chunks stream faster than a grid-wide stride).
 template <int KIND, typename T, bool VEC>
-__global__ void __launch_bounds__(kRThreads) reduce_kernel(const T* __restrict__ a, const T* __restrict__ b, size_t n, int iters,
+__global__ void __launch_bounds__(kRThreads) reduce_kernel(const T* __restrict__ a, const T* __restrict__ b, size_t n, unsigned int per_cta_items,
                                                             unsigned int* tickets, T* partials, T* result) {
     __shared__ T smem[kRThreads / 32];
     T acc[kRUnroll];
 #pragma unroll
     for (int u = 0; u < kRUnroll; ++u) acc[u] = T(0);
-    const size_t per_cta = (size_t)iters * kRUnroll * kRThreads;
-    const size_t base = (size_t)blockIdx.x * per_cta + threadIdx.x;
+    // per_cta_items: vectors (VEC) or elements owned by one CTA, a multiple of kRThreads chosen by the host so
+    // that a large input is cut into a whole number of CTAs per SM (a function of n only: deterministic)
+    const unsigned int iters = (per_cta_items + kRUnroll * kRThreads - 1) / (kRUnroll * kRThreads);
+    const size_t cta_begin = (size_t)blockIdx.x * per_cta_items, cta_end = cta_begin + per_cta_items;
+    const size_t base = cta_begin + threadIdx.x;
     if constexpr (VEC) {
         using V = typename RVec<T>::type;
         constexpr int W = RVec<T>::N;
         const size_t nvec = n / W;
-        for (int it = 0; it < iters; ++it) {
+        const size_t end = cta_end < nvec ? cta_end : nvec;
+        for (unsigned int it = 0; it < iters; ++it) {
             V va[kRUnroll], vb[kRUnroll];
             bool ok[kRUnroll];
 #pragma unroll
             for (int u = 0; u < kRUnroll; ++u) {
                 const size_t i = base + (size_t)(it * kRUnroll + u) * kRThreads;
-                ok[u] = i < nvec;
+                ok[u] = i < end;
                 if (ok[u]) {
                     va[u] = *reinterpret_cast<const V*>(a + i * W);
                     if constexpr (KIND == R_DOT) vb[u] = *reinterpret_cast<const V*>(b + i * W);
@@ -96,11 +100,12 @@ __global__ void __launch_bounds__(kRThreads) reduce_kernel(const T* __restrict__
             if (j < n) acc[1] = r_comb<KIND>(acc[1], r_load<KIND>(a[j], KIND == R_DOT ? b[j] : a[j]));
         }
     } else {
-        for (int it = 0; it < iters; ++it) {
+        const size_t end = cta_end < n ? cta_end : n;
+        for (unsigned int it = 0; it < iters; ++it) {
 #pragma unroll
             for (int u = 0; u < kRUnroll; ++u) {
                 const size_t j = base + (size_t)(it * kRUnroll + u) * kRThreads;
-                if (j < n) acc[u] = r_comb<KIND>(acc[u], r_load<KIND>(a[j], KIND == R_DOT ? b[j] : a[j]));
+                if (j < end) acc[u] = r_comb<KIND>(acc[u], r_load<KIND>(a[j], KIND == R_DOT ? b[j] : a[j]));
             }
         }
     }
@@ -246,14 +251,19 @@ static int launch_reduce(Ctx* ctx, const T* a, const T* b, size_t n, T* result) 
     size_t items = vec ? n / RVec<T>::N : n;
     if (items == 0) items = 1;
     // grid and per-CTA chunk are functions of n only (determinism)
+    // Small inputs: one CTA per 2048 items (8 per thread).  Large inputs: kMaxPartials = 4 CTAs per SM, the
+    // items cut evenly between them (rounded up to the block size), so every SM streams the same share.
     const size_t per_iter = (size_t)kRThreads * kRUnroll;
-    size_t blocks1 = (items + per_iter - 1) / per_iter;
     static const int max_partials = [] { const char* e = getenv("DSC_RED_MAXP"); int v = e ? atoi(e) : 0; return (v >= 1 && v <= kMaxPartials) ? v : kMaxPartials; }();
-    int iters = (int)((blocks1 + max_partials - 1) / max_partials);
-    if (iters < 1) iters = 1;
-    int grid = (int)((items + per_iter * iters - 1) / (per_iter * iters));
-    if (vec) reduce_kernel<KIND, T, true><<<grid, kRThreads, 0, ctx->stream>>>(a, b, n, iters, ticket, partials, result);
-    else reduce_kernel<KIND, T, false><<<grid, kRThreads, 0, ctx->stream>>>(a, b, n, iters, ticket, partials, result);
+    size_t per_cta = per_iter;
+    if ((items + per_iter - 1) / per_iter > (size_t)max_partials) {
+        per_cta = (items + max_partials - 1) / max_partials;
+        per_cta = (per_cta + kRThreads - 1) / kRThreads * kRThreads;
+    }
+    if (per_cta > 0xffffff00u) return fail(DSC_E_SHAPE, "reduction: input too large");
+    const int grid = (int)((items + per_cta - 1) / per_cta);
+    if (vec) reduce_kernel<KIND, T, true><<<grid, kRThreads, 0, ctx->stream>>>(a, b, n, (unsigned int)per_cta, ticket, partials, result);
+    else reduce_kernel<KIND, T, false><<<grid, kRThreads, 0, ctx->stream>>>(a, b, n, (unsigned int)per_cta, ticket, partials, result);
     DSC_LAUNCH_CHECK(ctx);
     return DSC_OK;
 }
