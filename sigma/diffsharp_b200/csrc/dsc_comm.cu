@@ -249,7 +249,9 @@ __global__ void __launch_bounds__(kP2PThreads) allreduce_p2p_kernel(P2PTable<T> 
     unsigned long long* stamps = reinterpret_cast<unsigned long long*>(local + 512);   // phase boundaries as CTA 0 sees them (dsc_comm_debug_stamps)
     const bool stamp = blockIdx.x == 0 && threadIdx.x == 0;
     if (stamp) stamps[0] = globaltimer_ns();
-    // 0. scatter this rank's contribution: slice q -> rank q, region A, slot [rank]
+    // 0. scatter this rank's contribution: slice q -> rank q, region A, slot [rank].
+    // Every rank walks the packed space starting at a different slice (rank r begins with slice r + 1), so that
+    // at any moment the N ranks write into N different destinations instead of all into the same one.
     for (int s = 0; s < t.count; ++s) {
         const T* p = t.ptr[s];
         const long long v_seg = t.start[s] / W;   // first vector of the segment in the packed space
@@ -258,8 +260,13 @@ __global__ void __launch_bounds__(kP2PThreads) allreduce_p2p_kernel(P2PTable<T> 
         if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
             const long long nv = n / W;
             const V* pv = reinterpret_cast<const V*>(p);
+            // rotation of the segment's vector index: position j -> vector (j + rot) mod nv, rot = the offset inside the
+            // segment of the first vector that belongs to slice rank + 1 (clamped to the segment)
+            long long rot = (long long)((a.rank + 1) % a.nranks) * per - v_seg;
+            rot = rot < 0 ? 0 : (rot >= nv ? 0 : rot);
 #pragma unroll 4
-            for (long long i = gtid; i < nv; i += gsize) {
+            for (long long j = gtid; j < nv; j += gsize) {
+                const long long i = j + rot < nv ? j + rot : j + rot - nv;
                 const V x = pv[i];
                 const long long v = v_seg + i;
                 const int q = (int)(v / per);
@@ -295,9 +302,14 @@ __global__ void __launch_bounds__(kP2PThreads) allreduce_p2p_kernel(P2PTable<T> 
                     acc.x += x[r].x; acc.y += x[r].y;
                     if constexpr (W == 4) { acc.z += x[r].z; acc.w += x[r].w; }
                 }
+            // destinations in rotated order (rank + 1, rank + 2, ...): no two ranks target the same peer at the same step
 #pragma unroll
-            for (int q = 0; q < kP2PMaxRanks; ++q)
-                if (q < a.nranks) reinterpret_cast<V*>(a.peer[q] + kP2PHeaderBytes + a.region_bytes)[v0 + i] = acc;
+            for (int j = 0; j < kP2PMaxRanks; ++j)
+                if (j < a.nranks) {
+                    int q = a.rank + 1 + j;
+                    q = q >= a.nranks ? q - a.nranks : q;
+                    reinterpret_cast<V*>(a.peer[q] + kP2PHeaderBytes + a.region_bytes)[v0 + i] = acc;
+                }
         }
     }
     if (stamp) stamps[3] = globaltimer_ns();

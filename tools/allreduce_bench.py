@@ -21,6 +21,21 @@ sizes = (784 * 1024, 1024 * 1024, 1024 * 10, 1024, 1024, 10)
 rng = np.random.default_rng(rank)
 host = [rng.standard_normal(n).astype(np.float32) for n in sizes]
 bufs = [CudaDataBuffer.from_host(ctx, h) for h in host]
+# correctness first: the sum over ranks, added in rank order in float32, bit for bit
+comm.allreduce_sum(bufs)
+comm.join()
+ctx.sync()
+for n, b in zip(sizes, bufs):
+    want = None
+    for r in range(world):
+        rr = np.random.default_rng(r)
+        parts = [rr.standard_normal(m).astype(np.float32) for m in sizes]
+        x = parts[sizes.index(n)] if sizes.count(n) == 1 else parts[[i for i, m in enumerate(sizes) if m == n][[bb is b for bb in bufs if bb.Length == n].index(True)]]
+        want = x.copy() if want is None else (want + x).astype(np.float32)
+    got = b.SubData
+    assert np.array_equal(got, want), (rank, n, float(np.abs(got - want).max()))
+if rank == 0:
+    print(f"world {world}: all-reduce result equals the rank-ordered float32 sum, bit for bit", flush=True)
 for _ in range(3):
     comm.allreduce_sum(bufs)
     comm.join()
