@@ -670,7 +670,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                     const unsigned nseg = (unsigned)(b_last - b_first + 1);
                     if (threadIdx.x == 32 * kEpi0) {
                         stamp(p, 6);   // segment parked
-                        atomicAdd(ticket, 1u);
+                        // the counter runs 0 .. 2 nseg - 1 and wraps to 0 by itself (atomicInc): nseg arrivals, then nseg
+                        // departures; neither needs its return value, so nothing waits for the round trip
+                        atomicInc(ticket, 2u * nseg - 1u);
                         unsigned int seen;
                         do {
                             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ticket) : "memory");
@@ -726,7 +728,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                         }
                     }
                     epi_bar();   // every thread has read the segments
-                    if (threadIdx.x == 32 * kEpi0 && atomicAdd(ticket, 1u) == 2u * nseg - 1u) *ticket = 0;   // the last reader re-arms the counter
+                    if (threadIdx.x == 32 * kEpi0) atomicInc(ticket, 2u * nseg - 1u);   // the last departure wraps the counter to 0
                     continue;
                 }
                 if (threadIdx.x == 32 * kEpi0) *s_flag = (atomicAdd(ticket, 1u) == (unsigned)(b_last - b_first));
