@@ -50,6 +50,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "dsc_internal.cuh"
 
 namespace dsc {
@@ -141,8 +143,8 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
                  "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
                  : "memory");
 }
-__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar, uint16_t mask) {   // arrives on `bar` in BOTH CTAs of the pair (mask = their cluster ranks)
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                  : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope: the arrivals come from both CTAs
@@ -159,22 +161,32 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
             : "memory");
     } while (!done);
 }
-__device__ __forceinline__ void mbar_arrive_leader_release(uint32_t bar) {   // release at cluster scope on cluster CTA 0's barrier
+__device__ __forceinline__ void mbar_arrive_leader_release(uint32_t bar, uint32_t leader) {   // release at cluster scope on the barrier of cluster CTA `leader`
     asm volatile(
         "{\n\t"
         ".reg .b32 rem;\n\t"
-        "mapa.shared::cluster.u32 rem, %0, 0;\n\t"
+        "mapa.shared::cluster.u32 rem, %0, %1;\n\t"
         "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [rem];\n\t"
-        "}" ::"r"(bar)
+        "}" ::"r"(bar), "r"(leader)
         : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {    // arrive on the barrier at the same offset in cluster CTA 0
+// 16 bytes into the shared memory of cluster CTA `rank`, at the offset `addr` has in this CTA (distributed shared memory)
+__device__ __forceinline__ void st_dsmem_f4(uint32_t addr, uint32_t rank, float4 v) {
     asm volatile(
         "{\n\t"
         ".reg .b32 rem;\n\t"
-        "mapa.shared::cluster.u32 rem, %0, 0;\n\t"
+        "mapa.shared::cluster.u32 rem, %0, %1;\n\t"
+        "st.shared::cluster.v4.f32 [rem], {%2, %3, %4, %5};\n\t"
+        "}" ::"r"(addr), "r"(rank), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar, uint32_t leader) {    // arrive on the barrier at the same offset in cluster CTA `leader`
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 rem;\n\t"
+        "mapa.shared::cluster.u32 rem, %0, %1;\n\t"
         "mbarrier.arrive.shared::cluster.b64 _, [rem];\n\t"
-        "}" ::"r"(bar)
+        "}" ::"r"(bar), "r"(leader)
         : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -284,6 +296,8 @@ struct Params {
     int vec4;                  // output rows are 16-byte aligned and n % 4 == 0
     int a_mn, b_mn;            // operand tiles are MN-major (source read in place, K index strided)
     int a_fused, b_fused;      // the operand's lo tile is computed in shared memory by the converter warps (no lo plane in HBM)
+    int kcluster;              // > 1: aligned split-K whose K ranges of a tile are the CTAs (pairs) of ONE cluster; the partial
+                               // tiles are exchanged through distributed shared memory instead of workspace slots
     unsigned long long* stamps; // null, or 8 slots for %globaltimer at the phase boundaries as CTA 0 sees them (dsc_gemm_debug_stamps)
 };
 __device__ __forceinline__ void stamp(const Params& p, int slot) {
@@ -349,8 +363,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                    const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, const Params p) {
     using cfg = Cfg<BN, PAIR, WIDE>;
     constexpr int TM = PAIR ? 2 * BM : BM;          // rows of an output tile
-    uint32_t cta_rank = 0;                          // 0 = leader of the pair (issues the MMAs)
-    if constexpr (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    // cluster = [K ranges of one tile (kcluster, optional)] x [the two CTAs of a pair (PAIR)]
+    uint32_t crank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const uint32_t cta_rank = PAIR ? (crank & 1u) : 0u;   // 0 = leader of the pair (issues the MMAs)
+    const uint32_t pair_leader = crank & ~1u;             // cluster rank of this CTA's pair leader
+    const uint32_t kidx = PAIR ? (crank >> 1) : crank;    // which K range of the tile (kcluster mode)
     const int nb = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;    // workers (CTAs or CTA pairs)
     const int bid = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     extern __shared__ uint8_t smem_raw[];
@@ -417,7 +435,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
     }
     tcgen05_fence_before();
     __syncthreads();
-    if constexpr (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
+    if (PAIR || p.kcluster > 1) cluster_sync_all();   // the peers run and their barriers are initialised before anything arrives there
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
     if (threadIdx.x == 0) stamp(p, 1);   // barriers initialised, TMEM allocated
@@ -449,7 +467,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to tcgen05.mma
                 __syncwarp();
                 if (lane == 0) {
-                    if constexpr (PAIR) mbar_arrive_leader_release(conv_bar(l));
+                    if constexpr (PAIR) mbar_arrive_leader_release(conv_bar(l), pair_leader);
                     else mbar_arrive(conv_bar(l));
                 }
                 if (++s == kS) { s = 0; ph ^= 1u; }
@@ -523,7 +541,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                 else umma_tf32(d, a, b, idesc, acc);
             };
             auto commit = [&](uint32_t bar) {
-                if constexpr (PAIR) tcgen05_commit_pair(bar);
+                if constexpr (PAIR) tcgen05_commit_pair(bar, (uint16_t)(3u << pair_leader));
                 else tcgen05_commit(bar);
             };
             // per 8-wide k-slice the descriptor start address moves by 32 B inside the swizzle row
@@ -616,7 +634,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    if constexpr (PAIR) mbar_arrive_leader(tempty_bar(as));
+                    if constexpr (PAIR) mbar_arrive_leader(tempty_bar(as), pair_leader);
                     else mbar_arrive(tempty_bar(as));
                 }
                 if (++as == 2) { as = 0; aph ^= 1u; }
@@ -641,6 +659,65 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                         }
                     }
                 }
+            } else if (p.kcluster > 1) {
+                // ---- split-K inside a cluster: exchange the partial tile through distributed shared memory ----
+                // The K ranges of this tile are the CTAs (pairs) of this cluster.  Thread t of every CTA holds the same
+                // row and the same HALF columns; the columns are cut into kcluster parts and part j is finished by the
+                // CTA with K index j.  Every CTA stores its other parts straight into the finisher's shared memory
+                // (the operand stages are free once every CTA's MMAs have retired: first cluster barrier), the second
+                // cluster barrier publishes them, and the finisher adds the contributions in K order (deterministic,
+                // the same order as the workspace scheme) and stores its part of C from registers.
+                auto exchange = [&](auto nseg_c) {
+                    constexpr int NSEG = decltype(nseg_c)::value;
+                    constexpr int NC4 = HALF / 4;
+                    constexpr int P4 = NC4 / NSEG > 0 ? NC4 / NSEG : 1;     // float4 per part and thread
+                    const int t = threadIdx.x - 32 * kEpi0;
+                    cluster_sync_all();                                    // every CTA of the cluster has drained its last accumulator chunk
+#pragma unroll
+                    for (int j = 0; j < NSEG; ++j) {
+                        if (j == (int)kidx) continue;
+                        const uint32_t target = PAIR ? (uint32_t)(2 * j) + cta_rank : (uint32_t)j;
+#pragma unroll
+                        for (int c = 0; c < P4; ++c) {
+                            const int a0 = (j * P4 + c) * 4;
+                            st_dsmem_f4(smem_base + 16u * (uint32_t)(((int)kidx * P4 + c) * 256 + t), target,
+                                        make_float4(acc[a0], acc[a0 + 1], acc[a0 + 2], acc[a0 + 3]));
+                        }
+                    }
+                    cluster_sync_all();                                    // all contributions have landed
+                    const int row = m0 + trow;
+                    const float bv = (p.bias != nullptr && row < p.m) ? p.bias[row] : 0.f;
+                    const float4* recv = reinterpret_cast<const float4*>(smem_gen) + t;
+#pragma unroll
+                    for (int j = 0; j < NSEG; ++j) {
+                        if (j != (int)kidx) continue;                       // j == kidx: the part this CTA finishes (compile-time register indices)
+#pragma unroll
+                        for (int c = 0; c < P4; ++c) {
+                            const int a0 = (j * P4 + c) * 4;
+                            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int src = 0; src < NSEG; ++src) {
+                                const float4 v = (src == j) ? make_float4(acc[a0], acc[a0 + 1], acc[a0 + 2], acc[a0 + 3]) : recv[(src * P4 + c) * 256];
+                                sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                            }
+                            if (row < p.m) {
+                                const int cc = n0 + half * HALF + a0;
+                                float* dst = p.C + (size_t)row * p.n + cc;
+                                if (p.vec4 && cc + 4 <= p.n) {
+                                    *reinterpret_cast<float4*>(dst) = make_float4(sum.x + bv, sum.y + bv, sum.z + bv, sum.w + bv);
+                                } else {
+                                    if (cc < p.n) dst[0] = sum.x + bv;
+                                    if (cc + 1 < p.n) dst[1] = sum.y + bv;
+                                    if (cc + 2 < p.n) dst[2] = sum.z + bv;
+                                    if (cc + 3 < p.n) dst[3] = sum.w + bv;
+                                }
+                            }
+                        }
+                    }
+                };
+                if (p.kcluster == 2) exchange(std::integral_constant<int, 2>());
+                else if (p.kcluster == 4) exchange(std::integral_constant<int, 4>());
+                else exchange(std::integral_constant<int, 8>());
             } else {
                 // partial segment: park it in this CTA's slot (0 = the segment that starts the CTA's range)
                 const int sk_tile = tile - p.dp_tiles;
@@ -795,6 +872,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
     }
 
     if (threadIdx.x == 32 * kEpi0) stamp(p, 5);          // epilogue done (stores, fix-up)
+    if (p.kcluster > 1 && !(warp >= kEpi0 && warp < kEpi0 + kEpiWarps)) {
+        cluster_sync_all();   // the two cluster barriers of the split-K exchange (the epilogue warps pass them inside the exchange)
+        cluster_sync_all();
+    }
     tcgen05_fence_before();
     __syncthreads();
     if constexpr (PAIR) cluster_sync_all();   // neither CTA may leave (or free TMEM) while the pair's MMAs / barrier arrivals are in flight
@@ -942,29 +1023,65 @@ static int make_map(CUtensorMap* map, const float* base, int inner, int outer, s
 }
 
 // `workers` = CTAs, or CTA pairs (clusters of 2: the two SMs of a TPC) when PAIR
-template <int BN, bool PAIR, bool WIDE = false>
-static int launch(Ctx* ctx, const CUtensorMap* maps, const Params& p, int workers) {
+template <int BN, bool PAIR, bool WIDE>
+static int set_smem_attr() {
     using cfg = Cfg<BN, PAIR, WIDE>;
     static bool attr_set = false;
     if (!attr_set) {
         DSC_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, PAIR, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::kSmemBytes));
         attr_set = true;
     }
+    return DSC_OK;
+}
+
+template <int BN, bool PAIR, bool WIDE = false>
+static int launch(Ctx* ctx, const CUtensorMap* maps, const Params& p, int workers) {
+    using cfg = Cfg<BN, PAIR, WIDE>;
+    DSC_TRY((set_smem_attr<BN, PAIR, WIDE>()));
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(PAIR ? 2 * workers : workers);
     lc.blockDim = dim3(cfg::kThreads);
     lc.dynamicSmemBytes = cfg::kSmemBytes;
     lc.stream = ctx->stream;
+    const int cluster = (PAIR ? 2 : 1) * (p.kcluster > 1 ? p.kcluster : 1);
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.x = cluster;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
     lc.attrs = at;
-    lc.numAttrs = PAIR ? 1 : 0;
+    lc.numAttrs = cluster > 1 ? 1 : 0;
     DSC_CUDA_CHECK(cudaLaunchKernelEx(&lc, gemm_tf32x3_kernel<BN, PAIR, WIDE>, maps[0], maps[1], maps[2], maps[3], p));
     DSC_LAUNCH_CHECK(ctx);
     return DSC_OK;
+}
+
+// How many clusters of `cluster` CTAs of this kernel can be resident at once (0 on error); cached per (kernel, size).
+template <int BN, bool PAIR, bool WIDE = false>
+static int max_active_clusters(int cluster) {
+    using cfg = Cfg<BN, PAIR, WIDE>;
+    static int cache[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
+    if (cluster < 1 || cluster > 8) return 0;
+    if (cache[cluster] >= 0) return cache[cluster];
+    if (set_smem_attr<BN, PAIR, WIDE>() != DSC_OK) return 0;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(cluster * 64);
+    lc.blockDim = dim3(cfg::kThreads);
+    lc.dynamicSmemBytes = cfg::kSmemBytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cluster;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tf32x3_kernel<BN, PAIR, WIDE>, &lc) != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    cache[cluster] = n;
+    return n;
 }
 
 // How one operand reaches the tensor core.
@@ -1128,6 +1245,25 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
     if (debug_plan)
         fprintf(stderr, "[dsc gemm] m=%d n=%d k=%d ta=%d tb=%d: BN=%d pair=%d grid=%d cpt=%d dp_waves=%d dp_extra=%d sk_units=%d perm_s=%d fused=%d%d\n", m, n, k, ta, tb, bn,
                 (int)pair, grid, cpt, dp_waves, dp_extra, sk_units_total, perm_s, (int)a_fused, (int)b_fused);
+    // Aligned split-K whose K ranges fit one cluster (<= 8 CTAs) and whose clusters are all resident at once:
+    // the partial tiles go through distributed shared memory (no workspace round trip, no tickets).
+    p.kcluster = 0;
+    {
+        static const int kc_env = [] { const char* e = getenv("DSC_GEMM_KCLUSTER"); return e ? atoi(e) : 1; }();
+        const int sp = perm_s;
+        const bool wide = pair && bn == 256 && a_fused && b_fused;
+        if (kc_env && !wide && (sp == 2 || sp == 4 || sp == 8) && (pair ? 2 : 1) * sp <= 8 && (bn / 8) % sp == 0) {
+            const int cl = (pair ? 2 : 1) * sp;
+            int fit = 0;
+            if (pair) fit = bn == 256 ? max_active_clusters<256, true>(cl) : (bn == 128 ? max_active_clusters<128, true>(cl) : max_active_clusters<64, true>(cl));
+            else fit = bn == 256 ? max_active_clusters<256, false>(cl) : (bn == 128 ? max_active_clusters<128, false>(cl) : max_active_clusters<64, false>(cl));
+            if (fit >= (int)tiles) {
+                p.kcluster = sp;
+                p.perm_tiles = 0;   // worker = tile * sp + K index: the K ranges of a tile are consecutive CTAs (one cluster)
+            }
+            if (debug_plan) fprintf(stderr, "[dsc gemm]   split-K through a cluster of %d: %d clusters fit, %ld tiles -> %s\n", cl, fit, tiles, p.kcluster ? "yes" : "no");
+        }
+    }
     DSC_TRY(ensure_gemm_tickets(ctx, (size_t)tiles * (pair ? 2 : 1)));
     p.tickets = ctx->gemm_tickets;
 
