@@ -403,12 +403,19 @@ def run_ours(args):
         loss_bufs, backend.capture_scalars = backend.capture_scalars, None
     sampler = ClockSampler(local)
     sampler.start()
+    # Warm-up: at least W replays and >= 0.6 s under load so that the clock sampler sees the load.  Every replay
+    # contains a collective, so the NUMBER of replays must be the same on every rank: it is derived from one
+    # timed batch whose duration is agreed over the ranks (max), never from a rank's own clock.
     t_warm = time.perf_counter()
-    n_warm = 0
-    while n_warm < max(args.warmup, 3) or time.perf_counter() - t_warm < 0.6:  # >= 0.6 s under load so the clock sampler sees it
+    for _ in range(16):
         ctx.graph_launch(graph)
-        n_warm += 1
-        if n_warm % 16 == 0:
+    ctx.sync()
+    t16 = D.max_over_ranks(time.perf_counter() - t_warm)
+    n_more = max(max(args.warmup, 3) - 16, int(0.6 / max(t16 / 16.0, 1e-5)) + 1)
+    n_more = min(n_more, 20000)
+    for i in range(n_more):
+        ctx.graph_launch(graph)
+        if i % 16 == 15:
             ctx.sync()
     ctx.sync()
     D.barrier(); ctx.sync()

@@ -151,7 +151,8 @@ __device__ __forceinline__ unsigned int ld_relaxed_sys(const unsigned int* p) {
 
 // All CTAs of this rank have finished the phase -> tell every peer (flag[rank] = value in the peer's
 // header) -> wait until every peer has told us.  `arrivals` is the cumulative CTA count expected at
-// the local counter.  A 60 s timeout turns a lost peer into an error word instead of a hung GPU.
+// the local counter.  A 20 s timeout turns a lost peer (or ranks that issued different numbers of all-reduces) into an error word instead of a hung GPU;
+// after the first failure the barriers of later calls return at once (dsc_comm_destroy reports the error).
 // Cost matters here (two barriers per all-reduce): ONE system fence per CTA on the way in, the flags of
 // all peers written in parallel by the lanes of one warp with relaxed stores (a release store per peer
 // is a system fence per peer: measured 78 us per all-reduce at 8 ranks against 37 us at 2), relaxed
@@ -175,11 +176,11 @@ __device__ __forceinline__ void p2p_barrier(const P2PArgs& a, unsigned int value
         }
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last && lane < (unsigned)a.nranks) st_relaxed_sys(reinterpret_cast<unsigned int*>(a.peer[lane]) + a.rank, value);
-        if (lane < (unsigned)a.nranks) {
+        if (lane < (unsigned)a.nranks && ld_relaxed_sys(sync + 2) == 0) {   // once a barrier has failed, later ones do not wait again
             const unsigned long long t0 = globaltimer_ns();
             unsigned int spins = 0;
             while ((int)(ld_relaxed_sys(flags + lane) - value) < 0) {
-                if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > 60000000000ull) {
+                if ((++spins & 1023u) == 0 && (globaltimer_ns() - t0 > 20000000000ull || ld_relaxed_sys(sync + 2) != 0)) {
                     sync[2] = 1;
                     break;
                 }
