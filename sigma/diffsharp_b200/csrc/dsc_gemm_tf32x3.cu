@@ -4,29 +4,35 @@
 //
 //   C(m x n) = op(A) op(B) [+ bias[i]]        Mul_M_M / Mul_M_M_Add_V_MCols (Backend.fs:119,121)
 //
-// Two launches per GEMM:
-//  (1) split pre-pass (HBM-bound, one launch for both operands).  kind::tf32 reads fp32 words from
-//      shared memory and IGNORES the low 13 mantissa bits, so the "hi" operand needs no plane of its
-//      own: the tensor core is pointed at the source buffer and sees hi = trunc_tf32(x).  The pre-pass
-//      only writes lo = rna_tf32(x - trunc_tf32(x)) (x - hi is exact in fp32), in the SAME layout as
-//      the source — 4 bytes read + 4 written per element instead of 4 + 8, and no transposes: an
-//      operand whose K index is not contiguous (B of an NN product, A of a TN product — every weight
-//      adjoint GEMM, AD.Float32.fs:4127-4143) is fed to the tensor core as an MN-major tile.
-//      Operands TMA cannot address directly (window not 16-byte aligned, contiguous extent not a
-//      multiple of 4) take the general route: hi and lo are both written as zero-padded K-major
-//      planes [rows x Kp], transposed through shared memory on the way if needed.
-//  (2) persistent warp-specialised kernel, one CTA per SM, 320 threads:
-//        warp 0    TMA producer: per k-block the hi and lo tiles of A and B into a STAGES-deep
-//                  shared-memory ring (K-major operand: one 32 x rows box per plane; MN-major operand:
-//                  one 32(MN) x 32(K) box per 32-wide MN block), completion on a `full` mbarrier
-//        warp 1    allocates TMEM and issues tcgen05.mma from one thread: per 8-wide k-slice
-//                  D += A_lo*B_hi; D += A_hi*B_lo; D += A_hi*B_hi  (128 x BN fp32 accumulator in
-//                  TMEM); tcgen05.commit releases the smem stage (`empty`) and, after the last
-//                  k-block of a chunk, publishes the accumulator (`tmem_full`)
-//        warps 2-9 epilogue: tcgen05.ld the accumulator (each warp owns the 32 TMEM lanes of its
-//                  quadrant and half of the columns), add the chunk into registers, and after the
-//                  last chunk add the bias and store float4s to C.  Two accumulator stages (2 x BN
-//                  TMEM columns) let the drain of chunk c overlap the MMAs of chunk c+1.
+// The operand split.  kind::tf32 reads fp32 words from shared memory and IGNORES the low 13 mantissa
+// bits, so the "hi" operand needs no plane of its own: the tensor core is pointed at the source buffer
+// and sees hi = trunc_tf32(x).  Only lo = rna_tf32(x - trunc_tf32(x)) (x - hi is exact in fp32) has to
+// be produced, in the SAME layout as the source, and no transposes are needed: an operand whose K index
+// is not contiguous (B of an NN product, A of a TN product — every weight adjoint GEMM,
+// AD.Float32.fs:4127-4143) is fed to the tensor core as an MN-major tile.  lo comes from
+//   * a pre-pass (split_pair_kernel, HBM-bound, one launch for both operands: 4 bytes read + 4 written
+//     per element) — the large products, or
+//   * converter warps inside the kernel (single-CTA 128 x 128 / 128 x 64 tiles: the small products,
+//     where a pre-pass launch costs more than it saves).
+// Operands TMA cannot address directly (window not 16-byte aligned, contiguous extent not a multiple of
+// 4) take the general route: hi and lo are both written by the pre-pass as zero-padded K-major planes
+// [rows x Kp], transposed through shared memory on the way if needed.
+//
+// The kernel (gemm_tf32x3_kernel<BN, PAIR, WIDE>): persistent, warp-specialised.
+//   warp 0     TMA producer: per 32-wide k-block the tiles of A and B into a ring of shared-memory stages
+//              (K-major operand: one 32 x rows box per plane; MN-major operand: one 32(MN) x 32(K) box
+//              per 32-wide MN block), completion on a `full` mbarrier
+//   warp 1     allocates TMEM and issues tcgen05.mma from one thread: per 8-wide k-slice
+//              D += A_lo*B_hi; D += A_hi*B_lo; D += A_hi*B_hi  (fp32 accumulator in TMEM);
+//              tcgen05.commit releases the smem stage (`empty`) and, after the last k-block of a chunk,
+//              publishes the accumulator (`tmem_full`)
+//   8 warps    epilogue: tcgen05.ld the accumulator (each warp owns the 32 TMEM lanes of its quadrant and
+//              half of the columns), add the chunk into registers, and after the last chunk add the bias
+//              and store float4s to C.  Two accumulator stages (2 x BN TMEM columns) let the drain of
+//              chunk c overlap the MMAs of chunk c+1.
+//   (+ 4 / 6)  converter warps in the variants that split in the kernel.
+// PAIR: the two CTAs of a cluster (the two SMs of a TPC) run ONE tcgen05.mma.cta_group::2 on a 256 x BN
+// tile — see Cfg below; this is the variant the planner picks for every large product.
 // The a_lo*b_lo term (<= 2^-22 relative) is dropped: that is the "3x" in 3xTF32.
 //
 // Accuracy of long reductions.  The tensor core's fp32 accumulator TRUNCATES on every accumulate
@@ -34,19 +40,19 @@
 // = 3 MMAs x K/16 x 2^-24).  The K loop is therefore cut into chunks of kChunkKb k-blocks (256
 // elements): each chunk accumulates from zero in TMEM (truncation bias <= 2.8e-6 of the chunk), and
 // the epilogue warps add the chunk results in registers with IEEE round-to-nearest fp32 adds.
-// The two TMEM accumulator stages alternate per chunk, so draining chunk c overlaps the MMAs of
-// chunk c+1.
 //
-// Stream-K.  The work of a GEMM is the list of (tile, K-chunk) units in tile-major order; the grid is
-// one CTA per SM (or per unit if there are fewer) and CTA b takes the b-th contiguous share of the
-// list, so every SM gets the same number of chunks (+-1) whatever the tile count — no partial last
-// wave (8192x1024x1024: 256 tiles on 148 SMs = 2 waves at 86 %; stream-K: 6.92 chunks per SM), and
-// small outputs with a deep K (weight adjoints: K = batch) are cut along K automatically.  A run of
-// units of one tile inside one CTA is a SEGMENT.  A segment that covers its whole tile is stored to C
-// directly.  Otherwise the CTA stores the segment sum to its workspace slot and takes a ticket for
-// the tile; the CTA that arrives last re-reads all the tile's segments in K order, adds them with
-// IEEE adds, applies the bias and stores C — the order of the additions is fixed, only who performs
-// them varies (deterministic).
+// Schedule.  The work of a GEMM is the list of (tile, K-chunk) units in tile-major order, shared out
+// over one worker (CTA, or CTA pair) per SM (pair of SMs):
+//   tiles >= workers : whole-tile waves, plus stream-K over the last, partial wave when K is deep;
+//   tiles <  workers : aligned split-K — every tile is cut into equal K ranges.
+// A run of units of one tile inside one worker is a SEGMENT.  A segment that covers its whole tile is
+// stored to C directly.  Partial segments are combined in K order with IEEE adds, whichever path they
+// take, so the result does not depend on timing (deterministic):
+//   * aligned split-K whose K ranges fit one thread-block cluster: the partial accumulators cross
+//     distributed shared memory and every CTA finishes 1/nseg of the columns from registers;
+//   * other aligned splits: plane-major workspace slots; the CTAs of a tile wait for each other and each
+//     reduces 1/nseg of the planes;
+//   * stream-K ranges: workspace slots + ticket; the CTA that arrives last adds the tile's segments.
 #include <cuda.h>
 #include <stdlib.h>
 
