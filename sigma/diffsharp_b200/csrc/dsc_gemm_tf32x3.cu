@@ -1116,52 +1116,28 @@ static int split_blocks(const OperandPlan& o, int rows, int k, int kp) {
     return ((rows + 31) / 32) * (kp / 32);
 }
 
-}  // namespace tf32x3
-
-int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const float* A, const float* B, const float* bias, float* C) {
-    using namespace tf32x3;
-    // Eligibility: enough rows/cols to fill 128-row tiles and enough depth to amortise the pre-pass.
-    // Skinny / tiny products stay on the CUDA-core kernel (they are bandwidth- or latency-bound).
-    if (m < 128 || n < 32 || k < 32) return 1;
-    DSC_TRY(load_encode());
-    const int kp = (k + BK - 1) / BK * BK;
-
-    // ---- plan: tile width, grid and schedule (all decided before anything is launched) ----
-    // Candidates: tile width 256 / 128 / 64, one CTA per tile (128 rows) or a CTA pair (256 rows); the
-    // cycle model is stated next to the candidate loop.
-    // Schedules (one kernel, see Params):
-    //   tiles >= SMs : whole-tile waves (neighbouring CTAs walk K in lockstep over neighbouring tiles,
-    //                  so operand panels are shared in L2) + stream-K over the tiles of the last,
-    //                  partial wave, whose operands fit in L2 whatever the order
-    //   tiles <  SMs : aligned split-K — every tile is cut into `s` equal K ranges (grid = tiles * s);
-    //                  CTAs of the same range stay in lockstep.  Unaligned stream-K ranges would keep
-    //                  all SMs busy but every CTA would stream its own operand slice from HBM
-    //                  (measured: 1024 x 1024 x 8192 ran 50 % slower that way).
-    const int num_kb = kp / BK;
-    const int cpt = (num_kb + kChunkKb - 1) / kChunkKb;
-    const int tiles_m = (m + BM - 1) / BM;
-    const double kb_per_chunk = (double)num_kb / cpt;
-    // op(A)(m x k): stored m x k (K contiguous) unless ta; op(B)(k x n): stored n x k (K contiguous) only if tb
-    const OperandPlan pa = plan_operand(A, !ta, m, k, kp), pb = plan_operand(B, tb != 0, n, k, kp);
-    // In-kernel split (tiles narrower than 256): a direct operand needs no pre-pass and no lo plane;
-    // only its fp32 words cross L2 -> SM (half the bytes), and the converter warps derive the lo tile.
-    static const int fuse_env0 = [] { const char* e = getenv("DSC_GEMM_FUSE"); return e ? atoi(e) : 1; }();
-    static const int force_bn0 = [] { const char* e = getenv("DSC_GEMM_BN"); return e ? atoi(e) : 0; }();
-    const int fuse_env = ctx->gemm_force_fuse >= 0 ? ctx->gemm_force_fuse : fuse_env0;
-    const int force_bn = ctx->gemm_force_bn > 0 ? ctx->gemm_force_bn : force_bn0;
-    static const int force_pair0 = [] { const char* e = getenv("DSC_GEMM_PAIR"); return e ? atoi(e) : -1; }();   // -1: planner decides
-    const int force_pair = ctx->gemm_force_pair >= 0 ? ctx->gemm_force_pair : force_pair0;
-    const int force_split = ctx->gemm_force_split;
-    // Kernel variants with converter warps (Cfg::kConvWarps > 0).  The WIDE pair kernel is correct but
-    // measured slower than pre-pass + plain pair kernel on every shape tried (8192 x 1024 x 1024:
-    // 91.5 us against 80.6 us including the pre-pass): the in-kernel split repeats the conversion for
-    // every tile that re-reads an operand and its 64 KB of converter traffic per k-block competes with
-    // the MMA operand fetch for shared-memory bandwidth.  It is only planned when asked for
-    // (dsc_gemm_tune fuse = 2), which is how the parity tests and tools/gemm_sweep.py reach it.
-    const bool allow_wide = ctx->gemm_force_fuse == 2;
-    auto has_converters = [allow_wide](int c, bool pr) { return pr ? (allow_wide && c == 256) : c < 256; };
+// ---- the planner: a pure function of the shape, the SM count and the pinned choices -------------------
+// (exported as dsc_gemm_plan so that the schedule arithmetic is unit-tested on a machine without a GPU)
+struct PlanIn {
+    int sm_count, m, n, k, num_kb, cpt;
+    bool a_direct, b_direct;      // operand is addressable by TMA in place (plan_operand)
+    int fuse;                     // 0: never split in the kernel; 1: single-CTA kernels may; 2: also the WIDE pair kernel
+    int force_bn, force_pair, force_split;
+    bool allow_wide;
+};
+struct PlanOut {
+    int bn, grid, dp_waves, dp_extra, sk_units_total, perm_s;
+    bool pair;
+};
+static bool make_plan(const PlanIn& in, PlanOut& out) {
     int bn = 256, grid = 1, dp_waves = 0, dp_extra = 0, sk_units_total = 0, perm_s = 0;
     bool pair = false;
+    const int cpt = in.cpt;
+    const double kb_per_chunk = (double)in.num_kb / cpt;
+    const int m = in.m, n = in.n, k = in.k;
+    const int fuse_env = in.fuse, force_bn = in.force_bn, force_pair = in.force_pair, force_split = in.force_split;
+    const bool allow_wide = in.allow_wide;
+    auto has_converters = [allow_wide](int c, bool pr) { return pr ? (allow_wide && c == 256) : c < 256; };
     {
         // Per worker (CTA, or CTA pair) and 32-wide k-block, in cycles:
         //   tensor pipe : 4 k-slices x 3 MMAs x (BN/256 x 128)                               = 6 BN
@@ -1178,11 +1154,11 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
             const int tiles_m_c = (m + tm - 1) / tm;
             const long tiles = (long)tiles_m_c * ((n + c - 1) / c);
             if (tiles * cpt > 0x3fffffff) continue;
-            const int workers = pr ? ctx->sm_count / 2 : ctx->sm_count;
+            const int workers = pr ? in.sm_count / 2 : in.sm_count;
             const int ctas_per_worker = pr ? 2 : 1;
             const int brows = pr ? c / 2 : c;
             const bool can_fuse = fuse_env && has_converters(c, pr);
-            bool fa = can_fuse && pa.direct, fb = can_fuse && pb.direct;
+            bool fa = can_fuse && in.a_direct, fb = can_fuse && in.b_direct;
             if (pr) fa = fb = (fa && fb);   // the pair kernel splits both operands in the kernel or neither
             const double bytes_kb = (double)BM * (fa ? 128.0 : 256.0) + (double)brows * (fb ? 128.0 : 256.0);
             const double smem_kb = (double)BM * (fa ? 6.0 : 5.0) + (double)brows * (fb ? 6.0 : 5.0);
@@ -1230,8 +1206,65 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
                 }
             }
         }
-        if (best < 0) return 1;
+        if (best < 0) return false;
     }
+    out.bn = bn; out.pair = pair; out.grid = grid; out.dp_waves = dp_waves; out.dp_extra = dp_extra;
+    out.sk_units_total = sk_units_total; out.perm_s = perm_s;
+    return true;
+}
+
+}  // namespace tf32x3
+
+int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const float* A, const float* B, const float* bias, float* C) {
+    using namespace tf32x3;
+    // Eligibility: enough rows/cols to fill 128-row tiles and enough depth to amortise the pre-pass.
+    // Skinny / tiny products stay on the CUDA-core kernel (they are bandwidth- or latency-bound).
+    if (m < 128 || n < 32 || k < 32) return 1;
+    DSC_TRY(load_encode());
+    const int kp = (k + BK - 1) / BK * BK;
+
+    // ---- plan: tile width, grid and schedule (all decided before anything is launched) ----
+    // Candidates: tile width 256 / 128 / 64, one CTA per tile (128 rows) or a CTA pair (256 rows); the
+    // cycle model is stated next to the candidate loop.
+    // Schedules (one kernel, see Params):
+    //   tiles >= SMs : whole-tile waves (neighbouring CTAs walk K in lockstep over neighbouring tiles,
+    //                  so operand panels are shared in L2) + stream-K over the tiles of the last,
+    //                  partial wave, whose operands fit in L2 whatever the order
+    //   tiles <  SMs : aligned split-K — every tile is cut into `s` equal K ranges (grid = tiles * s);
+    //                  CTAs of the same range stay in lockstep.  Unaligned stream-K ranges would keep
+    //                  all SMs busy but every CTA would stream its own operand slice from HBM
+    //                  (measured: 1024 x 1024 x 8192 ran 50 % slower that way).
+    const int num_kb = kp / BK;
+    const int cpt = (num_kb + kChunkKb - 1) / kChunkKb;
+    const int tiles_m = (m + BM - 1) / BM;
+    // op(A)(m x k): stored m x k (K contiguous) unless ta; op(B)(k x n): stored n x k (K contiguous) only if tb
+    const OperandPlan pa = plan_operand(A, !ta, m, k, kp), pb = plan_operand(B, tb != 0, n, k, kp);
+    // In-kernel split (tiles narrower than 256): a direct operand needs no pre-pass and no lo plane;
+    // only its fp32 words cross L2 -> SM (half the bytes), and the converter warps derive the lo tile.
+    static const int fuse_env0 = [] { const char* e = getenv("DSC_GEMM_FUSE"); return e ? atoi(e) : 1; }();
+    static const int force_bn0 = [] { const char* e = getenv("DSC_GEMM_BN"); return e ? atoi(e) : 0; }();
+    const int fuse_env = ctx->gemm_force_fuse >= 0 ? ctx->gemm_force_fuse : fuse_env0;
+    const int force_bn = ctx->gemm_force_bn > 0 ? ctx->gemm_force_bn : force_bn0;
+    static const int force_pair0 = [] { const char* e = getenv("DSC_GEMM_PAIR"); return e ? atoi(e) : -1; }();   // -1: planner decides
+    const int force_pair = ctx->gemm_force_pair >= 0 ? ctx->gemm_force_pair : force_pair0;
+    const int force_split = ctx->gemm_force_split;
+    // Kernel variants with converter warps (Cfg::kConvWarps > 0).  The WIDE pair kernel is correct but
+    // measured slower than pre-pass + plain pair kernel on every shape tried (8192 x 1024 x 1024:
+    // 91.5 us against 80.6 us including the pre-pass): the in-kernel split repeats the conversion for
+    // every tile that re-reads an operand and its 64 KB of converter traffic per k-block competes with
+    // the MMA operand fetch for shared-memory bandwidth.  It is only planned when asked for
+    // (dsc_gemm_tune fuse = 2), which is how the parity tests and tools/gemm_sweep.py reach it.
+    const bool allow_wide = ctx->gemm_force_fuse == 2;
+    auto has_converters = [allow_wide](int c, bool pr) { return pr ? (allow_wide && c == 256) : c < 256; };
+    PlanIn pin;
+    pin.sm_count = ctx->sm_count; pin.m = m; pin.n = n; pin.k = k; pin.num_kb = num_kb; pin.cpt = cpt;
+    pin.a_direct = pa.direct; pin.b_direct = pb.direct;
+    pin.fuse = fuse_env; pin.force_bn = force_bn; pin.force_pair = force_pair; pin.force_split = force_split;
+    pin.allow_wide = allow_wide;
+    PlanOut pout;
+    if (!make_plan(pin, pout)) return 1;
+    const int bn = pout.bn, grid = pout.grid, dp_waves = pout.dp_waves, dp_extra = pout.dp_extra, sk_units_total = pout.sk_units_total, perm_s = pout.perm_s;
+    const bool pair = pout.pair;
     Params p;
     p.m = m; p.n = n; p.num_kb = num_kb;
     p.tiles_m = pair ? (m + 2 * BM - 1) / (2 * BM) : tiles_m;
@@ -1344,6 +1377,41 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
 }
 
 }  // namespace dsc
+
+extern "C" int dsc_gemm_plan(int sm_count, int m, int n, int k, int a_direct, int b_direct, int bn, int pair, int split, int fuse, int32_t out[20]) {
+    using namespace dsc;
+    using namespace dsc::tf32x3;
+    if (!out || sm_count < 2 || m < 0 || n < 0 || k < 0) return fail(DSC_E_INVALID, "dsc_gemm_plan: bad arguments");
+    for (int i = 0; i < 20; ++i) out[i] = 0;
+    if (m < 128 || n < 32 || k < 32) return DSC_OK;   // not eligible: out[0] = 0
+    const int kp = (k + BK - 1) / BK * BK;
+    PlanIn pin;
+    pin.sm_count = sm_count; pin.m = m; pin.n = n; pin.k = k;
+    pin.num_kb = kp / BK;
+    pin.cpt = (pin.num_kb + kChunkKb - 1) / kChunkKb;
+    pin.a_direct = a_direct != 0; pin.b_direct = b_direct != 0;
+    pin.fuse = fuse < 0 ? 1 : fuse;
+    pin.force_bn = bn > 0 ? bn : 0;
+    pin.force_pair = pair < 0 ? -1 : (pair != 0);
+    pin.force_split = split;
+    pin.allow_wide = fuse == 2;
+    PlanOut po;
+    if (!make_plan(pin, po)) return DSC_OK;
+    const int tiles_m = po.pair ? (m + 2 * BM - 1) / (2 * BM) : (m + BM - 1) / BM;
+    const int tiles_n = (n + po.bn - 1) / po.bn;
+    const long tiles = (long)tiles_m * tiles_n;
+    auto has_converters = [&](int c, bool pr) { return pr ? (pin.allow_wide && c == 256) : c < 256; };
+    bool a_fused = pin.fuse && has_converters(po.bn, po.pair) && pin.a_direct, b_fused = pin.fuse && has_converters(po.bn, po.pair) && pin.b_direct;
+    if (po.pair) a_fused = b_fused = (a_fused && b_fused);
+    const bool wide = po.pair && po.bn == 256 && a_fused && b_fused;
+    const int sp = po.perm_s;
+    const int kc = (!wide && (sp == 2 || sp == 4 || sp == 8) && (po.pair ? 2 : 1) * sp <= 8 && (po.bn / 8) % sp == 0) ? sp : 0;
+    out[0] = 1; out[1] = po.bn; out[2] = po.pair ? 1 : 0; out[3] = po.grid; out[4] = pin.cpt; out[5] = pin.num_kb;
+    out[6] = tiles_m; out[7] = tiles_n; out[8] = po.dp_waves; out[9] = po.dp_extra; out[10] = po.sk_units_total; out[11] = po.perm_s;
+    out[12] = po.sk_units_total / po.grid; out[13] = po.sk_units_total % po.grid; out[14] = po.dp_waves * po.grid;
+    out[15] = po.perm_s ? (int)tiles : 0; out[16] = kc; out[17] = a_fused ? 1 : 0; out[18] = b_fused ? 1 : 0;
+    return DSC_OK;
+}
 
 extern "C" int dsc_gemm_debug_stamps(dsc_ctx_t c, uint64_t out[8]) {
     using namespace dsc;
