@@ -1291,7 +1291,7 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
         static const int kc_env = [] { const char* e = getenv("DSC_GEMM_KCLUSTER"); return e ? atoi(e) : 1; }();
         const int sp = perm_s;
         const bool wide = pair && bn == 256 && a_fused && b_fused;
-        if (kc_env && !wide && (sp == 2 || sp == 4) && (pair ? 2 : 1) * sp <= 8 && (bn / 8) % sp == 0) {   // (8 K ranges: not exercised on hardware yet)
+        if (kc_env && !wide && (sp == 2 || sp == 4) && (pair ? 2 : 1) * sp <= 4 && (bn / 8) % sp == 0) {   // clusters of 2 and 4 CTAs (8: not exercised on hardware yet)
             const int cl = (pair ? 2 : 1) * sp;
             int fit = 0;
             if (pair) fit = bn == 256 ? max_active_clusters<256, true>(cl) : (bn == 128 ? max_active_clusters<128, true>(cl) : max_active_clusters<64, true>(cl));
@@ -1405,7 +1405,7 @@ extern "C" int dsc_gemm_plan(int sm_count, int m, int n, int k, int a_direct, in
     if (po.pair) a_fused = b_fused = (a_fused && b_fused);
     const bool wide = po.pair && po.bn == 256 && a_fused && b_fused;
     const int sp = po.perm_s;
-    const int kc = (!wide && (sp == 2 || sp == 4) && (po.pair ? 2 : 1) * sp <= 8 && (po.bn / 8) % sp == 0) ? sp : 0;
+    const int kc = (!wide && (sp == 2 || sp == 4) && (po.pair ? 2 : 1) * sp <= 4 && (po.bn / 8) % sp == 0) ? sp : 0;
     out[0] = 1; out[1] = po.bn; out[2] = po.pair ? 1 : 0; out[3] = po.grid; out[4] = pin.cpt; out[5] = pin.num_kb;
     out[6] = tiles_m; out[7] = tiles_n; out[8] = po.dp_waves; out[9] = po.dp_extra; out[10] = po.sk_units_total; out[11] = po.perm_s;
     out[12] = po.sk_units_total / po.grid; out[13] = po.sk_units_total % po.grid; out[14] = po.dp_waves * po.grid;

@@ -110,7 +110,7 @@ def check_plan(p):
             assert seg_len == p["cpt"] // p["perm_s"] and ch0 == (lb % p["perm_s"]) * seg_len
     if p["kcluster"]:
         sp = p["kcluster"]
-        assert sp == p["perm_s"] and (2 if p["pair"] else 1) * sp <= 8 and (p["bn"] // 8) % sp == 0
+        assert sp == p["perm_s"] and (2 if p["pair"] else 1) * sp <= 4 and (p["bn"] // 8) % sp == 0
         _, seg_id = walk(p, perm_tiles=0)   # the cluster exchange runs with the identity worker order
         for lb, tile, ch0, seg_len, full, which, b_first, b_last in seg_id:
             assert tile == lb // sp and ch0 == (lb % sp) * seg_len and not full
@@ -158,6 +158,6 @@ def test_config_three_plans_are_what_the_profiles_describe():
     p = plan(148, 8192, 1024, 1024)
     assert (p["bn"], p["pair"], p["grid"], p["dp_waves"], p["dp_extra"]) == (256, 1, 74, 1, 54)
     p = plan(148, 1024, 1024, 8192)
-    assert (p["bn"], p["pair"], p["perm_s"], p["grid"]) == (256, 1, 4, 64) and p["kcluster"] == 4   # 16 clusters of 8 do not fit: decided at run time
+    assert (p["bn"], p["pair"], p["perm_s"], p["grid"]) == (256, 1, 4, 64) and p["kcluster"] == 0   # a cluster of 8 CTAs: workspace fix-up
     p = plan(148, 1024, 1024, 1024)
     assert (p["bn"], p["pair"], p["perm_s"], p["a_fused"], p["b_fused"], p["kcluster"]) == (128, 0, 2, 1, 1, 2)
