@@ -27,6 +27,14 @@ def test_library_has_sm100a_code():
     assert "sm_100a" in out
 
 
+def test_hot_kernels_use_the_blackwell_units():
+    """SASS evidence that the hot paths are what DESIGN.md says they are: tcgen05 MMAs (1- and 2-CTA) fed by TMA with
+    TMEM loads in the epilogue, thread-block cluster barriers, DMMA for float64, 128-bit global loads in the streams."""
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA.2CTA", "UTCHMMA", "UTMALDG.2D", "LDTM", "UTCBAR", "UCGABAR_ARV", "DMMA", "LDG.E.128", "SYNCS.PHASECHK"):
+        assert mnemonic in sass, mnemonic
+
+
 def test_version():
     assert _lib.lib.dsc_version() == 100
 
