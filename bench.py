@@ -2,7 +2,8 @@
 """bench.py — BASELINE.json's metric on BASELINE.json's config.
 
 metric  : "MLP grad steps/sec" on config 3 (784-1024-1024-10 tanh MLP, global batch 8192, float32,
-          batch rows sharded over N GPUs, NCCL all-reduce of the weight/bias adjoints), plus the
+          batch rows sharded over N GPUs, one all-reduce of the weight/bias adjoints: a peer-memory kernel over
+          NVLink, NCCL when peer access is unavailable), plus the
           backend-op sweep (config 2, 4096x4096 f32/f64) as HBM GB/s and GEMM TFLOP/s vs peak.
 A "step" = one reverse-mode gradient of the summed-squared-error loss: the full Backend<'T> call
 sequence the unchanged AD layer issues (zero-adjoint fills, transposes, adjoint accumulations, loss
@@ -13,8 +14,8 @@ scaling.
           call sequence (every kernel of the eager sequence runs; the host tape walk does not).
   eager : the same step driven op by op through the plugin interface (reported next to it).
   e2e   : through the public plugin call (workloads.mlp_grad over CudaBackend) with HOST buffers:
-          every step uploads its X/Y rows from pinned host memory and reads the loss and all
-          adjoints back to pinned host memory.
+          every step every rank uploads its X/Y rows from pinned host memory and reads its loss back; rank 0
+          also reads all (all-reduced) adjoints back to pinned host memory.
 
 `--impl reference` times the CPU oracle (oracle/: the same call sequence over OpenBLAS — the
 reference's own F#/OpenBLAS stack cannot be built here) on the box's host cores.
