@@ -34,8 +34,8 @@ namespace dsc {
 typedef struct { char internal[128]; } nccl_unique_id;
 typedef void* nccl_comm_t;
 enum { NCCL_SUCCESS = 0 };
-enum { NCCL_UINT8 = 1, NCCL_INT32 = 2, NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8 };  // ncclDataType_t values (nccl.h)
-enum { NCCL_SUM = 0, NCCL_MIN = 3 };
+enum { NCCL_UINT8 = 1, NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8 };  // ncclDataType_t values (nccl.h)
+enum { NCCL_SUM = 0 };
 
 struct NcclApi {
     void* lib = nullptr;
@@ -126,14 +126,6 @@ struct P2PArgs {
     size_t region_bytes;
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -435,7 +427,7 @@ static int allgather_impl(dsc_ctx_t c, dsc_buf_t sendh, dsc_buf_t recvh) {
 }
 
 // Map every rank's symmetric buffer into this process.  Collective: every rank must call it; the
-// outcome (p2p_ok) is agreed with a MIN all-reduce so that no rank takes the peer path alone.
+// outcome (p2p_ok) is agreed through two all-gathers so that no rank takes the peer path alone.
 static int p2p_setup(Ctx* ctx) {
     ctx->p2p_ok = false;
     const char* off = getenv("DSC_P2P");
