@@ -379,8 +379,14 @@ def run_ours(args):
 
     # ---- warm-up (also sizes the GEMM workspace and the pool before capture) ----
     for _ in range(max(args.warmup, 3)):
-        eager_step()
+        _, chk_W, chk_b = eager_step()
     ctx.sync()
+    # the all-reduced adjoints must be the SAME bits on every rank (rank-ordered sum): compare a float64 checksum
+    chk = float(np.sum(chk_W[-1].ToArray(), dtype=np.float64) + sum(np.sum(v.ToArray(), dtype=np.float64) for v in chk_b))
+    adjoints_identical = bool(D.max_over_ranks(chk) == -D.max_over_ranks(-chk))
+    if not adjoints_identical:
+        raise SystemExit(f"rank {rank}: the all-reduced adjoints differ between ranks (checksum {chk!r})")
+    del chk_W, chk_b
 
     # ---- eager timing: the plugin interface driven op by op ----
     s0 = ctx.stats()
@@ -588,7 +594,7 @@ def run_ours(args):
         "gpu_launches": int(launches_per_step * args.steps),
         "launches_per_step": int(launches_per_step),
         "step_gflop": STEP_GFLOP, "step_tflops": round(STEP_GFLOP / world / graph_ms, 2),
-        "loss": loss_graph, "loss_e2e": loss_e2e, "loss_e2e_eager": loss_e2e_eager,
+        "loss": loss_graph, "loss_e2e": loss_e2e, "loss_e2e_eager": loss_e2e_eager, "adjoints_identical_on_all_ranks": adjoints_identical,
         "clocks": clocks, "roofline": roofline, "peaks": peaks,
     }
     if not args.no_other:
