@@ -238,7 +238,11 @@ class OracleBackend(Backend):
         st = self._f("gesv")(A.Rows, _ptr(a), _ptr(bv), _ptr(out))
         return None if st != 0 else self._buf(out)
 
-    SolveSymmetric_M_V = Solve_M_V
+    def SolveSymmetric_M_V(self, A, b):
+        a, bv = self._mat(A), self._w(b)
+        out = self._new(A.Rows)
+        st = self._f("sysv")(A.Rows, _ptr(a), _ptr(bv), _ptr(out))
+        return None if st != 0 else self._buf(out)
 
     def Inverse_M(self, A):
         a = self._mat(A)

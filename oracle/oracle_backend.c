@@ -35,6 +35,8 @@ typedef void (*sger_t)(int, int, int, float, const float*, int, const float*, in
 typedef void (*dger_t)(int, int, int, double, const double*, int, const double*, int, double*, int);
 typedef void (*sgesv_t)(int*, int*, float*, int*, int*, float*, int*, int*);
 typedef void (*dgesv_t)(int*, int*, double*, int*, int*, double*, int*, int*);
+typedef void (*ssysv_t)(const char*, int*, int*, float*, int*, int*, float*, int*, float*, int*, int*);
+typedef void (*dsysv_t)(const char*, int*, int*, double*, int*, int*, double*, int*, double*, int*, int*);
 typedef void (*sgetrf_t)(int*, int*, float*, int*, int*, int*);
 typedef void (*dgetrf_t)(int*, int*, double*, int*, int*, int*);
 typedef void (*sgetri_t)(int*, float*, int*, int*, float*, int*, int*);
@@ -45,7 +47,7 @@ static struct {
     sdot_t sdot; ddot_t ddot; sasum_t sasum; dasum_t dasum; sdot_t dummy;
     sasum_t snrm2; dasum_t dnrm2; isamax_t isamax; idamax_t idamax;
     sgemm_t sgemm; dgemm_t dgemm; sgemv_t sgemv; dgemv_t dgemv; sger_t sger; dger_t dger;
-    sgesv_t sgesv; dgesv_t dgesv; sgetrf_t sgetrf; dgetrf_t dgetrf; sgetri_t sgetri; dgetri_t dgetri;
+    sgesv_t sgesv; dgesv_t dgesv; ssysv_t ssysv; dsysv_t dsysv; sgetrf_t sgetrf; dgetrf_t dgetrf; sgetri_t sgetri; dgetri_t dgetri;
     void (*set_threads)(int);
     int (*get_threads)(void);
     char* (*get_config)(void);
@@ -70,7 +72,7 @@ int oracle_init(const char* path, const char* prefix) {
     S(snrm2, "cblas_snrm2") S(dnrm2, "cblas_dnrm2") S(isamax, "cblas_isamax") S(idamax, "cblas_idamax")
     S(sgemm, "cblas_sgemm") S(dgemm, "cblas_dgemm") S(sgemv, "cblas_sgemv") S(dgemv, "cblas_dgemv")
     S(sger, "cblas_sger") S(dger, "cblas_dger")
-    S(sgesv, "sgesv_") S(dgesv, "dgesv_") S(sgetrf, "sgetrf_") S(dgetrf, "dgetrf_") S(sgetri, "sgetri_") S(dgetri, "dgetri_")
+    S(sgesv, "sgesv_") S(dgesv, "dgesv_") S(ssysv, "ssysv_") S(dsysv, "dsysv_") S(sgetrf, "sgetrf_") S(dgetrf, "dgetrf_") S(sgetri, "sgetri_") S(dgetri, "dgetri_")
     S(set_threads, "openblas_set_num_threads") S(get_threads, "openblas_get_num_threads") S(get_config, "openblas_get_config")
 #undef S
     return 0;
@@ -90,6 +92,7 @@ const char* oracle_openblas_config(void) { return g.get_config ? g.get_config() 
 #define BLS_gemv sgemv
 #define BLS_ger sger
 #define BLS_gesv sgesv
+#define BLS_sysv ssysv
 #define BLS_getrf sgetrf
 #define BLS_getri sgetri
 #include "oracle_backend_impl.h"
@@ -108,6 +111,7 @@ const char* oracle_openblas_config(void) { return g.get_config ? g.get_config() 
 #define BLD_gemv dgemv
 #define BLD_ger dger
 #define BLD_gesv dgesv
+#define BLD_sysv dsysv
 #define BLD_getrf dgetrf
 #define BLD_getri dgetri
 #include "oracle_backend_impl.h"

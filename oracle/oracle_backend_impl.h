@@ -230,6 +230,22 @@ int FN(gesv)(int n, const T* A, const T* b, T* x) {
     free(ipiv);
     return info == 0 ? 0 : -7;
 }
+/* SolveSymmetric_M_V (Backend.fs:103, call site AD.Float32.fs:2832): LAPACK ?sysv (Bunch-Kaufman LDL^T) on the
+ * upper triangle of the column-major matrix = the lower triangle of the row-major one. */
+int FN(sysv)(int n, const T* A, const T* b, T* x) {
+    T* At = (T*)malloc(sizeof(T) * (size_t)n * n);
+    int* ipiv = (int*)malloc(sizeof(int) * (size_t)n);
+    int lwork = n * 64 > 64 ? n * 64 : 64;
+    T* work = (T*)malloc(sizeof(T) * (size_t)lwork);
+    FN(transpose)(n, n, A, At);
+    memcpy(x, b, sizeof(T) * (size_t)n);
+    int nn = n, nrhs = 1, info = 0;
+    BL(sysv)("U", &nn, &nrhs, At, &nn, ipiv, x, &nn, work, &lwork, &info);
+    free(At);
+    free(ipiv);
+    free(work);
+    return info == 0 ? 0 : -7;
+}
 int FN(getri)(int n, const T* A, T* Ainv) {
     T* At = (T*)malloc(sizeof(T) * (size_t)n * n);
     int* ipiv = (int*)malloc(sizeof(int) * (size_t)n);

@@ -802,6 +802,15 @@ class DNDArray(_AD):
         d.f = self.f
         return d
 
+    def CustomOp(self, customInfo):  # :1758-1763 — opaque consumer hook (Backend.fs:137-139)
+        if self.kind == PRIMAL:
+            return DNDArray(Backend(self.p).CustomOp_DM_Forward(self.p, customInfo))
+        if self.kind == FORWARD:
+            return DNDArray.DMF(DNDArray(Backend(self.p).CustomOp_DM_Forward(self.p.Buffer, customInfo)),
+                                DNDArray(Backend(self.t).CustomOp_DM_Forward(self.t.Buffer, customInfo)), self.tag)
+        return DNDArray.DMR(DNDArray(Backend(self.p).CustomOp_DM_Forward(self.p.Buffer, customInfo)),
+                            TraceOp("Custom_DM", self, customInfo), self.tag)
+
     def ToArray(self) -> np.ndarray:
         return self.Buffer.to_numpy()
 
@@ -1503,6 +1512,7 @@ def _inverse_push(d, a):
 
 
 _reg("Inverse_DM", _a0, _inverse_push)
+_reg("Custom_DM", _a0, lambda d, a: [(DNDArray(Backend(a[0]).CustomOp_DM_Backward(a[0].P.Buffer, d.A.Buffer, d.P.Buffer, a[1])), a[0])])  # :4282
 _reg("Diagonal_DM", _a0, None)   # needs AddDiagonal (not restated)
 _reg("Noop", lambda a: [], lambda d, a: [])
 

@@ -39,7 +39,24 @@ def op_inputs(dtype, seed=7, n=37, m=5, k=7):
         "vm": rng.standard_normal(m).astype(dtype),
         "vk": rng.standard_normal(k).astype(dtype),
         "v6": rng.standard_normal(6).astype(dtype),
+        # drawn after everything above, so the earlier fixtures keep their values
+        "Sym": (lambda g: (g + g.T) / 2 + np.diag([3, -3, 2.5, -2, 4, -4]))(rng.standard_normal((6, 6))).astype(dtype),   # symmetric INDEFINITE
     }
+
+
+class ScaledSquare:
+    """A consumer-defined custom op (the `customInfo : obj` payload of CustomOp_DM_Forward / _Backward, Backend.fs:137-139;
+    call sites AD.Float32.fs:1760-1763, 4282): y = s * a .* a, adjoint = 2 s * origin .* adjoint — written against the
+    backend's own members, so it runs on whichever backend it is handed."""
+
+    def __init__(self, s):
+        self.s = s
+
+    def forward(self, backend, a):
+        return backend.Mul_S_M(backend.dtype.type(self.s), backend.Mul_Had_M_M(a, a))
+
+    def backward(self, backend, origin, adjoint, primal):
+        return backend.Mul_S_M(backend.dtype.type(2 * self.s), backend.Mul_Had_M_M(origin, adjoint))
 
 
 def run_ops(b, inp):
@@ -88,9 +105,59 @@ def run_ops(b, inp):
     out["solve"] = b.Solve_M_V(view(S), buf(inp["v6"])).SubData
     out["inverse"] = b.Inverse_M(view(S)).DataBuffer.SubData
     out["det"] = np.array([b.Det_M(view(S))])
+    out["solve_symmetric"] = b.SolveSymmetric_M_V(view(inp["Sym"]), buf(inp["v6"])).SubData
+    out["reshape_copy_mrows_v"] = b.ReshapeCopy_MRows_V(view(A)).SubData                         # Backend.fs:109
+    rc = b.ReshapeCopy_V_MRows(5, buf(np.arange(35, dtype=b.dtype)))                             # Backend.fs:134
+    out["reshape_copy_v_mrows"] = np.concatenate([np.array(rc.Shape, b.dtype), rc.DataBuffer.SubData])
+    rs = b.Reshape_M(view(A), [7, 5])                                                            # Backend.fs:129: same data, new shape
+    out["reshape"] = np.concatenate([np.array(rs.Shape, b.dtype), rs.DataBuffer.SubData[:35], b.Transpose_M(rs).DataBuffer.SubData[:35]])
+    cop = ScaledSquare(0.75)
+    fw = b.CustomOp_DM_Forward(view(A), cop)                                                     # Backend.fs:137
+    out["custom_forward"] = fw.DataBuffer.SubData
+    out["custom_backward"] = b.CustomOp_DM_Backward(view(A), view(A * 0.5 + 1), fw, cop).DataBuffer.SubData   # Backend.fs:138-139
     T3 = np.arange(24, dtype=b.dtype).reshape(2, 3, 4)
     out["permute"] = b.Permute_M(ShapedDataBufferView(buf(T3), 2, 3, 4), [2, 0, 1]).DataBuffer.SubData
     return out
+
+
+C3_LAYERS, C3_BATCH = [784, 1024, 1024, 10], 8192
+
+
+def c3_full_step():
+    """config 3 at its full size (global batch 8192) on whichever backend is installed: (loss, [dW1, dW2, dW3, db1, db2, db3])."""
+    X, Y, Ws, bs = wl.mlp_inputs(C3_LAYERS, C3_BATCH)
+    L, dW, db = wl.mlp_grad(wl.to_DM(X), wl.to_DM(Y), [wl.to_DM(w) for w in Ws], [wl.to_DV(b) for b in bs])
+    return float(L), [a.ToArray().reshape(-1) for a in dW + db]
+
+
+def sample_index(n, count=64):
+    """`count` positions spread over a buffer of n elements (first, last and a fixed stride in between)."""
+    return np.unique(np.linspace(0, n - 1, min(count, n)).astype(np.int64))
+
+
+def c3_digest(loss, grads):
+    """What bench.py and the N-GPU tests compare the all-reduced adjoints with ("gradients equal the 1-GPU
+    result <= 1e-5"): per adjoint buffer its L2 norm, its first 16 elements and 64 samples spread over the buffer."""
+    g = {"c3_loss": np.array([loss])}
+    for i, v in enumerate(grads):
+        g[f"c3_grad{i}_l2"] = np.array([np.sqrt(np.sum(v.astype(np.float64) ** 2))])
+        g[f"c3_grad{i}_head"] = v[:16].copy()
+        g[f"c3_grad{i}_samp"] = v[sample_index(v.size)].copy()
+    return g
+
+
+def c3_digest_max_rel(loss, grads, gold):
+    """max over the digest entries of |got - gold| / scale (scale = the buffer's max magnitude among the stored samples /
+    its L2 norm / the loss)."""
+    worst = abs(loss - float(gold["c3_loss"][0])) / abs(float(gold["c3_loss"][0]))
+    for i, v in enumerate(grads):
+        l2 = np.sqrt(np.sum(v.astype(np.float64) ** 2))
+        worst = max(worst, abs(l2 - float(gold[f"c3_grad{i}_l2"][0])) / float(gold[f"c3_grad{i}_l2"][0]))
+        ref = np.concatenate([gold[f"c3_grad{i}_head"], gold[f"c3_grad{i}_samp"]]).astype(np.float64)
+        got = np.concatenate([v[:16], v[sample_index(v.size)]]).astype(np.float64)
+        scale = max(np.abs(ref).max(), float(gold[f"c3_grad{i}_l2"][0]) / np.sqrt(v.size))
+        worst = max(worst, float(np.abs(got - ref).max() / scale))
+    return worst
 
 
 def config_goldens():
@@ -102,6 +169,7 @@ def config_goldens():
         v = a.ToArray().reshape(-1)
         g[f"c1_grad{i}_head"] = v[:16].copy()
         g[f"c1_grad{i}_l2"] = np.array([np.sqrt(np.sum(v.astype(np.float64) ** 2))])
+    g.update(c3_digest(*c3_full_step()))
     W1, b1, W2, b2, x = wl.jacobian_inputs(96)
     g["c4_rows"] = wl.jacobian_rows(wl.to_DM(W1), wl.to_DV(b1), wl.to_DM(W2), wl.to_DV(b2), wl.to_DV(x), 16, 32).ToArray()
     x, v, d = wl.hvp_inputs(4096)

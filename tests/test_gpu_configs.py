@@ -56,6 +56,40 @@ def test_c3_shape_small_batch_parity(oracle_provider, cuda_provider, use_provide
         assert rel_err(a, b) <= 1e-5
 
 
+@pytest.fixture(scope="module")
+def c3_oracle_full(oracle_provider):
+    """ONE full-size config-3 step on the CPU oracle (a few seconds), shared by the tests below."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden as mg
+    from sigma.diffsharp_b200.config import GlobalConfig
+    old = GlobalConfig.BackendProvider
+    GlobalConfig.BackendProvider = oracle_provider
+    try:
+        return mg.c3_full_step()
+    finally:
+        GlobalConfig.BackendProvider = old
+
+
+@pytest.mark.parametrize("fixture", ["cuda_provider", "cuda_provider_nofuse"])
+def test_c3_full_size_against_the_oracle(request, c3_oracle_full, use_provider, fixture):
+    """config 3 AT THE SIZE THE METRIC IS QUOTED ON (784-1024-1024-10, batch 8192, float32): loss and all six adjoints
+    within 1e-5 of the CPU oracle, with and without the deferred evaluation, and against the committed digest that
+    bench.py and the N-GPU runs compare with.  The weight adjoints reduce over K = 8192 batch rows on the tensor cores."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden as mg
+    Lr, gr = c3_oracle_full
+    use_provider(request.getfixturevalue(fixture))
+    Lg, gg = mg.c3_full_step()
+    assert abs(Lg - Lr) <= 1e-5 * abs(Lr)
+    for i, (a, b) in enumerate(zip(gg, gr)):
+        assert a.shape == b.shape
+        assert rel_err(a, b) <= 1e-5, (i, rel_err(a, b))
+    assert mg.c3_digest_max_rel(Lg, gg, GOLD) <= 1e-5
+    assert mg.c3_digest_max_rel(Lr, gr, GOLD) <= 1e-6      # the oracle reproduces its own frozen digest
+
+
 def test_c3_full_size_shard_additivity(cuda_provider, use_provider):
     """full batch 8192: the loss is a sum over rows, so gradients of two half-batches add up to the
     gradient of the whole batch (the property the multi-GPU sharding relies on)."""
@@ -87,6 +121,24 @@ def test_c4_jacobian_rows(oracle_provider, cuda_provider, use_provider):
     W1, b1, W2, b2, x = wl.jacobian_inputs(96)
     J96 = wl.jacobian_rows(wl.to_DM(W1), wl.to_DV(b1), wl.to_DM(W2), wl.to_DV(b2), wl.to_DV(x), 16, 32).ToArray()
     assert rel_err(J96, GOLD["c4_rows"]) <= 1e-12
+
+
+def test_c4_full_size_sampled_rows_against_the_oracle(oracle_provider, cuda_provider, use_provider):
+    """config 4 at n = 4096 (float64): the GPU computes one rank's shard of tangent rows (512 of 4096, what a rank of the
+    8-GPU run computes); 64 of those rows, sampled, are recomputed by the CPU oracle from the same identity tangents and must
+    agree to 1e-12 — and both with the closed form."""
+    n, c0, cnt = 4096, 1024, 512
+    W1, b1, W2, b2, x = wl.jacobian_inputs(n)
+    rows = np.sort(np.random.default_rng(11).choice(cnt, 64, replace=False))
+    use_provider(cuda_provider)
+    Jg = wl.jacobian_rows(wl.to_DM(W1), wl.to_DV(b1), wl.to_DM(W2), wl.to_DV(b2), wl.to_DV(x), c0, cnt).ToArray()
+    use_provider(oracle_provider)
+    T = np.zeros((rows.size, n), np.float64)
+    T[np.arange(rows.size), c0 + rows] = 1
+    Jr = wl.jacobian_rows(wl.to_DM(W1), wl.to_DV(b1), wl.to_DM(W2), wl.to_DV(b2), wl.to_DV(x), 0, rows.size, tangent=wl.to_DM(T)).ToArray()
+    assert rel_err(Jg[rows], Jr) <= 1e-12
+    ref = wl.jacobian_closed_form(W1, b1, W2, b2, x)[c0:c0 + cnt]
+    assert rel_err(Jg, ref) <= 1e-12 and rel_err(Jr, ref[rows]) <= 1e-12
 
 
 def test_c5_hvp(oracle_provider, cuda_provider, use_provider):

@@ -19,7 +19,8 @@ from sigma.diffsharp_b200.buffers import CudaDataBuffer, NativeDataBuffer, Shape
 
 pytestmark = pytest.mark.gpu
 RTOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-12}
-EXACT = ("argmax", "argmin", "transpose", "repeat_rows", "repeat_cols", "diag", "permute")
+EXACT = ("argmax", "argmin", "transpose", "repeat_rows", "repeat_cols", "diag", "permute",
+         "reshape_copy_mrows_v", "reshape_copy_v_mrows", "reshape")
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden.npz"))
 
 
@@ -39,7 +40,7 @@ def test_every_op_against_oracle_and_goldens(cuda_provider, dtype):
             assert np.array_equal(got[k], ref[k]), k
             assert np.array_equal(got[k], GOLD[f"{name}_{k}"]), k
         else:
-            scale = 100 if k in ("solve", "inverse", "det") else 1  # conditioning of the 6x6 solve
+            scale = 100 if k in ("solve", "solve_symmetric", "inverse", "det") else 1  # conditioning of the 6x6 solve
             assert rel_err(got[k], ref[k]) <= RTOL[np.dtype(dtype)] * scale, k
             assert rel_err(got[k], GOLD[f"{name}_{k}"]) <= RTOL[np.dtype(dtype)] * scale, k
 
@@ -180,6 +181,121 @@ def test_f32_tensor_core_gemm_variants(cuda_provider, bn, pair, split, fuse, m, 
         check(lib.dsc_gemm_tune(cuda_provider.ctx.handle, -1, -1, -1, -1))
     st1 = cuda_provider.ctx.stats()
     assert st1["gemm_tcgen05"] - st0["gemm_tcgen05"] == 8     # none of the calls fell back to the CUDA-core kernel
+
+
+def _plan(m, n, k, bn=-1, pair=-1, split=-1, fuse=-1, sms=148):
+    import ctypes as C
+    out = (C.c_int32 * 20)()
+    _lib.check(_lib.lib.dsc_gemm_plan(sms, m, n, k, 1, 1, bn, pair, split, fuse, out))
+    keys = "elig bn pair workers cpt kb tm tn dp_waves dp_extra sk_units perm_s base rem dp_tiles perm_tiles kc a_f b_f".split()
+    return dict(zip(keys, list(out)))
+
+
+# (m, n, k, tune, how the partial tiles of the plan are combined) — the modes are asserted against dsc_gemm_plan below
+DEEP_K = [
+    (1024, 1024, 8192, (-1, -1, -1, -1), "workspace"),   # the weight-adjoint product of config 3 as the planner runs it
+    (1024, 784, 8192, (-1, -1, -1, -1), "workspace"),    # dW1^T shape (n = 784)
+    (1024, 1024, 8192, (128, 0, 2, 1), "cluster"),       # K ranges of a tile = the 2 CTAs of a cluster (DSM exchange), in-kernel split
+    (1024, 1024, 8192, (256, 1, 2, 0), "cluster"),       # 2 CTA pairs per cluster
+    (1024, 1024, 8192, (256, 0, -1, 0), "cluster"),      # 4 single CTAs per cluster
+    (1024, 1024, 8192, (256, 1, 1, 0), "whole"),         # one accumulation chain of 32 chunks per tile, no split
+    (2048, 1280, 8192, (-1, -1, -1, -1), "streamk"),     # a whole-tile wave + stream-K ranges over the rest
+]
+
+
+@pytest.mark.parametrize("m,n,k,tune,mode", DEEP_K)
+def test_f32_tensor_core_gemm_deep_k_same_sign(cuda_provider, m, n, k, tune, mode):
+    """K = 8192 with SAME-SIGN data — the case where a single TMEM accumulation chain was 9.1e-5 off (the tensor core's
+    fp32 accumulator truncates) and the reason K is cut into 256-element chunks: every way of combining the chunks
+    (registers only, cluster DSM exchange, workspace slots, stream-K fix-up) against OpenBLAS sgemm and float64, in the
+    layouts config 3 uses (NN for forward, TN for the weight adjoints, NT for the input adjoints)."""
+    from sigma.diffsharp_b200._lib import check, lib
+    b, o = backend(cuda_provider, np.float32), OracleBackend(np.float32)
+    pl = _plan(m, n, k, *tune)
+    assert pl["elig"] == 1 and pl["cpt"] == 32
+    got_mode = ("whole" if pl["sk_units"] == 0 or (pl["perm_s"] == 0 and pl["workers"] == pl["tm"] * pl["tn"]) else
+                "cluster" if pl["kc"] > 1 else "workspace" if pl["perm_s"] > 1 else "streamk")
+    assert got_mode == mode, pl
+    rng = np.random.default_rng(k + m + n)
+    A = rng.random((m, k)).astype(np.float32)            # all positive
+    B = rng.random((k, n)).astype(np.float32)
+    exact = A.astype(np.float64) @ B.astype(np.float64)
+    st0 = cuda_provider.ctx.stats()
+    check(lib.dsc_gemm_tune(cuda_provider.ctx.handle, *tune))
+    try:
+        for ta, tb in ((0, 0), (1, 0), (0, 1)):
+            As = np.ascontiguousarray(A.T if ta else A)
+            Bs = np.ascontiguousarray(B.T if tb else B)
+            dA, dB = b.CreateDataBuffer(As.reshape(-1)), b.CreateDataBuffer(Bs.reshape(-1))
+            got = b._out(b._f["gemm"], m * n, ta, tb, m, n, k, dA.handle, dB.handle, 0).SubData.reshape(m, n).astype(np.float64)
+            ref = o.gemm(ta, tb, m, n, k, As.reshape(-1), Bs.reshape(-1)).reshape(m, n).astype(np.float64)
+            # same-sign data: |A||B| = A B, so the bound is simply 1e-5 relative, element by element
+            assert np.all(np.abs(got - ref) <= 1e-5 * exact), (ta, tb, float((np.abs(got - ref) / exact).max()))
+            assert np.all(np.abs(got - exact) <= 1e-5 * exact), (ta, tb, float((np.abs(got - exact) / exact).max()))
+    finally:
+        check(lib.dsc_gemm_tune(cuda_provider.ctx.handle, -1, -1, -1, -1))
+    assert cuda_provider.ctx.stats()["gemm_tcgen05"] - st0["gemm_tcgen05"] == 3
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [1, 2, 17, 64, 200])
+def test_lapack_class_ops(cuda_provider, dtype, n):
+    """Solve_M_V / SolveSymmetric_M_V / Inverse_M / Det_M (Backend.fs:102-103,125-126) against LAPACK ?gesv / ?sysv / ?getri /
+    ?getrf through the oracle, beyond the 6 x 6 fixture: residual-based bounds (the problems are well conditioned by
+    construction), `None` for singular input."""
+    b, o = backend(cuda_provider, dtype), OracleBackend(dtype)
+    rng = np.random.default_rng(100 + n)
+    G = rng.standard_normal((n, n))
+    A = (G + n * np.eye(n)).astype(dtype)                                   # diagonally dominant
+    S = ((G + G.T) / 2 + np.diag(np.where(np.arange(n) % 2 == 0, n + 1.0, -(n + 1.0)))).astype(dtype)   # symmetric indefinite
+    rhs = rng.standard_normal(n).astype(dtype)
+    eps = np.finfo(dtype).eps
+    for M, name in ((A, "Solve_M_V"), (S, "SolveSymmetric_M_V")):
+        dv = ShapedDataBufferView(b.CreateDataBuffer(M.reshape(-1)), n, n)
+        hv = ShapedDataBufferView(NativeDataBuffer(M.reshape(-1)), n, n)
+        xg = getattr(b, name)(dv, b.CreateDataBuffer(rhs)).SubData.astype(np.float64)
+        xr = getattr(o, name)(hv, NativeDataBuffer(rhs)).SubData.astype(np.float64)
+        cond = np.linalg.cond(M.astype(np.float64))
+        assert np.abs(xg - xr).max() <= 50 * n * eps * cond * np.abs(xr).max(), name
+        assert np.abs(M.astype(np.float64) @ xg - rhs).max() <= 50 * n * eps * (np.abs(M).astype(np.float64) @ np.abs(xg)).max(), name
+    dv, hv = ShapedDataBufferView(b.CreateDataBuffer(A.reshape(-1)), n, n), ShapedDataBufferView(NativeDataBuffer(A.reshape(-1)), n, n)
+    Ig, Ir = b.Inverse_M(dv).to_numpy().astype(np.float64), o.Inverse_M(hv).to_numpy().astype(np.float64)
+    assert np.abs(Ig - Ir).max() <= 50 * n * eps * np.linalg.cond(A.astype(np.float64)) * np.abs(Ir).max()
+    dg, dr = float(b.Det_M(dv)), float(o.Det_M(hv))
+    assert abs(dg - dr) <= 50 * n * eps * abs(dr)
+    if n > 1:
+        Z = A.copy(); Z[-1] = Z[0]                                            # two equal rows: singular
+        zv = ShapedDataBufferView(b.CreateDataBuffer(Z.reshape(-1)), n, n)
+        assert b.Solve_M_V(zv, b.CreateDataBuffer(rhs)) is None or dtype == np.float32   # exact zero pivot in float64; float32 may round
+        assert abs(float(b.Det_M(zv))) <= 1e3 * n * eps * abs(dr)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_custom_op_through_the_ad_layer(cuda_provider, oracle_provider, use_provider, dtype):
+    """DNDArray.CustomOp (AD.Float32.fs:1758-1763) and its adjoint Custom_DM (:4282): the consumer hook is forwarded with the
+    backend, the primal / adjoint buffers and the opaque payload, in primal, forward and reverse mode; the same program on
+    the CUDA backend and on the oracle, and against the same function written with native operators."""
+    from sigma.diffsharp_b200 import ad, workloads as wl
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((9, 7)).astype(dtype)
+    W = rng.standard_normal((7, 5)).astype(dtype)
+    op = mg.ScaledSquare(0.75)
+    res = {}
+    for name, prov in (("cuda", cuda_provider), ("oracle", oracle_provider)):
+        use_provider(prov)
+        dX, dW = wl.to_DM(X), wl.to_DM(W)
+        f_custom = lambda w: (dX * w).CustomOp(op).Sum()                              # noqa: E731
+        f_native = lambda w: (ad.had(dX * w, dX * w) * ad.DNumber(0.75, dtype)).Sum()  # noqa: E731
+        p1, g1 = ad.grad_(f_custom, dW)
+        p2, g2 = ad.grad_(f_native, dW)
+        pf, tf = ad.jacobianv_(lambda w: (dX * w).CustomOp(op), dW, wl.to_DM(np.ones_like(W)))
+        res[name] = (float(p1), g1.ToArray(), float(p2), g2.ToArray(), pf.ToArray(), tf.ToArray())
+    tol = RTOL[np.dtype(dtype)]
+    c, r = res["cuda"], res["oracle"]
+    assert abs(c[0] - r[0]) <= tol * abs(r[0]) and abs(c[0] - c[2]) <= 10 * tol * abs(c[2])
+    assert rel_err(c[1], r[1]) <= tol and rel_err(c[1], c[3]) <= 10 * tol
+    assert rel_err(c[4], r[4]) <= tol and rel_err(c[5], r[5]) <= tol
+    assert rel_err(c[4], 0.75 * (X.astype(np.float64) @ W.astype(np.float64)) ** 2) <= 10 * tol
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])

@@ -121,3 +121,11 @@ def test_config_goldens_reproduce(oracle_provider, use_provider):
     for k, v in g.items():
         tol = 5e-5 if k.startswith("c1") else 1e-12
         np.testing.assert_allclose(v, GOLD[k], rtol=tol, atol=tol * np.abs(GOLD[k]).max(), err_msg=k)
+
+
+def test_oracle_reproduces_the_c3_full_size_digest(oracle_provider, use_provider):
+    """config 3 at the size the metric is quoted on (batch 8192): the oracle reproduces the committed 1-GPU digest that
+    bench.py and the GPU tests compare the (all-reduced) adjoints with."""
+    use_provider(oracle_provider)
+    loss, grads = mg.c3_full_step()
+    assert mg.c3_digest_max_rel(loss, grads, GOLD) <= 1e-6
