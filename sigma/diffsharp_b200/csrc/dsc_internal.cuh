@@ -21,30 +21,88 @@ constexpr uint32_t kCtxMagic = 0xD5CC7801u;
 constexpr int kNumTickets = 4096;
 
 struct Ctx;
+struct LazyNode;
 
 // One device allocation handed out by the pool; shared by a buffer and the views taken from it.
 struct Block {
     void* ptr = nullptr;
     size_t bytes = 0;   // rounded (pool bin) size
-    int refs = 0;
+    int refs = 0;       // buffers (views, copy-on-write aliases) and pending deferred operations that hold the block
     Ctx* ctx = nullptr;
     int arena = 0;      // 0 = main pool; >0 = id of the CUDA-graph private pool it belongs to
-    bool has_views = false;   // a true view (dsc_buf_view: shared MUTABLE storage) exists or existed
-    bool cow_shared = false;  // copy-on-write aliases (dsc_buf_share) exist or existed
+    int views = 0;      // live TRUE views (dsc_buf_view: shared MUTABLE storage) besides the owner
+    int cow = 0;        // live holders that must never observe a write through another holder: copy-on-write aliases
+                        // (dsc_buf_share, results shared by several handles) — a writer detaches while cow > 0
+    std::vector<LazyNode*> readers;   // deferred operations that will read this block: run before any in-place write
+    // Operand-split companion of a float32 block (3xTF32 GEMM): lo = rna_tf32(x - trunc_tf32(x)) element by element, same
+    // layout.  Written by the kernel that produced the block (bias+activation, adjoint chains, GEMM epilogues) or by the
+    // split kernel on first use; valid for elements [lo_begin, lo_end) while lo_epoch == ctx->cache_epoch and nobody has
+    // written the block in place since.
+    Block* lo = nullptr;
+    uint64_t lo_epoch = 0;
+    size_t lo_begin = 0, lo_end = 0;
+    uint64_t last_other_stream_use = 0;   // ctx->other_stream_seq of the last copy / collective queued OFF the compute stream
 };
 
-// Device twin of ISigmaDiffDataBuffer<'T> (reference Util.fs:133-141): a window over a Block.
+// Device twin of ISigmaDiffDataBuffer<'T> (reference Util.fs:133-141): a window over a Block, or a value whose
+// computation is deferred (`lazy`, see LazyNode) until a consumer that cannot fuse with it needs the bytes.
 struct Buf {
     uint32_t magic = kBufMagic;
     int dtype = DSC_F32;
     Ctx* ctx = nullptr;
-    Block* block = nullptr;  // null iff len == 0
+    Block* block = nullptr;  // null iff len == 0 or the value is still deferred
     size_t off = 0;          // window start, in elements from block->ptr
     int32_t len = 0;
+    LazyNode* lazy = nullptr;   // non-null: deferred value (block == nullptr)
+    bool is_view = false;       // created by dsc_buf_view
+    bool is_cow = false;        // counted in block->cow
     template <typename T>
     T* ptr() const {
         return block ? reinterpret_cast<T*>(block->ptr) + off : nullptr;
     }
+};
+
+// ---- deferred evaluation behind the unchanged Backend<'T> call sequence ----------------------------------------
+// A call whose result may fuse with the call(s) that follow returns a buffer handle whose value is a LazyNode.  Consumers that
+// recognise a pattern take the node's OPERANDS and launch one fused kernel; every other consumer materialises the node with
+// the same kernel(s) the eager sequence would have run, so results are bit-identical either way (tests).  Nodes are reference
+// counted: handles and other nodes hold them; a node holds its operands (blocks or nodes).
+enum LazyKind {
+    LZ_ZERO = 1,   // n zeros                        CreateDataBuffer(CreateZeroArray n)           AD.Float32.fs:1834-1835,3746
+    LZ_FILL,       // n copies of s                  CreateDataBuffer(CreateValueArray(n, s))      :3430 (Sum_DM adjoint)
+    LZ_T,          // transpose of src (m x n)       Transpose_M                                    :4127-4143
+    LZ_ROWS,       // m copies of vector src         RepeatReshapeCopy_V_MRows                      :1860-1865
+    LZ_ADD_ROWS,   // src0 (m x n) + rows(src1)      Add_M_M(A, RepeatReshapeCopy_V_MRows(m, v))    :2357
+    LZ_MAP,        // f_op(src0)                     Map_F_V / Map_F_M (Cosh, Sign: heads of adjoint chains)
+    LZ_SECH,       // 1 / cosh(src0)                 Map_F_S(1, Div, Map(Cosh, x))                  :4238
+    LZ_HAD,        // src0 .* src1                   Mul_Had_M_M / Map2(Mul)                        :4240,4280-4281
+    LZ_SCALAR,     // scalar broadcast op(kind, s, src0)   Add_S / Sub_S / Mul_S                    :4280-4281
+    LZ_GEMM,       // op(src0) op(src1) [+ src2 rows]      Mul_M_M                                  :2382
+};
+
+struct Operand {          // an input of a deferred operation: a device window, or another deferred value
+    Block* block = nullptr;
+    size_t off = 0;
+    int32_t len = 0;
+    LazyNode* node = nullptr;
+    bool same(const Operand& o) const { return node ? node == o.node : (o.node == nullptr && block == o.block && off == o.off && len == o.len); }
+};
+
+struct LazyNode {
+    int refs = 0;
+    int kind = 0;
+    int dtype = DSC_F32;
+    Ctx* ctx = nullptr;
+    int32_t len = 0;
+    int op = 0;                 // MapOp / dsc_scalar_kind
+    double s = 0.0;             // scalar parameter
+    int m = 0, n = 0, k = 0, ta = 0, tb = 0;
+    Operand src[3];
+    int nsrc = 0;
+    Block* result = nullptr;    // set once materialised (the node holds one reference)
+    size_t result_off = 0;
+    bool consumed = false;      // some consumer has taken this value (or its operands, fused): not flushed at sync points
+    int pending_idx = -1;       // position in ctx->pending, -1 when not listed
 };
 
 struct Graph {
@@ -109,6 +167,13 @@ struct Ctx {
     dsc_stats stats{};
     int sm_count = kNumSMs;
     size_t smem_optin = 0;
+    // deferred evaluation
+    bool fuse = true;                    // !DSC_FLAG_NO_FUSE
+    std::vector<LazyNode*> pending;      // deferred COMPUTE nodes nobody has consumed yet: run at the next synchronisation point
+    uint64_t cache_epoch = 1;            // operand-split companions older than this are stale (bumped at graph begin / end)
+    uint64_t other_stream_seq = 0;       // counts copies / collectives queued off the compute stream (see Block::last_other_stream_use)
+    uint64_t other_stream_joined = 0;    // value of other_stream_seq the compute stream is known to be ordered after
+    bool nvtx = false;                   // DSC_FLAG_NVTX: one NVTX range per C-ABI entry
 };
 
 // ---- error plumbing -----------------------------------------------------------------------
@@ -169,10 +234,30 @@ void block_release(Block* blk);
 int buf_new(Ctx* ctx, int dtype, int32_t n, Buf** out);
 // Resolve an "out" parameter: allocate when *out == 0, otherwise validate dtype/length.
 int out_buf(Ctx* ctx, int dtype, int32_t n, dsc_buf_t* out, Buf** res);
-// Validate an input handle of the given dtype (zero-length buffers are valid).
+// Validate an input handle of the given dtype (zero-length buffers are valid) and MATERIALISE a deferred value.
 int in_buf(Ctx* ctx, int dtype, dsc_buf_t h, Buf** res, const char* what);
-// Copy-on-write: before writing through `b`, give it a private block if its block has CoW aliases.
+// The same without materialising: the caller inspects b->lazy (fusing consumers).
+int in_buf_peek(Ctx* ctx, int dtype, dsc_buf_t h, Buf** res, const char* what);
+// Before writing through `b` in place: materialise it, run the deferred operations that still read its block, give it a
+// private block if copy-on-write aliases exist, and drop the operand-split companion.
 int buf_writable(Ctx* ctx, Buf* b);
+// ---- deferred evaluation (dsc_lazy.cu) ----
+LazyNode* lazy_new(Ctx* ctx, int kind, int dtype, int32_t len);
+void lazy_set_operand(LazyNode* nd, int i, Buf* b);          // operand i := the value of b (its block window, or its node)
+void lazy_set_operand(LazyNode* nd, int i, const Operand& o);
+void lazy_unref(LazyNode* nd);
+int lazy_buf(Ctx* ctx, LazyNode* nd, dsc_buf_t* out);          // new handle whose value is nd (takes over the caller's reference)
+int lazy_materialize(LazyNode* nd);                            // compute nd->result (idempotent)
+int buf_resolve(Buf* b);                                       // make b a plain device window
+int operand_resolve(Ctx* ctx, Operand& o);                     // make o a plain device window (materialises its node)
+int flush_pending(Ctx* ctx);                                   // run every deferred compute node nobody has consumed
+inline LazyNode* lazy_of(const Buf* b) { return (b && !b->block) ? b->lazy : nullptr; }
+inline LazyNode* lazy_of(const Buf* b, int kind) { LazyNode* n = lazy_of(b); return (n && n->kind == kind && !n->result) ? n : nullptr; }
+void buf_adopt(Buf* b, Block* blk, size_t off, bool cow);      // b := window over blk (takes a new reference)
+int buf_share_into(Buf* dst, Buf* src);                        // dst := copy-on-write alias of src's value (dst must hold nothing)
+// the compute stream is about to reuse / the host is about to free memory last touched off the compute stream
+int join_other_streams(Ctx* ctx);
+inline void note_other_stream_use(Ctx* ctx, Block* b) { if (b) b->last_other_stream_use = ++ctx->other_stream_seq; }
 int ensure_red_scratch(Ctx* ctx, size_t bytes);
 int ensure_gemm_ws(Ctx* ctx, size_t bytes);
 int ensure_gemm_tickets(Ctx* ctx, size_t count);
@@ -183,6 +268,24 @@ inline int grid_for(size_t work_items, int per_block, int max_blocks) {
     if (b > (size_t)max_blocks) b = max_blocks;
     return (int)b;
 }
+
+// ---- raw executors: kernels on device pointers, no handle logic (used by the entry points and by the deferred-evaluation
+// engine; each is explicitly instantiated for float and double in the translation unit that owns the kernel) -------------
+template <typename T> int ew_map(Ctx*, int op, const T* x, T* y, size_t n);                       // dsc_elementwise.cu
+template <typename T> int ew_map_s(Ctx*, int op, T s, const T* x, T* y, size_t n);
+template <typename T> int ew_map2(Ctx*, int op, const T* a, const T* b, T* y, size_t n);
+template <typename T> int ew_scalar(Ctx*, int kind, T s, const T* x, T* y, size_t n);
+template <typename T> int ew_neg(Ctx*, const T* x, T* y, size_t n);
+template <typename T> int ew_sech(Ctx*, const T* x, T* y, size_t n);                              // 1 / cosh(x), the two roundings of the unfused pair
+// y = chain(dA, p) (dsc_fused_kind); y_lo (float32 only, may be null): the operand-split companion of y, written in the same pass
+template <typename T> int ew_fused_bwd(Ctx*, int kind, const T* dA, const T* p, T* y, T* y_lo, size_t n);
+// z[i,j] = A[i,j] (bop) v[j] with bop in {ADD, SUB, MUL, DIV}; if act >= 0 additionally h = f_act(z) (and h_lo, float32 only)
+template <typename T> int ew_rows(Ctx*, int bop, int act, int m, int n, const T* A, const T* v, T* z, T* h, T* h_lo);
+template <typename T> int transpose_launch(Ctx* ctx, const T* A, T* B, int m, int n);             // dsc_layout.cu
+template <typename T> int repeat_rows_launch(Ctx* ctx, const T* v, T* out, int m, int n);
+int fill_raw(Ctx* ctx, int dtype, void* base, size_t n, double v);                                // dsc_core.cu
+// lo[i] = rna_tf32(x[i] - trunc_tf32(x[i]))  (dsc_gemm_tf32x3.cu)
+int split_lo_launch(Ctx* ctx, const float* x, float* lo, size_t n);
 
 // ---- typed implementations (one template per op, instantiated for float and double) -------
 template <typename T> int gemm_impl(Ctx*, int ta, int tb, int m, int n, int k, Buf* A, Buf* B, Buf* bias, Buf* C);

@@ -246,8 +246,8 @@ def test_lapack_class_ops(cuda_provider, dtype, n):
     b, o = backend(cuda_provider, dtype), OracleBackend(dtype)
     rng = np.random.default_rng(100 + n)
     G = rng.standard_normal((n, n))
-    A = (G + n * np.eye(n)).astype(dtype)                                   # diagonally dominant
-    S = ((G + G.T) / 2 + np.diag(np.where(np.arange(n) % 2 == 0, n + 1.0, -(n + 1.0)))).astype(dtype)   # symmetric indefinite
+    A = (G / n + np.eye(n)).astype(dtype)                                   # well conditioned, |det| = O(1)
+    S = ((G + G.T) / (2 * n) + np.diag(np.where(np.arange(n) % 2 == 0, 1.5, -1.5))).astype(dtype)   # symmetric INDEFINITE
     rhs = rng.standard_normal(n).astype(dtype)
     eps = np.finfo(dtype).eps
     for M, name in ((A, "Solve_M_V"), (S, "SolveSymmetric_M_V")):

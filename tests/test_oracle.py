@@ -128,4 +128,4 @@ def test_oracle_reproduces_the_c3_full_size_digest(oracle_provider, use_provider
     bench.py and the GPU tests compare the (all-reduced) adjoints with."""
     use_provider(oracle_provider)
     loss, grads = mg.c3_full_step()
-    assert mg.c3_digest_max_rel(loss, grads, GOLD) <= 1e-6
+    assert mg.c3_digest_max_rel(loss, grads, GOLD) <= 1e-5 and loss == float(GOLD["c3_loss"][0])
