@@ -207,8 +207,9 @@ def op_sweep(provider, peaks, n=4096):
     from sigma.diffsharp_b200.buffers import ShapedDataBufferView
     out = {"method": "12 launches per CUDA graph rotating over 4 input sets (footprint > L2); device time / 12"}
     ctx = provider.ctx
+    ctx.set_fuse(False)
     for dtype, name in ((np.float32, "f32"), (np.float64, "f64")):
-        b = CudaBackend(dtype, ctx=ctx, fuse=False)
+        b = CudaBackend(dtype, ctx=ctx)   # the sweep runs with deferred evaluation off (set below): one kernel per call
         es = np.dtype(dtype).itemsize
         rng = np.random.default_rng(2)
         host = (rng.random(n * n) * 2 - 1).astype(dtype)
@@ -239,6 +240,7 @@ def op_sweep(provider, peaks, n=4096):
         if dtype == np.float32:
             out[f"Mul_M_M_{name}"]["frac_of_cublas_tf32_over_3"] = round(tf / (peaks["tf32_tflops"] / 3.0), 3)
         del As, Bs
+    ctx.set_fuse(True)
     return out
 
 
@@ -545,7 +547,8 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel: the f32 GEMM of the widest layer, as launched in the step ----
     from sigma.diffsharp_b200.backend import CudaBackend
-    rb = CudaBackend(np.float32, ctx=ctx, fuse=False)
+    rb = CudaBackend(np.float32, ctx=ctx)
+    ctx.set_fuse(False)
     rng = np.random.default_rng(0)
     Am = ShapedDataBufferView(rb.CreateDataBuffer((rng.random(rows * 1024) * 2 - 1).astype(np.float32)), rows, 1024)
     Bm = ShapedDataBufferView(rb.CreateDataBuffer((rng.random(1024 * 1024) * 2 - 1).astype(np.float32)), 1024, 1024)
@@ -564,6 +567,7 @@ def run_ours(args):
                            f"algorithmic bytes A + B + C = {(rows * 1024 + 1024 * 1024 + rows * 1024) * 4}")
     except Exception:
         pass
+    ctx.set_fuse(True)
     st = ctx.stats()
     roofline = {"bound": "tensor", "achieved": round(achieved, 2), "peak": round(peak3, 2), "unit": "TFLOP/s",
                 "frac": round(achieved / peak3, 4), "traffic": traffic, "traffic_source": traffic_src,

@@ -19,7 +19,7 @@ import sysconfig
 
 import numpy as np
 
-from sigma.diffsharp_b200.backend import Backend, ConstArray, MapOp  # interface types only
+from sigma.diffsharp_b200.interface import Backend, ConstArray, MapOp  # interface types only: no device code is imported
 from sigma.diffsharp_b200.buffers import ISigmaDiffDataBuffer, NativeDataBuffer, ShapedDataBufferView
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

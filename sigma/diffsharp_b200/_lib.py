@@ -19,7 +19,7 @@ DSC_OK = 0
 DSC_E_INVALID, DSC_E_SHAPE, DSC_E_OOM, DSC_E_CUDA, DSC_E_NCCL = -1, -2, -3, -4, -5
 DSC_E_UNSUPPORTED_OP, DSC_E_SINGULAR, DSC_E_DTYPE = -6, -7, -8
 DSC_F32, DSC_F64 = 0, 1
-DSC_FLAG_GEMM_FP32_SIMT, DSC_FLAG_GEMM_F64_SIMT, DSC_FLAG_NO_POOL = 1, 2, 4
+DSC_FLAG_GEMM_FP32_SIMT, DSC_FLAG_GEMM_F64_SIMT, DSC_FLAG_NO_POOL, DSC_FLAG_NO_FUSE, DSC_FLAG_NVTX = 1, 2, 4, 8, 16
 
 
 class DscError(RuntimeError):
@@ -111,6 +111,9 @@ _sig("dsc_last_error", restype=C.c_char_p)
 _sig("dsc_get_stats", ctx_t, P(Stats))
 _sig("dsc_get_stream", ctx_t, P(C.c_void_p))
 _sig("dsc_trim_pool", ctx_t)
+_sig("dsc_set_fuse", ctx_t, C.c_int)
+_sig("dsc_flush", ctx_t)
+_sig("dsc_invalidate_caches", ctx_t)
 _sig("dsc_event_create", ctx_t, P(C.c_uint64))
 _sig("dsc_event_record", ctx_t, C.c_uint64)
 _sig("dsc_event_elapsed_ms", ctx_t, C.c_uint64, C.c_uint64, P(C.c_float))

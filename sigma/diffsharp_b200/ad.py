@@ -23,7 +23,7 @@ import math
 
 import numpy as np
 
-from .backend import MapOp
+from .interface import MapOp
 from .buffers import NativeDataBuffer, ShapedDataBufferView
 from .config import GlobalConfig
 

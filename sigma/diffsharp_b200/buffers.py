@@ -4,19 +4,14 @@ Mirrors (same names, same members) the reference's
   * ``ISigmaDiffDataBuffer<'T>``   src/DiffSharp/Util.fs:133-141
   * ``NativeDataBuffer<'T>``       src/DiffSharp/Util.fs:147-165   (host array)
   * ``ShapedDataBufferView<'T>``   src/DiffSharp/Util.fs:167-215   (buffer + int64[] shape, row-major)
-and adds ``CudaDataBuffer``: the device-resident implementation whose storage lives in HBM behind
-a ``dsc_buf_t`` handle of libdiffsharp_cuda.so.  ``Data``/``SubData`` are lazy downloads; nothing on
-the AD path touches them, so reverse sweeps never round-trip through host memory.
+The device-resident implementation, ``CudaDataBuffer`` (storage in HBM behind a ``dsc_buf_t`` handle of
+libdiffsharp_cuda.so), and ``CudaContext`` live in device.py; they are reachable from here by name
+(``from .buffers import CudaDataBuffer``) but importing THIS module never loads the CUDA library, so the CPU oracle and the
+reference arm of bench.py run without it.
 """
 from __future__ import annotations
 
-import ctypes as C
-import weakref
-
 import numpy as np
-
-from . import _lib
-from ._lib import check, lib
 
 
 def _np_dtype(dtype) -> np.dtype:
@@ -89,158 +84,6 @@ class NativeDataBuffer(ISigmaDiffDataBuffer):
 
     def __repr__(self):
         return f"DataBuffer-{self._length} {self.SubData!r}"
-
-
-class CudaContext:
-    """One context = one GPU = one compute stream (+ one communication stream).  Wraps dsc_ctx_t."""
-
-    def __init__(self, device: int = 0, flags: int = 0):
-        h = _lib.ctx_t()
-        check(lib.dsc_create(device, flags, C.byref(h)))
-        self.handle = h
-        self.device = device
-        self.flags = flags
-        self._finalizer = weakref.finalize(self, lib.dsc_destroy, h)
-
-    def sync(self):
-        check(lib.dsc_sync(self.handle))
-
-    def stats(self) -> dict:
-        s = _lib.Stats()
-        check(lib.dsc_get_stats(self.handle, C.byref(s)))
-        return s.as_dict()
-
-    def flush_l2(self):
-        check(lib.dsc_flush_l2(self.handle))
-
-    def trim_pool(self):
-        check(lib.dsc_trim_pool(self.handle))
-
-    # CUDA events on the context's stream
-    def event(self) -> int:
-        e = C.c_uint64()
-        check(lib.dsc_event_create(self.handle, C.byref(e)))
-        return e.value
-
-    def record(self, ev: int):
-        check(lib.dsc_event_record(self.handle, ev))
-
-    def elapsed_ms(self, a: int, b: int) -> float:
-        ms = C.c_float()
-        check(lib.dsc_event_elapsed_ms(self.handle, a, b, C.byref(ms)))
-        return ms.value
-
-    def event_destroy(self, ev: int):
-        check(lib.dsc_event_destroy(self.handle, ev))
-
-    # CUDA graphs
-    def graph_begin(self):
-        check(lib.dsc_graph_begin(self.handle))
-
-    def graph_end(self) -> int:
-        g = C.c_uint64()
-        check(lib.dsc_graph_end(self.handle, C.byref(g)))
-        return g.value
-
-    def graph_launch(self, g: int):
-        check(lib.dsc_graph_launch(self.handle, g))
-
-    def graph_destroy(self, g: int):
-        check(lib.dsc_graph_destroy(self.handle, g))
-
-    def close(self):
-        self._finalizer()
-
-
-def _free_handle(h):
-    lib.dsc_buf_free(h)
-
-
-class CudaDataBuffer(ISigmaDiffDataBuffer):
-    """Device-resident ``ISigmaDiffDataBuffer`` (SURVEY §8b ``CudaDataBuffer<'T>``).
-
-    Owns one ``dsc_buf_t``; the handle is released when the object is collected (the managed
-    twin is a SafeHandle)."""
-
-    def __init__(self, ctx: CudaContext, dtype, handle: int, length: int, offset: int = 0):
-        self.ctx = ctx
-        self.dtype = _np_dtype(dtype)
-        self.handle = handle
-        self._length = int(length)
-        self._offset = int(offset)  # offset of the window inside the underlying allocation
-        self._lazy_t = None
-        self._finalizer = weakref.finalize(self, _free_handle, handle)
-
-    # -- construction ---------------------------------------------------------------------------
-    @staticmethod
-    def _code(dtype) -> int:
-        return _lib.DSC_F32 if np.dtype(dtype) == np.float32 else _lib.DSC_F64
-
-    @classmethod
-    def empty(cls, ctx, dtype, n):
-        h = _lib.buf_t()
-        check(lib.dsc_buf_alloc(ctx.handle, cls._code(dtype), n, C.byref(h)))
-        return cls(ctx, dtype, h.value, n)
-
-    @classmethod
-    def filled(cls, ctx, dtype, n, value):
-        h = _lib.buf_t()
-        check(lib.dsc_buf_alloc_fill(ctx.handle, cls._code(dtype), n, float(value), C.byref(h)))
-        return cls(ctx, dtype, h.value, n)
-
-    @classmethod
-    def from_host(cls, ctx, array):
-        a = np.ascontiguousarray(array).reshape(-1)
-        b = cls.empty(ctx, a.dtype, a.size)
-        if a.size:
-            check(lib.dsc_buf_upload(b.handle, 0, a.ctypes.data, a.size))
-        return b
-
-    # -- ISigmaDiffDataBuffer -------------------------------------------------------------------
-    Length = property(lambda s: s._length)
-    Offset = property(lambda s: s._offset)
-
-    @property
-    def SubData(self) -> np.ndarray:
-        out = np.empty(self._length, self.dtype)
-        if self._length:
-            check(lib.dsc_buf_download(self.handle, 0, out.ctypes.data, self._length))
-        return out
-
-    @property
-    def Data(self) -> np.ndarray:
-        # The reference exposes the whole underlying array; consumers index it at Offset.  We hand
-        # back an array that is valid at [Offset, Offset+Length) (the only range the reference's own
-        # indexers touch: Util.fs:190-197).
-        out = np.zeros(self._offset + self._length, self.dtype)
-        out[self._offset:] = self.SubData
-        return out
-
-    def GetValues(self, startIndex, length):
-        h = _lib.buf_t()
-        check(lib.dsc_buf_view(self.handle, startIndex, length, C.byref(h)))
-        return CudaDataBuffer(self.ctx, self.dtype, h.value, length, self._offset + startIndex)
-
-    def GetStackedValues(self, rows, cols, rowStart, rowFinish, colStart, colFinish):
-        h = _lib.buf_t()
-        check(lib.dsc_buf_gather2d(self.handle, rows, cols, rowStart, rowFinish, colStart, colFinish, C.byref(h)))
-        return CudaDataBuffer(self.ctx, self.dtype, h.value, (rowFinish - rowStart + 1) * (colFinish - colStart + 1))
-
-    def DeepCopy(self):
-        h = _lib.buf_t()
-        check(lib.dsc_buf_copy(self.handle, C.byref(h)))
-        return CudaDataBuffer(self.ctx, self.dtype, h.value, self._length)
-
-    def ShallowCopy(self):
-        return self.GetValues(0, self._length)
-
-    def upload(self, array, offset: int = 0):
-        a = np.ascontiguousarray(array, dtype=self.dtype).reshape(-1)
-        if a.size:
-            check(lib.dsc_buf_upload(self.handle, offset, a.ctypes.data, a.size))
-
-    def __repr__(self):
-        return f"CudaDataBuffer-{self._length} ({self.dtype}, device {self.ctx.device})"
 
 
 class ShapedDataBufferView:
@@ -318,3 +161,11 @@ class ShapedDataBufferView:
 
     def __repr__(self):
         return f"ShapedDataBuffer view {self._buffer!r} as {self._shape}"
+
+
+def __getattr__(name):
+    # device types, resolved on first use (PEP 562): keeps this module free of the CUDA library
+    if name in ("CudaContext", "CudaDataBuffer"):
+        from . import device
+        return getattr(device, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

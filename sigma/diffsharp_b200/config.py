@@ -65,11 +65,15 @@ class CudaBackendProvider(DictBackendProvider):
     """One GPU context shared by a float32 and a float64 ``CudaBackend``."""
 
     def __init__(self, device: int = 0, flags: int = 0, fuse: bool = True, ctx=None):
+        """`fuse=False` creates the context with DSC_FLAG_NO_FUSE: the library launches every call's own kernel at once
+        (the deferred evaluation of csrc/dsc_lazy.cu is a property of the context, not of this shim)."""
+        from . import _lib
         from .backend import CudaBackend
-        from .buffers import CudaContext
-        self.ctx = ctx if ctx is not None else CudaContext(device, flags)
-        super().__init__(CudaBackend(np.float32, ctx=self.ctx, fuse=fuse),
-                         CudaBackend(np.float64, ctx=self.ctx, fuse=fuse))
+        from .device import CudaContext
+        if ctx is None:
+            ctx = CudaContext(device, flags | (0 if fuse else _lib.DSC_FLAG_NO_FUSE))
+        self.ctx = ctx
+        super().__init__(CudaBackend(np.float32, ctx=self.ctx), CudaBackend(np.float64, ctx=self.ctx))
 
 
 class _NullProvider(IBackendProvider):

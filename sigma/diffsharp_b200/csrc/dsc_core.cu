@@ -80,10 +80,33 @@ int pool_alloc(Ctx* ctx, size_t bytes, Block** out) {
     return DSC_OK;
 }
 
+// Copies on the copy streams and collectives on the communication stream run OFF the compute stream.  Before a block they
+// touched is written by compute-stream work, or handed back to the pool (where the next compute-stream kernel may pick it
+// up), the compute stream is ordered after those streams.  Cheap (three event records / waits, no host synchronisation) and
+// only done when such a use is actually outstanding.
+int join_other_streams(Ctx* ctx) {
+    if (ctx->other_stream_joined == ctx->other_stream_seq) return DSC_OK;
+    if (ctx->capturing) return DSC_OK;   // copy-stream transfers cannot be captured; captured collectives are joined by dsc_comm_join / graph_end
+    DSC_CUDA_CHECK(cudaEventRecord(ctx->ev_copy_b, ctx->copy_stream));
+    DSC_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_b, 0));
+    DSC_CUDA_CHECK(cudaEventRecord(ctx->ev_copy_c, ctx->copy_stream_down));
+    DSC_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_c, 0));
+    DSC_CUDA_CHECK(cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
+    DSC_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
+    ctx->comm_pending = false;
+    ctx->other_stream_joined = ctx->other_stream_seq;
+    return DSC_OK;
+}
+
 void block_release(Block* blk) {
     if (!blk) return;
     if (--blk->refs > 0) return;
     Ctx* ctx = blk->ctx;
+    if (blk->lo) {
+        block_release(blk->lo);
+        blk->lo = nullptr;
+    }
+    if (blk->last_other_stream_use > ctx->other_stream_joined) join_other_streams(ctx);
     if (blk->arena == 0) {
         ctx->pool.in_use -= blk->bytes;
         if (ctx->flags & DSC_FLAG_NO_POOL) {
@@ -126,19 +149,66 @@ int buf_new(Ctx* ctx, int dtype, int32_t n, Buf** out) {
     return DSC_OK;
 }
 
-int buf_writable(Ctx* ctx, Buf* b) {
+int buf_writable(Ctx* ctx, Buf* b, bool on_compute_stream) {
+    DSC_TRY(buf_resolve(b));
     Block* old = b->block;
-    if (!old || !old->cow_shared || old->refs <= 1) return DSC_OK;
-    Block* nb = nullptr;
-    const size_t es = dtype_size(b->dtype);
-    DSC_TRY(pool_alloc(ctx, (size_t)b->len * es, &nb));
-    cudaError_t e = cudaMemcpyAsync(nb->ptr, reinterpret_cast<const char*>(old->ptr) + b->off * es, (size_t)b->len * es,
-                                    cudaMemcpyDeviceToDevice, ctx->stream);
-    if (e != cudaSuccess) {
-        block_release(nb);
-        return fail(DSC_E_CUDA, "copy-on-write copy failed: %s", cudaGetErrorString(e));
+    if (!old) return DSC_OK;
+    // deferred operations that still have to read this block see the value it has NOW
+    while (!old->readers.empty()) {
+        LazyNode* nd = old->readers.back();
+        nd->refs++;
+        int s = lazy_materialize(nd);   // releases its operands: removes itself from old->readers
+        if (s == DSC_OK && !old->readers.empty() && old->readers.back() == nd) s = fail(DSC_E_INVALID, "deferred reader did not release its operand");
+        lazy_unref(nd);
+        if (s != DSC_OK) return s;
     }
-    ctx->stats.kernel_launches++;
+    // a write issued on the compute stream must come after copies / collectives that touch the block on the other streams
+    // (a write issued on a copy stream is ordered by that stream and by the caller's events)
+    if (on_compute_stream && old->last_other_stream_use > ctx->other_stream_joined) DSC_TRY(join_other_streams(ctx));
+    if (old->cow > 0 && old->refs > 1) {
+        // copy-on-write: other handles (or deferred results) hold this block and must keep seeing the old value
+        Block* nb = nullptr;
+        const size_t es = dtype_size(b->dtype);
+        DSC_TRY(pool_alloc(ctx, (size_t)b->len * es, &nb));
+        cudaError_t e = cudaMemcpyAsync(nb->ptr, reinterpret_cast<const char*>(old->ptr) + b->off * es, (size_t)b->len * es,
+                                        cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e != cudaSuccess) {
+            block_release(nb);
+            return fail(DSC_E_CUDA, "copy-on-write copy failed: %s", cudaGetErrorString(e));
+        }
+        ctx->stats.kernel_launches++;
+        if (b->is_cow) old->cow--;
+        b->is_cow = false;
+        block_release(old);
+        b->block = nb;
+        b->off = 0;
+        return DSC_OK;
+    }
+    if (b->is_cow && old->refs == 1) {   // the last holder owns the block outright
+        b->is_cow = false;
+        old->cow--;
+    }
+    old->lo_epoch = 0;   // the operand-split companion no longer matches
+    return DSC_OK;
+}
+
+// b is about to be overwritten completely: like buf_writable, but a deferred value is dropped instead of computed and a
+// shared block is left to the other holders instead of copied.
+static int buf_overwritable(Ctx* ctx, Buf* b) {
+    if (b->len == 0) return DSC_OK;
+    if (!b->block) {
+        if (b->lazy) {
+            lazy_unref(b->lazy);
+            b->lazy = nullptr;
+        }
+        return pool_alloc(ctx, (size_t)b->len * dtype_size(b->dtype), &b->block);
+    }
+    Block* old = b->block;
+    if (b->is_view || old->views > 0 || !(old->cow > 0 && old->refs > 1)) return buf_writable(ctx, b);   // shared mutable storage, or sole holder
+    Block* nb = nullptr;
+    DSC_TRY(pool_alloc(ctx, (size_t)b->len * dtype_size(b->dtype), &nb));
+    if (b->is_cow) old->cow--;
+    b->is_cow = false;
     block_release(old);
     b->block = nb;
     b->off = 0;
@@ -159,18 +229,23 @@ int out_buf(Ctx* ctx, int dtype, int32_t n, dsc_buf_t* out, Buf** res) {
     if (b->ctx != ctx) return fail(DSC_E_INVALID, "output buffer belongs to another context");
     if (b->dtype != dtype) return fail(DSC_E_DTYPE, "output buffer has the wrong dtype");
     if (b->len != n) return fail(DSC_E_SHAPE, "output buffer has length %d, expected %d", b->len, n);
-    DSC_TRY(buf_writable(ctx, b));
+    DSC_TRY(buf_overwritable(ctx, b));
     *res = b;
     return DSC_OK;
 }
 
-int in_buf(Ctx* ctx, int dtype, dsc_buf_t h, Buf** res, const char* what) {
+int in_buf_peek(Ctx* ctx, int dtype, dsc_buf_t h, Buf** res, const char* what) {
     Buf* b = as_buf(h);
     if (!b) return fail(DSC_E_INVALID, "%s is not a live buffer handle", what);
     if (b->ctx != ctx) return fail(DSC_E_INVALID, "%s belongs to another context", what);
     if (b->dtype != dtype) return fail(DSC_E_DTYPE, "%s has the wrong dtype", what);
     *res = b;
     return DSC_OK;
+}
+
+int in_buf(Ctx* ctx, int dtype, dsc_buf_t h, Buf** res, const char* what) {
+    DSC_TRY(in_buf_peek(ctx, dtype, h, res, what));
+    return buf_resolve(*res);
 }
 
 int ensure_red_scratch(Ctx* ctx, size_t bytes) {
@@ -227,22 +302,26 @@ __global__ void fill_kernel(T* __restrict__ p, size_t n, T v) {
     for (; i < n; i += stride) p[i] = v;
 }
 
-static int fill_window(Ctx* ctx, Buf* b, int32_t off, int32_t n, double v) {
+int fill_raw(Ctx* ctx, int dtype, void* base, size_t n, double v) {
     if (n == 0) return DSC_OK;
-    size_t es = dtype_size(b->dtype);
-    char* base = reinterpret_cast<char*>(b->block->ptr) + (b->off + off) * es;
-    if (v == 0.0) {
-        DSC_CUDA_CHECK(cudaMemsetAsync(base, 0, (size_t)n * es, ctx->stream));
+    if (v == 0.0 && !signbit(v)) {
+        DSC_CUDA_CHECK(cudaMemsetAsync(base, 0, n * dtype_size(dtype), ctx->stream));
         ctx->stats.kernel_launches++;
         return DSC_OK;
     }
     int grid = grid_for(n, 256 * 8, ctx->sm_count * 8);
-    if (b->dtype == DSC_F32)
+    if (dtype == DSC_F32)
         fill_kernel<float><<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<float*>(base), n, (float)v);
     else
         fill_kernel<double><<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<double*>(base), n, v);
     DSC_LAUNCH_CHECK(ctx);
     return DSC_OK;
+}
+
+static int fill_window(Ctx* ctx, Buf* b, int32_t off, int32_t n, double v) {
+    if (n == 0) return DSC_OK;
+    size_t es = dtype_size(b->dtype);
+    return fill_raw(ctx, b->dtype, reinterpret_cast<char*>(b->block->ptr) + (b->off + off) * es, (size_t)n, v);
 }
 
 // strided 2-D gather used by GetStackedValues (Util.fs:204-210)
@@ -303,6 +382,12 @@ int dsc_create(int device, uint32_t flags, dsc_ctx_t* out) {
     ctx->flags = flags;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    {
+        const char* e = getenv("DSC_FUSE");   // DSC_FUSE=0: same as DSC_FLAG_NO_FUSE (debugging)
+        ctx->fuse = !(flags & DSC_FLAG_NO_FUSE) && !(e && *e == '0');
+        const char* v = getenv("DSC_NVTX");
+        ctx->nvtx = (flags & DSC_FLAG_NVTX) || (v && *v == '1');
+    }
     DSC_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     DSC_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
     DSC_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -361,6 +446,7 @@ int dsc_sync(dsc_ctx_t c) {
     if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
     Ctx* ctx = as_ctx(c);
     if (ctx->capturing) return fail(DSC_E_INVALID, "dsc_sync while capturing a graph");
+    DSC_TRY(flush_pending(ctx));
     DSC_TRY(dsc_comm_join(c));
     DSC_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     return DSC_OK;
@@ -406,6 +492,7 @@ int dsc_event_create(dsc_ctx_t c, dsc_event_t* ev) {
 }
 int dsc_event_record(dsc_ctx_t c, dsc_event_t ev) {
     if (!ctx_ok(c) || !ev) return fail(DSC_E_INVALID, "bad context or event");
+    DSC_TRY(flush_pending(as_ctx(c)));   // what the caller issued so far runs before the event
     DSC_CUDA_CHECK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev), as_ctx(c)->stream));
     return DSC_OK;
 }
@@ -461,9 +548,12 @@ int dsc_graph_begin(dsc_ctx_t c) {
     if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
     Ctx* ctx = as_ctx(c);
     if (ctx->capturing) return fail(DSC_E_INVALID, "already capturing");
+    DSC_TRY(flush_pending(ctx));
+    DSC_TRY(join_other_streams(ctx));
     DSC_TRY(dsc_comm_join(c));
     DSC_CUDA_CHECK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
     ctx->capturing = true;
+    ctx->cache_epoch++;   // operand-split companions computed before the capture are not trusted inside it: a replay must recompute what depends on replaced inputs
     ctx->cur_arena = ctx->next_arena++;
     ctx->arena_pool = Pool();
     ctx->arena_blocks.clear();
@@ -474,6 +564,18 @@ int dsc_graph_end(dsc_ctx_t c, dsc_graph_t* out) {
     if (!ctx_ok(c) || !out) return fail(DSC_E_INVALID, "bad context or null graph pointer");
     Ctx* ctx = as_ctx(c);
     if (!ctx->capturing) return fail(DSC_E_INVALID, "not capturing");
+    {
+        int fs = flush_pending(ctx);   // deferred work issued inside the capture belongs to the graph
+        if (fs != DSC_OK) {
+            cudaGraph_t dead = nullptr;
+            cudaStreamEndCapture(ctx->stream, &dead);
+            if (dead) cudaGraphDestroy(dead);
+            cudaGetLastError();
+            ctx->capturing = false;
+            return fs;
+        }
+    }
+    ctx->cache_epoch++;   // ... and companions computed inside it describe the capture-time values only
     if (ctx->comm_pending) {
         // join the communication stream back into the origin stream before ending the capture
         cudaEventRecord(ctx->ev_comm, ctx->comm_stream);
@@ -558,6 +660,14 @@ int dsc_buf_alloc(dsc_ctx_t c, int dtype, int32_t n, dsc_buf_t* out) {
 }
 
 int dsc_buf_alloc_fill(dsc_ctx_t c, int dtype, int32_t n, double v, dsc_buf_t* out) {
+    if (ctx_ok(c) && out && as_ctx(c)->fuse && n > 0 && (dtype == DSC_F32 || dtype == DSC_F64) && v == v) {
+        // two zero adjoints per tape node (AD.Float32.fs:1834-1835,3746) and the all-ones seed of Sum_DM's adjoint (:3430):
+        // nothing is allocated or written until somebody needs the bytes
+        const bool zero = v == 0.0 && !signbit(v);
+        LazyNode* nd = lazy_new(as_ctx(c), zero ? LZ_ZERO : LZ_FILL, dtype, n);
+        nd->s = v;
+        return lazy_buf(as_ctx(c), nd, out);
+    }
     DSC_TRY(dsc_buf_alloc(c, dtype, n, out));
     Buf* b = as_buf(*out);
     int s = fill_window(as_ctx(c), b, 0, n, v);
@@ -572,6 +682,11 @@ int dsc_buf_free(dsc_buf_t h) {
     if (h == 0) return DSC_OK;
     Buf* b = as_buf(h);
     if (!b) return fail(DSC_E_INVALID, "dsc_buf_free: not a live buffer handle");
+    if (b->lazy) lazy_unref(b->lazy);
+    if (b->block) {
+        if (b->is_cow) b->block->cow--;
+        if (b->is_view) b->block->views--;
+    }
     block_release(b->block);
     b->magic = 0;
     delete b;
@@ -623,6 +738,7 @@ int dsc_buf_download(dsc_buf_t h, int32_t off, void* host, int32_t n) {
     if (!host) return fail(DSC_E_INVALID, "download: null host pointer");
     Ctx* ctx = b->ctx;
     if (ctx->capturing) return fail(DSC_E_INVALID, "synchronous download while capturing a graph");
+    DSC_TRY(buf_resolve(b));
     DSC_TRY(dsc_comm_join(reinterpret_cast<dsc_ctx_t>(ctx)));
     size_t es = dtype_size(b->dtype);
     const char* src = reinterpret_cast<const char*>(b->block->ptr) + (b->off + off) * es;
@@ -639,6 +755,7 @@ int dsc_buf_download_async(dsc_buf_t h, int32_t off, void* host, int32_t n) {
     if (n == 0) return DSC_OK;
     if (!host) return fail(DSC_E_INVALID, "download_async: null host pointer");
     Ctx* ctx = b->ctx;
+    DSC_TRY(buf_resolve(b));
     size_t es = dtype_size(b->dtype);
     const char* src = reinterpret_cast<const char*>(b->block->ptr) + (b->off + off) * es;
     DSC_CUDA_CHECK(cudaMemcpyAsync(host, src, (size_t)n * es, cudaMemcpyDeviceToHost, ctx->stream));
@@ -654,9 +771,11 @@ int dsc_copy_upload(dsc_buf_t h, int32_t off, const void* host, int32_t n) {
     if (!host) return fail(DSC_E_INVALID, "copy_upload: null host pointer");
     Ctx* ctx = b->ctx;
     if (ctx->capturing) return fail(DSC_E_INVALID, "copy-stream transfers cannot be captured");
+    DSC_TRY(buf_writable(ctx, b, false));   // deferred readers run first, copy-on-write aliases keep the old value, the split companion is dropped
     size_t es = dtype_size(b->dtype);
     char* dst = reinterpret_cast<char*>(b->block->ptr) + (b->off + off) * es;
     DSC_CUDA_CHECK(cudaMemcpyAsync(dst, host, (size_t)n * es, cudaMemcpyHostToDevice, ctx->copy_stream));
+    note_other_stream_use(ctx, b->block);
     ctx->stats.memcpy_h2d_bytes += (size_t)n * es;
     return DSC_OK;
 }
@@ -669,9 +788,11 @@ int dsc_copy_download(dsc_buf_t h, int32_t off, void* host, int32_t n) {
     if (!host) return fail(DSC_E_INVALID, "copy_download: null host pointer");
     Ctx* ctx = b->ctx;
     if (ctx->capturing) return fail(DSC_E_INVALID, "copy-stream transfers cannot be captured");
+    if (!b->block) return fail(DSC_E_INVALID, "copy_download: the buffer's value is still deferred (read it on the compute stream, or synchronise first)");
     size_t es = dtype_size(b->dtype);
     const char* src = reinterpret_cast<const char*>(b->block->ptr) + (b->off + off) * es;
     DSC_CUDA_CHECK(cudaMemcpyAsync(host, src, (size_t)n * es, cudaMemcpyDeviceToHost, ctx->copy_stream_down));
+    note_other_stream_use(ctx, b->block);
     ctx->stats.memcpy_d2h_bytes += (size_t)n * es;
     return DSC_OK;
 }
@@ -679,6 +800,7 @@ int dsc_copy_download(dsc_buf_t h, int32_t off, void* host, int32_t n) {
 int dsc_copy_wait_compute(dsc_ctx_t c) {
     if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
     Ctx* ctx = as_ctx(c);
+    DSC_TRY(flush_pending(ctx));
     DSC_TRY(dsc_comm_join(c));
     DSC_CUDA_CHECK(cudaEventRecord(ctx->ev_copy_a, ctx->stream));
     DSC_CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy_a, 0));
@@ -693,6 +815,7 @@ int dsc_compute_wait_copy(dsc_ctx_t c) {
     DSC_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_b, 0));
     DSC_CUDA_CHECK(cudaEventRecord(ctx->ev_copy_c, ctx->copy_stream_down));
     DSC_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_c, 0));
+    if (!ctx->comm_pending) ctx->other_stream_joined = ctx->other_stream_seq;
     return DSC_OK;
 }
 
@@ -715,10 +838,7 @@ int dsc_buf_view(dsc_buf_t h, int32_t off, int32_t n, dsc_buf_t* out) {
     Buf* b = as_buf(h);
     if (!b || !out) return fail(DSC_E_INVALID, "view: bad handle or null out");
     DSC_TRY(check_range(b, off, n, "view"));
-    if (n > 0) {
-        DSC_TRY(buf_writable(b->ctx, b));  // a true view shares MUTABLE storage: detach from CoW aliases first
-        b->block->has_views = true;
-    }
+    if (n > 0) DSC_TRY(buf_writable(b->ctx, b));  // a true view shares MUTABLE storage: materialise, detach from copy-on-write aliases first
     Buf* v = new Buf();
     v->dtype = b->dtype;
     v->ctx = b->ctx;
@@ -726,6 +846,8 @@ int dsc_buf_view(dsc_buf_t h, int32_t off, int32_t n, dsc_buf_t* out) {
     if (n > 0) {
         v->block = b->block;
         v->block->refs++;
+        v->block->views++;
+        v->is_view = true;
         v->off = b->off + off;
     }
     *out = reinterpret_cast<dsc_buf_t>(v);
@@ -737,18 +859,16 @@ int dsc_buf_copy(dsc_buf_t h, dsc_buf_t* out);
 int dsc_buf_share(dsc_buf_t h, dsc_buf_t* out) {
     Buf* b = as_buf(h);
     if (!b || !out) return fail(DSC_E_INVALID, "share: bad handle or null out");
-    if (b->len == 0 || b->block->has_views) {
-        *out = 0;
-        return dsc_buf_copy(h, out);  // a block with true views (shared mutable storage) is copied eagerly
-    }
     Buf* v = new Buf();
     v->dtype = b->dtype;
     v->ctx = b->ctx;
     v->len = b->len;
-    v->block = b->block;
-    v->off = b->off;
-    b->block->refs++;
-    b->block->cow_shared = true;
+    int s = buf_share_into(v, b);
+    if (s == 1) {   // a block with true views (shared mutable storage) is copied eagerly
+        delete v;
+        *out = 0;
+        return dsc_buf_copy(h, out);
+    }
     *out = reinterpret_cast<dsc_buf_t>(v);
     return DSC_OK;
 }
@@ -757,6 +877,7 @@ int dsc_buf_copy(dsc_buf_t h, dsc_buf_t* out) {
     Buf* b = as_buf(h);
     if (!b || !out) return fail(DSC_E_INVALID, "copy: bad handle or null out");
     Ctx* ctx = b->ctx;
+    DSC_TRY(buf_resolve(b));
     Buf* o = nullptr;
     DSC_TRY(out_buf(ctx, b->dtype, b->len, out, &o));
     if (b->len == 0) return DSC_OK;
@@ -776,6 +897,7 @@ int dsc_buf_gather2d(dsc_buf_t h, int32_t rows, int32_t cols, int32_t r0, int32_
         return fail(DSC_E_SHAPE, "gather2d: %d x %d exceeds buffer length %d", rows, cols, b->len);
     if (r0 < 0 || r1 >= rows || c0 < 0 || c1 >= cols || r1 < r0 - 1 || c1 < c0 - 1)
         return fail(DSC_E_SHAPE, "gather2d: slice [%d..%d, %d..%d] outside %d x %d", r0, r1, c0, c1, rows, cols);
+    DSC_TRY(buf_resolve(b));
     int orows = r1 - r0 + 1, ocols = c1 - c0 + 1;
     Ctx* ctx = b->ctx;
     Buf* o = nullptr;
@@ -794,12 +916,32 @@ int dsc_buf_info(dsc_buf_t h, int* dtype, int32_t* length, int32_t* offset, int3
                  void** device_ptr) {
     Buf* b = as_buf(h);
     if (!b) return fail(DSC_E_INVALID, "info: bad handle");
+    if (device_ptr || alloc_length) DSC_TRY(buf_resolve(b));
     if (dtype) *dtype = b->dtype;
     if (length) *length = b->len;
     if (offset) *offset = (int32_t)b->off;
     if (alloc_length) *alloc_length = b->block ? (int32_t)std::min<size_t>(b->block->bytes / dtype_size(b->dtype), 0x7fffffff) : 0;
     if (device_ptr) *device_ptr = b->block ? reinterpret_cast<char*>(b->block->ptr) + b->off * dtype_size(b->dtype) : nullptr;
     return DSC_OK;
+}
+
+int dsc_set_fuse(dsc_ctx_t c, int on) {
+    if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
+    Ctx* ctx = as_ctx(c);
+    if (!on) DSC_TRY(flush_pending(ctx));
+    ctx->fuse = on != 0;
+    return DSC_OK;
+}
+
+int dsc_invalidate_caches(dsc_ctx_t c) {
+    if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
+    as_ctx(c)->cache_epoch++;
+    return DSC_OK;
+}
+
+int dsc_flush(dsc_ctx_t c) {
+    if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
+    return flush_pending(as_ctx(c));
 }
 
 int dsc_host_alloc_pinned(size_t bytes, void** out) {

@@ -97,32 +97,48 @@ static int gemm_simt(Ctx* ctx, int ta, int tb, int m, int n, int k, const T* A, 
     return DSC_OK;
 }
 
-template <>
-int gemm_impl<float>(Ctx* ctx, int ta, int tb, int m, int n, int k, Buf* A, Buf* B, Buf* bias, Buf* C) {
-    const float* bp = bias ? bias->ptr<float>() : nullptr;
-    {
-        int s = gemm_skinny<float>(ctx, ta, tb, m, n, k, A->ptr<float>(), B->ptr<float>(), bp, C->ptr<float>());
-        if (s <= 0) return s;
-    }
-    if (!(ctx->flags & DSC_FLAG_GEMM_FP32_SIMT)) {
-        int s = gemm_tf32x3_tcgen05(ctx, ta, tb, m, n, k, A->ptr<float>(), B->ptr<float>(), bp, C->ptr<float>());
-        if (s <= 0) return s;  // handled (0) or failed (<0); 1 = not eligible
-    }
-    return gemm_simt<float>(ctx, ta, tb, m, n, k, A->ptr<float>(), B->ptr<float>(), bp, C->ptr<float>());
+// The epilogue as a second pass over C, for the kernels that do not fuse it (CUDA-core, skinny, DMMA).
+template <typename T>
+static int epilogue_pass(Ctx* ctx, int m, int n, T* C, const GemmEpilogue* ep) {
+    if (!ep || ep->mode == GEMM_EP_NONE) return DSC_OK;
+    T* lo = reinterpret_cast<T*>(ep->lo);
+    if (ep->mode == GEMM_EP_BIAS_ACT)
+        return ew_rows<T>(ctx, DSC_OP_ADD, ep->op, m, n, C, reinterpret_cast<const T*>(ep->vec), C, reinterpret_cast<T*>(ep->out2), lo);
+    return ew_fused_bwd<T>(ctx, ep->op, C, reinterpret_cast<const T*>(ep->aux), C, lo, (size_t)m * n);
 }
 
 template <>
-int gemm_impl<double>(Ctx* ctx, int ta, int tb, int m, int n, int k, Buf* A, Buf* B, Buf* bias, Buf* C) {
-    const double* bp = bias ? bias->ptr<double>() : nullptr;
+int gemm_run<float>(Ctx* ctx, int ta, int tb, int m, int n, int k, MatRef A, MatRef B, const float* bias, float* C, const GemmEpilogue* ep) {
+    const float *Ap = reinterpret_cast<const float*>(A.ptr), *Bp = reinterpret_cast<const float*>(B.ptr);
     {
-        int s = gemm_skinny<double>(ctx, ta, tb, m, n, k, A->ptr<double>(), B->ptr<double>(), bp, C->ptr<double>());
-        if (s <= 0) return s;
+        int s = gemm_skinny<float>(ctx, ta, tb, m, n, k, Ap, Bp, bias, C);
+        if (s < 0) return s;
+        if (s == 0) return epilogue_pass<float>(ctx, m, n, C, ep);
+    }
+    if (!(ctx->flags & DSC_FLAG_GEMM_FP32_SIMT)) {
+        int s = gemm_tf32x3_tcgen05(ctx, ta, tb, m, n, k, A, B, bias, C, ep);
+        if (s <= 0) return s;  // handled, epilogue included (0) or failed (<0); 1 = not eligible; 2 = product stored, epilogue still to run
+        if (s == 2) return epilogue_pass<float>(ctx, m, n, C, ep);
+    }
+    DSC_TRY(gemm_simt<float>(ctx, ta, tb, m, n, k, Ap, Bp, bias, C));
+    return epilogue_pass<float>(ctx, m, n, C, ep);
+}
+
+template <>
+int gemm_run<double>(Ctx* ctx, int ta, int tb, int m, int n, int k, MatRef A, MatRef B, const double* bias, double* C, const GemmEpilogue* ep) {
+    const double *Ap = reinterpret_cast<const double*>(A.ptr), *Bp = reinterpret_cast<const double*>(B.ptr);
+    {
+        int s = gemm_skinny<double>(ctx, ta, tb, m, n, k, Ap, Bp, bias, C);
+        if (s < 0) return s;
+        if (s == 0) return epilogue_pass<double>(ctx, m, n, C, ep);
     }
     if (!(ctx->flags & DSC_FLAG_GEMM_F64_SIMT)) {
-        int s = gemm_f64_dmma(ctx, ta, tb, m, n, k, A->ptr<double>(), B->ptr<double>(), bp, C->ptr<double>());
-        if (s <= 0) return s;
+        int s = gemm_f64_dmma(ctx, ta, tb, m, n, k, Ap, Bp, bias, C);
+        if (s < 0) return s;
+        if (s == 0) return epilogue_pass<double>(ctx, m, n, C, ep);
     }
-    return gemm_simt<double>(ctx, ta, tb, m, n, k, A->ptr<double>(), B->ptr<double>(), bp, C->ptr<double>());
+    DSC_TRY(gemm_simt<double>(ctx, ta, tb, m, n, k, Ap, Bp, bias, C));
+    return epilogue_pass<double>(ctx, m, n, C, ep);
 }
 
 template <typename T>
@@ -130,24 +146,61 @@ static int gemm_entry(dsc_ctx_t c, int ta, int tb, int32_t m, int32_t n, int32_t
     if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
     Ctx* ctx = as_ctx(c);
     Buf *A, *B, *bias = nullptr, *C;
-    DSC_TRY(in_buf(ctx, dtype_of<T>::value, Ah, &A, "Mul_M_M: A"));
-    DSC_TRY(in_buf(ctx, dtype_of<T>::value, Bh, &B, "Mul_M_M: B"));
+    DSC_TRY(in_buf_peek(ctx, dtype_of<T>::value, Ah, &A, "Mul_M_M: A"));
+    DSC_TRY(in_buf_peek(ctx, dtype_of<T>::value, Bh, &B, "Mul_M_M: B"));
     if (biash) DSC_TRY(in_buf(ctx, dtype_of<T>::value, biash, &bias, "Mul_M_M_Add_V_MCols: v"));
     if (m < 0 || n < 0 || k < 0) return fail(DSC_E_SHAPE, "Mul_M_M: negative dimension");
     if ((int64_t)m * k > A->len) return fail(DSC_E_SHAPE, "Mul_M_M: A is %d x %d but its buffer holds %d elements", m, k, A->len);
     if ((int64_t)k * n > B->len) return fail(DSC_E_SHAPE, "Mul_M_M: B is %d x %d but its buffer holds %d elements", k, n, B->len);
     if ((int64_t)m * n > 0x7fffffff) return fail(DSC_E_SHAPE, "Mul_M_M: result too large for an int32 length");
     if (bias && bias->len != m) return fail(DSC_E_SHAPE, "Mul_M_M_Add_V_MCols: vector length %d, result has %d rows", bias->len, m);
-    DSC_TRY(out_buf(ctx, dtype_of<T>::value, m * n, Ch, &C));
-    if (m * n == 0) return DSC_OK;
-    if (C->ptr<T>() == A->ptr<T>() || C->ptr<T>() == B->ptr<T>()) return fail(DSC_E_INVALID, "Mul_M_M: output aliases an input");
-    if (k == 0) {
-        int grid = grid_for((size_t)m * n, 256 * 4, ctx->sm_count * 8);
-        bias_rows_kernel<T><<<grid, 256, 0, ctx->stream>>>(bias ? bias->ptr<T>() : nullptr, C->ptr<T>(), m, n);
-        DSC_LAUNCH_CHECK(ctx);
-        return DSC_OK;
+    // Transpose_M followed by Mul_M_M (every adjoint of a product, AD.Float32.fs:4127-4143): read the stored matrix through a
+    // transposed tile map instead of running the transpose.  op(A) is m x k: a pending transpose of a stored k x m matrix.
+    Operand oa, ob;
+    auto take = [&](Buf* X, int& t, int rows, int cols, Operand& o) {
+        LazyNode* tn = lazy_of(X, LZ_T);   // X = transpose of src (tn->m x tn->n), i.e. X is tn->n x tn->m
+        if (tn && tn->n == rows && tn->m == cols && (int64_t)rows * cols == X->len) {
+            o = tn->src[0];
+            t ^= 1;
+            tn->consumed = true;
+            return;
+        }
+        o = Operand();
+        o.len = X->len;
+        if (X->block) { o.block = X->block; o.off = X->off; }
+        else o.node = X->lazy;
+    };
+    int eta = ta ? 1 : 0, etb = tb ? 1 : 0;
+    take(A, eta, ta ? k : m, ta ? m : k, oa);
+    take(B, etb, tb ? n : k, tb ? k : n, ob);
+    // hold the operands while they are being resolved (a deferred operand may be dropped by its handle meanwhile)
+    LazyNode* hold = lazy_new(ctx, LZ_GEMM, dtype_of<T>::value, m * n);
+    hold->consumed = true;
+    lazy_set_operand(hold, 0, oa);
+    lazy_set_operand(hold, 1, ob);
+    int st = DSC_OK;
+    for (int i = 0; i < 2 && st == DSC_OK; ++i) st = operand_resolve(ctx, hold->src[i]);
+    if (st == DSC_OK) st = out_buf(ctx, dtype_of<T>::value, m * n, Ch, &C);
+    if (st == DSC_OK && m * n > 0) {
+        auto mat = [](const Operand& o) {
+            MatRef r;
+            r.block = o.node ? o.node->result : o.block;
+            r.off = o.node ? o.node->result_off : o.off;
+            r.ptr = r.block ? reinterpret_cast<const T*>(r.block->ptr) + r.off : nullptr;
+            return r;
+        };
+        MatRef ma = mat(hold->src[0]), mb = mat(hold->src[1]);
+        if (C->ptr<T>() == ma.ptr || C->ptr<T>() == mb.ptr) st = fail(DSC_E_INVALID, "Mul_M_M: output aliases an input");
+        else if (k == 0) {
+            int grid = grid_for((size_t)m * n, 256 * 4, ctx->sm_count * 8);
+            bias_rows_kernel<T><<<grid, 256, 0, ctx->stream>>>(bias ? bias->ptr<T>() : nullptr, C->ptr<T>(), m, n);
+            ctx->stats.kernel_launches++;
+        } else {
+            st = gemm_run<T>(ctx, eta, etb, m, n, k, ma, mb, bias ? bias->ptr<T>() : nullptr, C->ptr<T>(), nullptr);
+        }
     }
-    return gemm_impl<T>(ctx, ta ? 1 : 0, tb ? 1 : 0, m, n, k, A, B, bias, C);
+    lazy_unref(hold);
+    return st;
 }
 
 }  // namespace dsc

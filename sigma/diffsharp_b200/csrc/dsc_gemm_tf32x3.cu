@@ -1207,8 +1207,10 @@ static bool make_plan(const PlanIn& in, PlanOut& out) {
 
 }  // namespace tf32x3
 
-int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const float* A, const float* B, const float* bias, float* C) {
+int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, MatRef Am, MatRef Bm, const float* bias, float* C, const GemmEpilogue* ep) {
     using namespace tf32x3;
+    const float* A = reinterpret_cast<const float*>(Am.ptr);
+    const float* B = reinterpret_cast<const float*>(Bm.ptr);
     // Eligibility: enough rows/cols to fill 128-row tiles and enough depth to amortise the pre-pass.
     // Skinny / tiny products stay on the CUDA-core kernel (they are bandwidth- or latency-bound).
     if (m < 128 || n < 32 || k < 32) return 1;
@@ -1365,7 +1367,7 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, const flo
     }
     if (s != DSC_OK) return s;
     ctx->stats.gemm_tcgen05++;
-    return DSC_OK;
+    return (ep && ep->mode != GEMM_EP_NONE) ? 2 : DSC_OK;   // 2: product stored, the caller applies the epilogue as a second pass
 }
 
 }  // namespace dsc

@@ -240,7 +240,7 @@ int in_buf(Ctx* ctx, int dtype, dsc_buf_t h, Buf** res, const char* what);
 int in_buf_peek(Ctx* ctx, int dtype, dsc_buf_t h, Buf** res, const char* what);
 // Before writing through `b` in place: materialise it, run the deferred operations that still read its block, give it a
 // private block if copy-on-write aliases exist, and drop the operand-split companion.
-int buf_writable(Ctx* ctx, Buf* b);
+int buf_writable(Ctx* ctx, Buf* b, bool on_compute_stream = true);
 // ---- deferred evaluation (dsc_lazy.cu) ----
 LazyNode* lazy_new(Ctx* ctx, int kind, int dtype, int32_t len);
 void lazy_set_operand(LazyNode* nd, int i, Buf* b);          // operand i := the value of b (its block window, or its node)
@@ -248,6 +248,7 @@ void lazy_set_operand(LazyNode* nd, int i, const Operand& o);
 void lazy_unref(LazyNode* nd);
 int lazy_buf(Ctx* ctx, LazyNode* nd, dsc_buf_t* out);          // new handle whose value is nd (takes over the caller's reference)
 int lazy_materialize(LazyNode* nd);                            // compute nd->result (idempotent)
+void lazy_set_result(LazyNode* nd, Block* blk, size_t off);    // a fused consumer produced nd's value as a by-product: record it, release the operands
 int buf_resolve(Buf* b);                                       // make b a plain device window
 int operand_resolve(Ctx* ctx, Operand& o);                     // make o a plain device window (materialises its node)
 int flush_pending(Ctx* ctx);                                   // run every deferred compute node nobody has consumed
@@ -269,6 +270,17 @@ inline int grid_for(size_t work_items, int per_block, int max_blocks) {
     return (int)b;
 }
 
+// The operand split of the 3xTF32 GEMM (dsc_gemm_tf32x3.cu): the tensor core reads the fp32 word itself as the "hi" part
+// (kind::tf32 ignores the low 13 mantissa bits), lo = rna_tf32(x - trunc_tf32(x)); x - hi is exact in fp32.  Kernels that
+// PRODUCE a matrix a later GEMM will read write this next to the value (Block::lo) so that no separate split pass runs.
+__device__ __forceinline__ float dsc_lo_of(float x) {
+    const float res = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(res));
+    return (res - res == 0.f) ? __uint_as_float(r) : 0.f;   // non-finite x contributes through hi only
+}
+__device__ __forceinline__ double dsc_lo_of(double) { return 0.0; }   // never called: float64 GEMMs use DMMA
+
 // ---- raw executors: kernels on device pointers, no handle logic (used by the entry points and by the deferred-evaluation
 // engine; each is explicitly instantiated for float and double in the translation unit that owns the kernel) -------------
 template <typename T> int ew_map(Ctx*, int op, const T* x, T* y, size_t n);                       // dsc_elementwise.cu
@@ -288,11 +300,34 @@ int fill_raw(Ctx* ctx, int dtype, void* base, size_t n, double v);              
 int split_lo_launch(Ctx* ctx, const float* x, float* lo, size_t n);
 
 // ---- typed implementations (one template per op, instantiated for float and double) -------
-template <typename T> int gemm_impl(Ctx*, int ta, int tb, int m, int n, int k, Buf* A, Buf* B, Buf* bias, Buf* C);
-// f32 tensor-core path (dsc_gemm_tf32x3.cu): returns DSC_OK if it handled the GEMM, 1 if the
-// shape is not eligible (caller falls through to the CUDA-core kernel; never a CPU fallback).
-int gemm_tf32x3_tcgen05(Ctx*, int ta, int tb, int m, int n, int k, const float* A, const float* B,
-                        const float* bias, float* C);
+// A matrix operand: its device window and the block behind it (the float32 tensor-core GEMM keeps / finds the operand-split
+// companion there, see Block::lo).  block may be null (no caching for that operand).
+struct MatRef {
+    const void* ptr = nullptr;
+    Block* block = nullptr;
+    size_t off = 0;      // window start in elements from block->ptr
+};
+// What the GEMM does with an output tile besides storing it (the calls that FOLLOW Mul_M_M in the unchanged sequence):
+//   GEMM_EP_BIAS_ACT: z = acc + v[j] -> C;  h = f_op(z) -> out2 (op < 0: no h)      Add_M_M(., rows(v)) -> Map_F_M   (:2357,:2704)
+//   GEMM_EP_CHAIN   : y = chain_op(acc, aux[i,j]) -> C  (dsc_fused_kind)             the adjoint chains            (:4238-4240,4280-4281)
+// lo (float32, may be null): operand-split companion of the LAST output (h, or z when op < 0, or y), same layout.
+enum { GEMM_EP_NONE = 0, GEMM_EP_BIAS_ACT = 1, GEMM_EP_CHAIN = 2 };
+struct GemmEpilogue {
+    int mode = GEMM_EP_NONE;
+    int op = -1;
+    const void* vec = nullptr;   // v (n)
+    const void* aux = nullptr;   // p (m x n)
+    void* out2 = nullptr;        // h (m x n)
+    float* lo = nullptr;
+};
+// C(m x n) = op(A) op(B) [+ bias[i]] [epilogue]: picks the kernel (skinny / tensor core / CUDA core); kernels without a fused
+// epilogue run it as a second pass over C.
+template <typename T> int gemm_run(Ctx*, int ta, int tb, int m, int n, int k, MatRef A, MatRef B, const T* bias, T* C, const GemmEpilogue* ep);
+// f32 tensor-core path (dsc_gemm_tf32x3.cu): returns DSC_OK if it handled the GEMM (epilogue included), 1 if the
+// shape is not eligible (caller falls through to the CUDA-core kernel; never a CPU fallback), 2 if the product is stored
+// but the epilogue has to run as a second pass.
+int gemm_tf32x3_tcgen05(Ctx*, int ta, int tb, int m, int n, int k, MatRef A, MatRef B,
+                        const float* bias, float* C, const GemmEpilogue* ep);
 int gemm_f64_dmma(Ctx*, int ta, int tb, int m, int n, int k, const double* A, const double* B,
                   const double* bias, double* C);
 // n <= 16 products on CUDA cores (dsc_gemm_skinny.cu); same return convention

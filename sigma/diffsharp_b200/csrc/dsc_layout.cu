@@ -80,9 +80,6 @@ __global__ void __launch_bounds__(256) transpose_f64_v2_kernel(const double* __r
 
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <typename T>
-int transpose_launch(Ctx* ctx, const T* A, T* B, int m, int n);
-
 template <>
 int transpose_launch<float>(Ctx* ctx, const float* A, float* B, int m, int n) {
     if ((m % 4 == 0) && (n % 4 == 0) && al16(A) && al16(B)) {
@@ -174,7 +171,7 @@ __global__ void diag_kernel(const T* __restrict__ A, T* __restrict__ out, int n,
 // Which CTA does the last step varies; the order of the additions does not (deterministic).
 template <typename T, int W>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ M, T* __restrict__ partial, T* __restrict__ v,
-                                                      unsigned int* __restrict__ tickets, int m, int n, int rows_per_chunk) {
+                                                      unsigned int* __restrict__ tickets, int m, int n, int rows_per_chunk, int accumulate) {
     __shared__ T sm[8][32 * W + 1];
     __shared__ int s_last;
     const int col0 = (blockIdx.x * 32 + threadIdx.x) * W;
@@ -227,7 +224,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ M, T*
     if (chunks == 1) {
         if (threadIdx.y == 0 && col0 < n) {
 #pragma unroll
-            for (int w = 0; w < W; ++w) v[col0 + w] += acc[w];
+            for (int w = 0; w < W; ++w) v[col0 + w] = accumulate ? v[col0 + w] + acc[w] : acc[w];
         }
         return;
     }
@@ -259,13 +256,13 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ M, T*
     tree();
     if (threadIdx.y == 0 && col0 < n) {
 #pragma unroll
-        for (int w = 0; w < W; ++w) v[col0 + w] += acc[w];
+        for (int w = 0; w < W; ++w) v[col0 + w] = accumulate ? v[col0 + w] + acc[w] : acc[w];
     }
     if (threadIdx.x == 0 && threadIdx.y == 0) tickets[blockIdx.x] = 0;
 }
 
 template <typename T>
-int colsum_launch(Ctx* ctx, const T* M, T* v, int m, int n) {
+int colsum_launch(Ctx* ctx, const T* M, T* v, int m, int n, bool accumulate) {
     constexpr int W = sizeof(T) == 4 ? 4 : 2;
     bool vec = (n % W == 0) && al16(M);
     int cols_per_block = vec ? 32 * W : 32;
@@ -285,8 +282,8 @@ int colsum_launch(Ctx* ctx, const T* M, T* v, int m, int n) {
     DSC_TRY(ensure_red_scratch(ctx, need));
     T* partial = reinterpret_cast<T*>(reinterpret_cast<char*>(ctx->red_scratch) + 256);
     dim3 block(32, 8), grid(gx, chunks);
-    if (vec) colsum_kernel<T, W><<<grid, block, 0, ctx->stream>>>(M, partial, v, ctx->tickets, m, n, rows_per_chunk);
-    else colsum_kernel<T, 1><<<grid, block, 0, ctx->stream>>>(M, partial, v, ctx->tickets, m, n, rows_per_chunk);
+    if (vec) colsum_kernel<T, W><<<grid, block, 0, ctx->stream>>>(M, partial, v, ctx->tickets, m, n, rows_per_chunk, accumulate ? 1 : 0);
+    else colsum_kernel<T, 1><<<grid, block, 0, ctx->stream>>>(M, partial, v, ctx->tickets, m, n, rows_per_chunk, accumulate ? 1 : 0);
     DSC_LAUNCH_CHECK(ctx);
     return DSC_OK;
 }
@@ -297,8 +294,18 @@ static int transpose_impl(dsc_ctx_t c, int32_t m, int32_t n, dsc_buf_t Ah, dsc_b
     if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
     Ctx* ctx = as_ctx(c);
     Buf *A, *o;
-    DSC_TRY(in_buf(ctx, dtype_of<T>::value, Ah, &A, "Transpose_M: A"));
+    DSC_TRY(in_buf_peek(ctx, dtype_of<T>::value, Ah, &A, "Transpose_M: A"));
     if (m < 0 || n < 0 || (int64_t)m * n > A->len) return fail(DSC_E_SHAPE, "Transpose_M: %d x %d exceeds buffer length %d", m, n, A->len);
+    if (!outh) return fail(DSC_E_INVALID, "null output handle pointer");
+    if (ctx->fuse && *outh == 0 && (int64_t)m * n > 0 && (int64_t)m * n == A->len) {
+        // every weight / input adjoint transposes an operand right before Mul_M_M (AD.Float32.fs:4127-4143): the product reads
+        // the stored matrix through a transposed tile map instead; any other consumer materialises the transpose
+        LazyNode* nd = lazy_new(ctx, LZ_T, A->dtype, m * n);
+        nd->m = m; nd->n = n;
+        lazy_set_operand(nd, 0, A);
+        return lazy_buf(ctx, nd, outh);
+    }
+    DSC_TRY(buf_resolve(A));
     DSC_TRY(out_buf(ctx, dtype_of<T>::value, m * n, outh, &o));
     if (m * n == 0) return DSC_OK;
     if (o->ptr<T>() == A->ptr<T>()) return fail(DSC_E_INVALID, "Transpose_M: in-place transpose is not supported");
@@ -336,6 +343,24 @@ static int permute_impl(dsc_ctx_t c, int rank, const int64_t* shape, const int32
     return DSC_OK;
 }
 
+template <typename T>
+int repeat_rows_launch(Ctx* ctx, const T* v, T* out, int m, int n) {
+    constexpr int W = sizeof(T) == 4 ? 4 : 2;
+    const size_t total = (size_t)m * n;
+    if ((n % W == 0) && al16(v) && al16(out)) {
+        using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+        int grid = grid_for(total / W, 256 * 4, ctx->sm_count * 8);
+        repeat_rows_vec_kernel<T, V, W><<<grid, 256, 0, ctx->stream>>>(v, out, m, n / W);
+    } else {
+        int grid = grid_for(total, 256 * 4, ctx->sm_count * 8);
+        repeat_kernel<T, true><<<grid, 256, 0, ctx->stream>>>(v, out, m, n);
+    }
+    DSC_LAUNCH_CHECK(ctx);
+    return DSC_OK;
+}
+template int repeat_rows_launch<float>(Ctx*, const float*, float*, int, int);
+template int repeat_rows_launch<double>(Ctx*, const double*, double*, int, int);
+
 template <typename T, bool ROWS>
 static int repeat_impl(dsc_ctx_t c, int32_t reps, dsc_buf_t vh, dsc_buf_t* outh) {
     if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
@@ -345,18 +370,21 @@ static int repeat_impl(dsc_ctx_t c, int32_t reps, dsc_buf_t vh, dsc_buf_t* outh)
     if (reps < 0) return fail(DSC_E_SHAPE, "RepeatReshapeCopy: negative repeat count");
     int64_t total = (int64_t)reps * v->len;
     if (total > 0x7fffffff) return fail(DSC_E_SHAPE, "RepeatReshapeCopy: result too large for an int32 length");
+    if (!outh) return fail(DSC_E_INVALID, "null output handle pointer");
+    if (ROWS && ctx->fuse && *outh == 0 && total > 0) {
+        // the fork broadcasts a bias as m copies of the vector and adds them (AD.Float32.fs:1860-1865): the copies are written
+        // only if somebody other than Add_M_M reads them
+        LazyNode* nd = lazy_new(ctx, LZ_ROWS, v->dtype, (int32_t)total);
+        nd->m = reps; nd->n = v->len;
+        lazy_set_operand(nd, 0, v);
+        return lazy_buf(ctx, nd, outh);
+    }
     DSC_TRY(out_buf(ctx, dtype_of<T>::value, (int32_t)total, outh, &o));
     if (total == 0) return DSC_OK;
     int m = ROWS ? reps : v->len, n = ROWS ? v->len : reps;
-    constexpr int W = sizeof(T) == 4 ? 4 : 2;
-    if (ROWS && (n % W == 0) && al16(v->ptr<T>()) && al16(o->ptr<T>())) {
-        using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
-        int grid = grid_for((size_t)total / W, 256 * 4, ctx->sm_count * 8);
-        repeat_rows_vec_kernel<T, V, W><<<grid, 256, 0, ctx->stream>>>(v->ptr<T>(), o->ptr<T>(), m, n / W);
-    } else {
-        int grid = grid_for((size_t)total, 256 * 4, ctx->sm_count * 8);
-        repeat_kernel<T, ROWS><<<grid, 256, 0, ctx->stream>>>(v->ptr<T>(), o->ptr<T>(), m, n);
-    }
+    if (ROWS) return repeat_rows_launch<T>(ctx, v->ptr<T>(), o->ptr<T>(), m, n);
+    int grid = grid_for((size_t)total, 256 * 4, ctx->sm_count * 8);
+    repeat_kernel<T, ROWS><<<grid, 256, 0, ctx->stream>>>(v->ptr<T>(), o->ptr<T>(), m, n);
     DSC_LAUNCH_CHECK(ctx);
     return DSC_OK;
 }
@@ -367,12 +395,21 @@ static int colsum_impl(dsc_ctx_t c, int32_t m, int32_t n, dsc_buf_t Mh, dsc_buf_
     Ctx* ctx = as_ctx(c);
     Buf *M, *v;
     DSC_TRY(in_buf(ctx, dtype_of<T>::value, Mh, &M, "Add_M_Colwise_V_InPlace: M"));
-    DSC_TRY(in_buf(ctx, dtype_of<T>::value, vh, &v, "Add_M_Colwise_V_InPlace: v"));
+    DSC_TRY(in_buf_peek(ctx, dtype_of<T>::value, vh, &v, "Add_M_Colwise_V_InPlace: v"));
     if (m < 0 || n < 0 || (int64_t)m * n > M->len) return fail(DSC_E_SHAPE, "Add_M_Colwise_V_InPlace: %d x %d exceeds buffer length %d", m, n, M->len);
     if (v->len != n) return fail(DSC_E_SHAPE, "Add_M_Colwise_V_InPlace: vector length %d, matrix has %d columns", v->len, n);
     if (m == 0 || n == 0) return DSC_OK;
+    if (LazyNode* z = lazy_of(v, LZ_ZERO)) {
+        // a bias adjoint is a fresh zero vector when its column sums arrive (AD.Float32.fs:4255 after :3640-3641): 0 + s = s,
+        // so the sums are stored instead of added and the zeros are never written
+        v->lazy = nullptr;
+        lazy_unref(z);
+        DSC_TRY(pool_alloc(ctx, (size_t)n * sizeof(T), &v->block));
+        v->off = 0;
+        return colsum_launch<T>(ctx, M->ptr<T>(), v->ptr<T>(), m, n, false);
+    }
     DSC_TRY(buf_writable(ctx, v));
-    return colsum_launch<T>(ctx, M->ptr<T>(), v->ptr<T>(), m, n);
+    return colsum_launch<T>(ctx, M->ptr<T>(), v->ptr<T>(), m, n, true);
 }
 
 template <typename T>

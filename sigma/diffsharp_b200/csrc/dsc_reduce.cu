@@ -17,7 +17,11 @@ constexpr int kRThreads = 256;
 constexpr int kRUnroll = 8;
 constexpr int kMaxPartials = 148 * 4;   // measured (tools/sum_tune.py, 4096^2): 592 -> 4.60 TB/s f32, 1184 -> 4.50, 2368 -> 4.30
 
-enum { R_SUM = 0, R_ASUM = 1, R_SUMSQ = 2, R_AMAX = 3, R_DOT = 4 };
+enum { R_SUM = 0, R_ASUM = 1, R_SUMSQ = 2, R_AMAX = 3, R_DOT = 4,
+       R_PRODSUM = 5 };   // Sum(a .* b) with the product ROUNDED first: bit-identical to Mul_Had_M_M followed by Sum_M
+
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 
 template <int KIND, typename T>
 __device__ __forceinline__ T r_load(T a, T b) {
@@ -25,6 +29,7 @@ __device__ __forceinline__ T r_load(T a, T b) {
     else if constexpr (KIND == R_ASUM) return a < T(0) ? -a : a;
     else if constexpr (KIND == R_SUMSQ) return a * a;
     else if constexpr (KIND == R_AMAX) return a < T(0) ? -a : a;
+    else if constexpr (KIND == R_PRODSUM) return mul_rn(a, b);   // never contracted into an FMA with the accumulation
     else return a * b;
 }
 template <int KIND, typename T>
@@ -84,7 +89,7 @@ __global__ void __launch_bounds__(kRThreads) reduce_kernel(const T* __restrict__
                 ok[u] = i < end;
                 if (ok[u]) {
                     va[u] = *reinterpret_cast<const V*>(a + i * W);
-                    if constexpr (KIND == R_DOT) vb[u] = *reinterpret_cast<const V*>(b + i * W);
+                    if constexpr (KIND == R_DOT || KIND == R_PRODSUM) vb[u] = *reinterpret_cast<const V*>(b + i * W);
                     else vb[u] = va[u];
                 }
             }
@@ -97,7 +102,7 @@ __global__ void __launch_bounds__(kRThreads) reduce_kernel(const T* __restrict__
         }
         if (blockIdx.x == 0) {  // scalar tail (< W elements)
             const size_t j = nvec * W + threadIdx.x;
-            if (j < n) acc[1] = r_comb<KIND>(acc[1], r_load<KIND>(a[j], KIND == R_DOT ? b[j] : a[j]));
+            if (j < n) acc[1] = r_comb<KIND>(acc[1], r_load<KIND>(a[j], (KIND == R_DOT || KIND == R_PRODSUM) ? b[j] : a[j]));
         }
     } else {
         const size_t end = cta_end < n ? cta_end : n;
@@ -105,7 +110,7 @@ __global__ void __launch_bounds__(kRThreads) reduce_kernel(const T* __restrict__
 #pragma unroll
             for (int u = 0; u < kRUnroll; ++u) {
                 const size_t j = base + (size_t)(it * kRUnroll + u) * kRThreads;
-                if (j < end) acc[u] = r_comb<KIND>(acc[u], r_load<KIND>(a[j], KIND == R_DOT ? b[j] : a[j]));
+                if (j < end) acc[u] = r_comb<KIND>(acc[u], r_load<KIND>(a[j], (KIND == R_DOT || KIND == R_PRODSUM) ? b[j] : a[j]));
             }
         }
     }
@@ -247,7 +252,7 @@ template <int KIND, typename T>
 static int launch_reduce(Ctx* ctx, const T* a, const T* b, size_t n, T* result) {
     unsigned int* ticket = ctx->tickets;
     T* partials = reinterpret_cast<T*>(reinterpret_cast<char*>(ctx->red_scratch) + 256);
-    bool vec = al16(a) && (KIND != R_DOT || al16(b));
+    bool vec = al16(a) && ((KIND != R_DOT && KIND != R_PRODSUM) || al16(b));
     size_t items = vec ? n / RVec<T>::N : n;
     if (items == 0) items = 1;
     // grid and per-CTA chunk are functions of n only (determinism)
@@ -282,12 +287,44 @@ static int fetch_scalar(Ctx* ctx, const void* dev, T* out) {
     return DSC_OK;
 }
 
+// Sum of a DEFERRED Hadamard product (`had(E, E).Sum()`, the squared-error loss: AD.Float32.fs:2393 -> :2807): reduce the
+// rounded products in one pass over the factors instead of writing the product first.  Returns DSC_OK with the factor
+// pointers, 1 if x is not such a value.
+template <typename T>
+static int sum_of_product(Ctx* ctx, Buf* x, const T** pa, const T** pb) {
+    LazyNode* h = lazy_of(x, LZ_HAD);
+    if (!h || !ctx->fuse) return 1;
+    for (int i = 0; i < 2; ++i) DSC_TRY(operand_resolve(ctx, h->src[i]));
+    auto ptr = [](const Operand& o) {
+        return o.node ? reinterpret_cast<const T*>(o.node->result->ptr) + o.node->result_off : reinterpret_cast<const T*>(o.block->ptr) + o.off;
+    };
+    *pa = ptr(h->src[0]);
+    *pb = ptr(h->src[1]);
+    // the element -> thread assignment (hence the summation order) depends on the vector path: fuse only when the factors take
+    // the path the freshly allocated product would have taken
+    if ((reinterpret_cast<uintptr_t>(*pa) & 15) || (reinterpret_cast<uintptr_t>(*pb) & 15)) return 1;
+    h->consumed = true;
+    return DSC_OK;
+}
+
 template <int KIND, typename T>
 static int reduce_scalar(dsc_ctx_t c, dsc_buf_t xh, dsc_buf_t yh, T* out, const char* name) {
     if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
     if (!out) return fail(DSC_E_INVALID, "%s: null result pointer", name);
     Ctx* ctx = as_ctx(c);
     Buf *x, *y = nullptr;
+    if (KIND == R_SUM) {
+        DSC_TRY(in_buf_peek(ctx, dtype_of<T>::value, xh, &x, name));
+        if (x->len == 0) { *out = T(0); return DSC_OK; }
+        const T *pa, *pb;
+        int s = sum_of_product<T>(ctx, x, &pa, &pb);
+        if (s < 0) return s;
+        if (s == DSC_OK) {
+            T* slot = result_slot<T>(ctx);
+            DSC_TRY((launch_reduce<R_PRODSUM, T>(ctx, pa, pb, x->len, slot)));
+            return fetch_scalar<T>(ctx, slot, out);
+        }
+    }
     DSC_TRY(in_buf(ctx, dtype_of<T>::value, xh, &x, name));
     if (KIND == R_DOT) {
         DSC_TRY(in_buf(ctx, dtype_of<T>::value, yh, &y, name));
@@ -305,6 +342,16 @@ static int reduce_dev(dsc_ctx_t c, dsc_buf_t xh, dsc_buf_t yh, dsc_buf_t* outh, 
     if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
     Ctx* ctx = as_ctx(c);
     Buf *x, *y = nullptr, *o;
+    if (KIND == R_SUM) {
+        DSC_TRY(in_buf_peek(ctx, dtype_of<T>::value, xh, &x, name));
+        const T *pa, *pb;
+        int s = x->len > 0 ? sum_of_product<T>(ctx, x, &pa, &pb) : 1;
+        if (s < 0) return s;
+        if (s == DSC_OK) {
+            DSC_TRY(out_buf(ctx, dtype_of<T>::value, 1, outh, &o));
+            return launch_reduce<R_PRODSUM, T>(ctx, pa, pb, x->len, o->ptr<T>());
+        }
+    }
     DSC_TRY(in_buf(ctx, dtype_of<T>::value, xh, &x, name));
     if (KIND == R_DOT) {
         DSC_TRY(in_buf(ctx, dtype_of<T>::value, yh, &y, name));

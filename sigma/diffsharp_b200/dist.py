@@ -19,8 +19,12 @@ import os
 
 import numpy as np
 
-from . import _lib
-from ._lib import check, lib
+
+
+def _native():
+    """the ctypes binding, imported on first use so that the gloo-only helpers (shard_range, GlooHostComm) work without the CUDA library"""
+    from . import _lib
+    return _lib
 
 
 def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
@@ -69,6 +73,8 @@ class NcclComm:
         import torch.distributed as dist
         self.ctx = ctx
         self.rank, self.world, _ = env_rank()
+        _lib = _native()
+        check, lib = _lib.check, _lib.lib
         if self.world == 1:
             check(lib.dsc_comm_init(ctx.handle, 1, 0, None))
             return
@@ -85,19 +91,29 @@ class NcclComm:
         """In-place sum over ranks of a list of CudaDataBuffers of one dtype (one NCCL group)."""
         if not buffers:
             return
+        _lib = _native()
         p = "s" if buffers[0].dtype == np.float32 else "d"
+        for b in buffers:
+            b._flush_host_writes()
         arr = (_lib.buf_t * len(buffers))(*[b.handle for b in buffers])
-        check(getattr(lib, f"dsc_{p}allreduce_sum")(self.ctx.handle, len(buffers), arr))
+        _lib.check(getattr(_lib.lib, f"dsc_{p}allreduce_sum")(self.ctx.handle, len(buffers), arr))
+        for b in buffers:
+            b._invalidate_host()
 
     def allgather(self, send, recv):
+        _lib = _native()
         p = "s" if send.dtype == np.float32 else "d"
-        check(getattr(lib, f"dsc_{p}allgather")(self.ctx.handle, send.handle, recv.handle))
+        send._flush_host_writes()
+        _lib.check(getattr(_lib.lib, f"dsc_{p}allgather")(self.ctx.handle, send.handle, recv.handle))
+        recv._invalidate_host()
 
     def join(self):
-        check(lib.dsc_comm_join(self.ctx.handle))
+        _lib = _native()
+        _lib.check(_lib.lib.dsc_comm_join(self.ctx.handle))
 
     def close(self):
-        check(lib.dsc_comm_destroy(self.ctx.handle))
+        _lib = _native()
+        _lib.check(_lib.lib.dsc_comm_destroy(self.ctx.handle))
 
 
 class GlooHostComm:

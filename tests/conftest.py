@@ -40,8 +40,9 @@ def cuda_provider():
 
 @pytest.fixture(scope="session")
 def cuda_provider_nofuse(cuda_provider):
+    """a second context on the same GPU created with DSC_FLAG_NO_FUSE: every call launches its own kernel(s) at once"""
     from sigma.diffsharp_b200.config import CudaBackendProvider
-    return CudaBackendProvider(ctx=cuda_provider.ctx, fuse=False)
+    return CudaBackendProvider(device=0, fuse=False)
 
 
 @pytest.fixture()

@@ -166,9 +166,8 @@ def test_c2_full_size_properties(cuda_provider, dtype):
     dA = ShapedDataBufferView(b.CreateDataBuffer(A.reshape(-1)), n, n)
     tol = 1e-5 if dtype == np.float32 else 1e-12
     # Transpose_M: involution, bit exact
-    cuda_nf = type(b)(dtype, ctx=b.ctx, fuse=False)
-    At = cuda_nf.Transpose_M(dA)
-    assert np.array_equal(cuda_nf.Transpose_M(At).to_numpy(), A)
+    At = b.Transpose_M(dA)
+    assert np.array_equal(b.Transpose_M(At).to_numpy(), A)
     assert np.array_equal(At.to_numpy()[:64], A.T[:64])
     # Sum_M vs exact float64 sum (App. D-6)
     exact = float(A.astype(np.float64).sum())

@@ -46,8 +46,8 @@ def check(b, m, n, k, ta, tb, positive=False, time_it=False):
 
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "f32"
-    ctx = CudaContext(0)
-    b = CudaBackend(np.float32 if which == "f32" else np.float64, ctx=ctx, fuse=False)
+    ctx = CudaContext(0, 8)  # 8 = DSC_FLAG_NO_FUSE: every call launches its own kernel(s)
+    b = CudaBackend(np.float32 if which == "f32" else np.float64, ctx=ctx)
     tol = 1e-5 if which == "f32" else 1e-12
     worst = 0.0
     shapes = [(128, 64, 32), (128, 64, 64), (128, 256, 128), (256, 256, 256), (257, 129, 65), (128, 300, 784), (512, 512, 512),

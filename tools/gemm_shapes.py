@@ -10,8 +10,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sigma.diffsharp_b200.backend import CudaBackend  # noqa: E402
 from sigma.diffsharp_b200.buffers import CudaContext  # noqa: E402
 
-ctx = CudaContext(0)
-b = CudaBackend(np.float32 if sys.argv[1] == "f32" else np.float64, ctx=ctx, fuse=False)
+ctx = CudaContext(0, 8)  # 8 = DSC_FLAG_NO_FUSE: every call launches its own kernel(s)
+b = CudaBackend(np.float32 if sys.argv[1] == "f32" else np.float64, ctx=ctx)
 for spec in sys.argv[2:]:
     m, n, k, ta, tb = [int(x) for x in spec.split(",")]
     rng = np.random.default_rng(0)

@@ -15,8 +15,8 @@ from sigma.diffsharp_b200._lib import check, lib  # noqa: E402
 from sigma.diffsharp_b200.backend import CudaBackend  # noqa: E402
 from sigma.diffsharp_b200.buffers import CudaContext  # noqa: E402
 
-ctx = CudaContext(0)
-b = CudaBackend(np.float32, ctx=ctx, fuse=False)
+ctx = CudaContext(0, 8)  # 8 = DSC_FLAG_NO_FUSE: every call launches its own kernel(s)
+b = CudaBackend(np.float32, ctx=ctx)
 rng = np.random.default_rng(0)
 
 

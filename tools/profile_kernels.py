@@ -11,8 +11,8 @@ from sigma.diffsharp_b200.backend import CudaBackend, MapOp  # noqa: E402
 from sigma.diffsharp_b200.buffers import CudaContext, ShapedDataBufferView  # noqa: E402
 
 dt = np.float64 if (len(sys.argv) > 1 and sys.argv[1] == "f64") else np.float32
-ctx = CudaContext(0)
-b = CudaBackend(dt, ctx=ctx, fuse=False)
+ctx = CudaContext(0, 8)  # 8 = DSC_FLAG_NO_FUSE: every call launches its own kernel(s)
+b = CudaBackend(dt, ctx=ctx)
 rng = np.random.default_rng(0)
 n = 4096
 A = ShapedDataBufferView(b.CreateDataBuffer((rng.random(n * n) * 2 - 1).astype(dt)), n, n)

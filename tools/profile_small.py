@@ -13,7 +13,7 @@ from sigma.diffsharp_b200.buffers import CudaContext, ShapedDataBufferView  # no
 
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 ctx = CudaContext(0)
-b = CudaBackend(np.float32, ctx=ctx, fuse=True)
+b = CudaBackend(np.float32, ctx=ctx)
 rng = np.random.default_rng(0)
 mat = lambda m, n: ShapedDataBufferView(b.CreateDataBuffer((rng.random(m * n) * 2 - 1).astype(np.float32)), m, n)  # noqa: E731
 H, dZ, Z3, W3 = mat(rows, 1024), mat(rows, 1024), mat(rows, 10), mat(1024, 10)
