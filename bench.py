@@ -40,6 +40,7 @@ GLOBAL_BATCH = int(os.environ.get("DSC_BENCH_BATCH", "8192"))  # override only f
 # algorithmic GEMM work of one C3 step = fwd + dW + dH
 STEP_GFLOP = 78.35
 ALLREDUCE_MB = 7.45
+TIMED_BATCHES = 11   # the K timed steps are repeated this many times; the median batch is reported
 
 
 def load_peaks():
@@ -105,6 +106,27 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
+def digest_max_rel(loss, grads):
+    """The all-reduced adjoints of this run against the committed digest of the 1-GPU / CPU-oracle step on the same inputs
+    (tests/golden/golden.npz, written by tests/golden/make_golden.py::c3_digest: per adjoint buffer its L2 norm, its first
+    16 elements and 64 samples spread over the buffer; the loss against a float64 sum).  SURVEY 8(d): "gradients equal the
+    1-GPU result <= 1e-5".  Returns the largest relative deviation, or None when the digest does not apply."""
+    path = os.path.join(ROOT, "tests", "golden", "golden.npz")
+    if GLOBAL_BATCH != 8192 or not os.path.exists(path):
+        return None
+    gold = np.load(path)
+    worst = abs(loss - float(gold["c3_loss64"][0])) / abs(float(gold["c3_loss64"][0])) / 2   # Sum_M of 81 920 same-sign terms: bar 2e-5 (App. D-6)
+    for i, v in enumerate(grads):
+        v = v.reshape(-1)
+        l2g = float(gold[f"c3_grad{i}_l2"][0])
+        worst = max(worst, abs(float(np.sqrt(np.sum(v.astype(np.float64) ** 2))) - l2g) / l2g)
+        idx = np.unique(np.linspace(0, v.size - 1, min(64, v.size)).astype(np.int64))
+        ref = np.concatenate([gold[f"c3_grad{i}_head"], gold[f"c3_grad{i}_samp"]]).astype(np.float64)
+        got = np.concatenate([v[:16], v[idx]]).astype(np.float64)
+        worst = max(worst, float(np.abs(got - ref).max() / max(np.abs(ref).max(), l2g / np.sqrt(v.size))))
+    return worst
+
+
 def pinned_array(lib, check, shape, dtype):
     n = int(np.prod(shape))
     p = C.c_void_p()
@@ -114,39 +136,55 @@ def pinned_array(lib, check, shape, dtype):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_reference(args):
-    """CPU arm: the oracle's OpenBLAS path executing the same call sequence, all host threads."""
-    rank = int(os.environ.get("RANK", 0))
-    if rank != 0:
-        return
+def _cpu_full_step_times(min_steps, budget_s, warmup=1):
+    """The CPU oracle (the reference's call sequence over OpenBLAS) on the FULL config-3 batch: list of wall times per step.
+    Imports nothing of the CUDA library."""
     from oracle.backend import OracleBackend, get_num_threads, openblas_info, set_num_threads
     from sigma.diffsharp_b200 import workloads as wl
     from sigma.diffsharp_b200.config import DictBackendProvider, GlobalConfig
     cores = os.cpu_count() or 1
     set_num_threads(cores)
+    old = GlobalConfig.BackendProvider
     GlobalConfig.BackendProvider = DictBackendProvider(OracleBackend(np.float32), OracleBackend(np.float64))
-    sample_rows = GLOBAL_BATCH // 8  # bounded sample: 1/8 of the batch rows per timed step
-    X, Y, Ws, bs = wl.mlp_inputs(LAYERS, GLOBAL_BATCH, row_range=(0, sample_rows))
-    dX, dY = wl.to_DM(X), wl.to_DM(Y)
-    dWs, dbs = [wl.to_DM(w) for w in Ws], [wl.to_DV(b) for b in bs]
-    for _ in range(max(1, min(args.warmup, 2))):
-        wl.mlp_grad(dX, dY, dWs, dbs)
-    times = []
-    for _ in range(args.steps):
-        t0 = time.perf_counter()
-        wl.mlp_grad(dX, dY, dWs, dbs)
-        times.append(time.perf_counter() - t0)
-    t_sample = sum(times) / len(times)
-    t_step = t_sample * (GLOBAL_BATCH / sample_rows)  # every cost of the step is linear in the batch rows
+    try:
+        X, Y, Ws, bs = wl.mlp_inputs(LAYERS, GLOBAL_BATCH)
+        dX, dY = wl.to_DM(X), wl.to_DM(Y)
+        dWs, dbs = [wl.to_DM(w) for w in Ws], [wl.to_DV(b) for b in bs]
+        for _ in range(warmup):
+            wl.mlp_grad(dX, dY, dWs, dbs)
+        times = []
+        t_end = time.perf_counter() + budget_s
+        while len(times) < min(min_steps, 5) or (time.perf_counter() < t_end and len(times) < min_steps):
+            t0 = time.perf_counter()
+            wl.mlp_grad(dX, dY, dWs, dbs)
+            times.append(time.perf_counter() - t0)
+        info = f"{openblas_info()}; OpenBLAS threads={get_num_threads()}; nproc={cores}"
+        return times, get_num_threads(), info
+    finally:
+        GlobalConfig.BackendProvider = old
+
+
+def run_reference(args):
+    """CPU arm: the oracle's OpenBLAS path executing the same call sequence on the same config (global batch 8192, every
+    row: nothing is sampled or extrapolated), all host threads.  A step takes seconds, so `--steps K` is honoured up to a
+    wall-clock budget of a few minutes and at least 5 steps are timed; the median is reported."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    steps = max(5, min(args.steps, 40))
+    t0 = time.perf_counter()
+    times, threads, info = _cpu_full_step_times(steps, budget_s=120.0, warmup=max(1, min(args.warmup, 2)))
+    t_step = statistics.median(times)
     value = 1.0 / t_step
-    sample = (f"{sample_rows} of {GLOBAL_BATCH} batch rows per timed step, scaled x{GLOBAL_BATCH // sample_rows}; "
-              f"{openblas_info()}; threads={get_num_threads()}")
+    sample = (f"the full step (all {GLOBAL_BATCH} batch rows), {len(times)} timed steps, median (min {min(times) * 1e3:.0f} ms, max {max(times) * 1e3:.0f} ms, "
+              f"whole arm {time.perf_counter() - t0:.1f} s); {info}")
     line = {
         "impl": "reference", "metric": "MLP grad steps/sec", "value": value, "unit": "steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
+        "steps": len(times), "warmup": max(1, min(args.warmup, 2)), "ms_per_step": t_step * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C3: reverse-mode grad of 784-1024-1024-10 tanh MLP loss, global batch 8192, float32"},
-        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": "C3: reverse-mode grad of 784-1024-1024-10 tanh MLP loss, global batch 8192, float32",
+                   "global_batch": GLOBAL_BATCH},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -375,19 +413,35 @@ def run_ours(args):
     dWs, dbs = [wl.to_DM(w) for w in Ws], [wl.to_DV(b) for b in bs]
 
     def eager_step():
+        # a training loop feeds new X / updated W every step: nothing the library cached about the operands of the previous
+        # step (operand-split companions of the float32 GEMM) may be carried over into this one
+        ctx.invalidate_caches()
         L, dW, db = D.sharded_mlp_grad(comm, dX, dY, dWs, dbs)
         comm.join()
         return L, dW, db
 
     # ---- warm-up (also sizes the GEMM workspace and the pool before capture) ----
     for _ in range(max(args.warmup, 3)):
-        _, chk_W, chk_b = eager_step()
+        chk_L, chk_W, chk_b = eager_step()
     ctx.sync()
     # the all-reduced adjoints must be the SAME bits on every rank (rank-ordered sum): compare a float64 checksum
     chk = float(np.sum(chk_W[-1].ToArray(), dtype=np.float64) + sum(np.sum(v.ToArray(), dtype=np.float64) for v in chk_b))
     adjoints_identical = bool(D.max_over_ranks(chk) == -D.max_over_ranks(-chk))
     if not adjoints_identical:
         raise SystemExit(f"rank {rank}: the all-reduced adjoints differ between ranks (checksum {chk!r})")
+    # ... and equal to the 1-GPU result: the committed digest of the CPU-oracle / 1-GPU step on the same inputs
+    import torch
+    import torch.distributed as tdist
+    loss_total = float(chk_L)
+    if world > 1:
+        t = torch.tensor([loss_total], dtype=torch.float64)
+        tdist.all_reduce(t)
+        loss_total = float(t[0])
+    dmax = digest_max_rel(loss_total, [a.ToArray() for a in chk_W] + [v.ToArray() for v in chk_b])
+    adjoints_match_1gpu = None if dmax is None else {"ok": bool(dmax <= 1e-5), "max_rel": dmax, "tolerance": 1e-5,
+                                                     "against": "tests/golden/golden.npz c3_* (CPU oracle, full batch, 1 process)"}
+    if dmax is not None and dmax > 1e-5:
+        raise SystemExit(f"rank {rank}: the all-reduced adjoints deviate from the 1-GPU digest by {dmax:.3e} (> 1e-5)")
     del chk_W, chk_b
 
     # ---- eager timing: the plugin interface driven op by op ----
@@ -427,13 +481,18 @@ def run_ours(args):
         if i % 16 == 15:
             ctx.sync()
     ctx.sync()
-    D.barrier(); ctx.sync()
-    ctx.record(e0)
-    for _ in range(args.steps):
-        ctx.graph_launch(graph)
-    ctx.record(e1)
-    ctx.sync(); D.barrier()
-    graph_ms = D.max_over_ranks(ctx.elapsed_ms(e0, e1)) / args.steps
+    # K steps per timed batch, bracketed by barrier + synchronise, max over ranks; the batch is repeated and the MEDIAN batch
+    # is reported (one batch is ~10 ms: a single daemon tick would move it)
+    batch_ms = []
+    for _ in range(TIMED_BATCHES):
+        D.barrier(); ctx.sync()
+        ctx.record(e0)
+        for _ in range(args.steps):
+            ctx.graph_launch(graph)
+        ctx.record(e1)
+        ctx.sync(); D.barrier()
+        batch_ms.append(D.max_over_ranks(ctx.elapsed_ms(e0, e1)) / args.steps)
+    graph_ms = statistics.median(batch_ms)
     clocks = sampler.stop()
     loss_graph = float(loss_bufs[0].SubData[0])
     del gW, gb, loss_bufs
@@ -451,10 +510,13 @@ def run_ours(args):
     hY[...] = Y
     n_params = sum(w.size for w in Ws) + sum(b.size for b in bs)
     h2d = (X.size + Y.size) * 4
-    # The all-reduced adjoints are identical on every rank: the job reads them back to the host ONCE
-    # (rank 0); every rank reads back the loss of its own rows.  d2h_bytes_per_step is rank 0's count.
-    read_grads = rank == 0
-    d2h = (n_params * 4 if read_grads else 0) + 4
+    # The all-reduced adjoints are identical on every rank: the job reads them back to host memory ONCE per step, every rank
+    # its 1/N slice of the concatenated adjoint vector (a rank's PCIe link carries 7.45 MB / N, not 7.45 MB); every rank also
+    # reads back the loss of its own rows.  The byte counts below are whole-job totals per step.
+    read_grads = True
+    sl0, sl1 = D.shard_range(n_params, rank, world)
+    d2h = n_params * 4 + 4 * world
+    h2d_job = GLOBAL_BATCH * (LAYERS[0] + LAYERS[-1]) * 4
     sets = []
     for s_ in range(2):
         bX = CudaDataBuffer.empty(ctx, np.float32, X.size)
@@ -464,13 +526,16 @@ def run_ours(args):
                      "eY": DNDArray(ShapedDataBufferView(bY, *Y.shape)), "hG": hG, "pin": _pG, "ev": ctx.event(), "ev_up": ctx.event()})
 
     def e2e_eager_step(st):
+        ctx.invalidate_caches()
         check(lib.dsc_buf_upload_async(st["bX"].handle, 0, hX.ctypes.data, X.size))
         check(lib.dsc_buf_upload_async(st["bY"].handle, 0, hY.ctypes.data, Y.size))
         L, dW, db = D.sharded_mlp_grad(comm, st["eX"], st["eY"], dWs, dbs)   # Sum_M inside returns the loss to the host
         comm.join()
         off = 0
-        for a in ([w.Buffer.DataBuffer for w in dW] + [v.Buffer for v in db]) if read_grads else []:
-            check(lib.dsc_buf_download_async(a.handle, 0, st["hG"].ctypes.data + 4 * off, a.Length))
+        for a in [w.Buffer.DataBuffer for w in dW] + [v.Buffer for v in db]:
+            lo_, hi_ = max(sl0, off), min(sl1, off + a.Length)     # this rank's slice of the concatenated adjoints
+            if hi_ > lo_:
+                check(lib.dsc_buf_download_async(a.handle, lo_ - off, st["hG"].ctypes.data + 4 * lo_, hi_ - lo_))
             off += a.Length
         ctx.sync()
         return float(L)
@@ -495,7 +560,7 @@ def run_ours(args):
         finally:
             st["graph"] = ctx.graph_end()
             st["loss"], backend.capture_scalars = backend.capture_scalars[0], None
-        st["outs"] = ([w.Buffer.DataBuffer for w in cW] + [v.Buffer for v in cb]) if read_grads else []
+        st["outs"] = [w.Buffer.DataBuffer for w in cW] + [v.Buffer for v in cb]
         st["keep"] = (cW, cb)
 
     def queue_upload(st):
@@ -506,7 +571,9 @@ def run_ours(args):
     def queue_download(st):
         off = 0
         for a in st["outs"]:
-            check(lib.dsc_copy_download(a.handle, 0, st["hG"].ctypes.data + 4 * off, a.Length))
+            lo_, hi_ = max(sl0, off), min(sl1, off + a.Length)
+            if hi_ > lo_:
+                check(lib.dsc_copy_download(a.handle, lo_ - off, st["hG"].ctypes.data + 4 * lo_, hi_ - lo_))
             off += a.Length
         check(lib.dsc_copy_download(st["loss"].handle, 0, st["hG"].ctypes.data + 4 * n_params, 1))
         check(lib.dsc_event_record_copy_down(ctx.handle, st["ev"]))   # downloads ride their own stream: PCIe is full duplex
@@ -532,12 +599,15 @@ def run_ours(args):
         return losses
 
     e2e_loop(4)
-    ctx.sync(); check(lib.dsc_copy_sync(ctx.handle)); D.barrier()
-    ctx.record(e0)
-    losses = e2e_loop(args.steps)
-    ctx.record(e1)
-    ctx.sync(); check(lib.dsc_copy_sync(ctx.handle)); D.barrier()
-    e2e_ms = D.max_over_ranks(ctx.elapsed_ms(e0, e1)) / args.steps
+    e2e_batches = []
+    for _ in range(5):
+        ctx.sync(); check(lib.dsc_copy_sync(ctx.handle)); D.barrier()
+        ctx.record(e0)
+        losses = e2e_loop(args.steps)
+        ctx.record(e1)
+        ctx.sync(); check(lib.dsc_copy_sync(ctx.handle)); D.barrier()
+        e2e_batches.append(D.max_over_ranks(ctx.elapsed_ms(e0, e1)) / args.steps)
+    e2e_ms = statistics.median(e2e_batches)
     loss_e2e = losses[-1]
     for st in sets:
         st["outs"] = None
@@ -552,7 +622,11 @@ def run_ours(args):
     rng = np.random.default_rng(0)
     Am = ShapedDataBufferView(rb.CreateDataBuffer((rng.random(rows * 1024) * 2 - 1).astype(np.float32)), rows, 1024)
     Bm = ShapedDataBufferView(rb.CreateDataBuffer((rng.random(1024 * 1024) * 2 - 1).astype(np.float32)), 1024, 1024)
-    gemm_ms = time_kernel(ctx, lambda: rb.Mul_M_M(Am, Bm), iters=20, flush=False)
+    def cold_gemm():
+        ctx.invalidate_caches()          # no operand-split companion survives from the previous launch: the split pre-pass is timed
+        return rb.Mul_M_M(Am, Bm)
+    gemm_ms = time_kernel(ctx, cold_gemm, iters=20, flush=False)
+    gemm_warm_ms = time_kernel(ctx, lambda: rb.Mul_M_M(Am, Bm), iters=20, flush=False)   # companions present, as in the step (written by the producer)
     gemm_flop = 2.0 * rows * 1024 * 1024
     achieved = gemm_flop / gemm_ms / 1e9
     peak3 = peaks["tf32x3_tflops"]
@@ -571,7 +645,10 @@ def run_ours(args):
     st = ctx.stats()
     roofline = {"bound": "tensor", "achieved": round(achieved, 2), "peak": round(peak3, 2), "unit": "TFLOP/s",
                 "frac": round(achieved / peak3, 4), "traffic": traffic, "traffic_source": traffic_src,
-                "kernel": f"Mul_M_M f32 {rows}x1024x1024 (hidden-layer GEMM of the step); includes the hi/lo operand split pre-pass",
+                "kernel": f"Mul_M_M f32 {rows}x1024x1024 (hidden-layer GEMM of the step); includes the hi/lo operand split pre-pass of both operands",
+                "achieved_with_operand_splits_present": round(gemm_flop / gemm_warm_ms / 1e9, 2),
+                "note": "in the step the split companion of the activations is written by the kernel that produces them (bias + tanh, tanh adjoint) "
+                        "and only the weights are split by a pre-pass; `achieved` is the conservative figure (both operands split inside the timed launch)",
                 "peak_source": "3xTF32 roofline = " + peaks["tf32x3_source"],
                 "gemm_path": {"tcgen05": st["gemm_tcgen05"], "simt": st["gemm_simt"], "dmma": st["gemm_dmma"]}}
 
@@ -588,17 +665,20 @@ def run_ours(args):
         "eager": {"value": round(1e3 / eager_ms, 3), "unit": "steps/s", "ms_per_step": round(eager_ms, 4),
                   "note": "same step driven op by op from Python through the C ABI (host-bound)"},
         "e2e": {"value": round(1e3 / e2e_ms, 3), "unit": "steps/s", "ms_per_step": round(e2e_ms, 4),
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "mode": "every rank: its X/Y rows host -> device every step and its loss -> host every step; rank 0 also reads all (all-reduced) "
-                        "adjoints back every step; the step is a CUDA-graph replay of the captured call sequence; copies of steps i+2 / i ride "
-                        "the copy stream while step i+1 computes (2 input sets)"},
+                "h2d_bytes_per_step": h2d_job, "d2h_bytes_per_step": d2h, "h2d_bytes_per_step_per_rank": h2d,
+                "mode": "every rank: its X/Y rows host -> device every step, its loss -> host every step, and its 1/N slice of the (all-reduced) "
+                        "adjoints -> host every step (byte counts are whole-job totals); the step is a CUDA-graph replay of the captured call sequence; "
+                        "copies of steps i+2 / i ride the copy streams while step i+1 computes (2 input sets); median of 5 batches of K steps"},
         "e2e_eager": {"value": round(1e3 / e2e_eager_ms, 3), "unit": "steps/s", "ms_per_step": round(e2e_eager_ms, 4),
-                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                      "h2d_bytes_per_step": h2d_job, "d2h_bytes_per_step": d2h,
                       "mode": "the same, but the step is driven op by op through the plugin interface (no graph, no copy/compute overlap)"},
         "gpu_launches": int(launches_per_step * args.steps),
         "launches_per_step": int(launches_per_step),
         "step_gflop": STEP_GFLOP, "step_tflops": round(STEP_GFLOP / world / graph_ms, 2),
         "loss": loss_graph, "loss_e2e": loss_e2e, "loss_e2e_eager": loss_e2e_eager, "adjoints_identical_on_all_ranks": adjoints_identical,
+        "adjoints_match_1gpu": adjoints_match_1gpu,
+        "timing": {"batches": TIMED_BATCHES, "steps_per_batch": args.steps, "ms_per_step_min": round(min(batch_ms), 4), "ms_per_step_max": round(max(batch_ms), 4),
+                   "reported": "median batch"},
         "clocks": clocks, "roofline": roofline, "peaks": peaks,
     }
     if not args.no_other:
@@ -614,31 +694,12 @@ def run_ours(args):
 
 
 def cpu_baseline():
-    """The oracle (port of the reference's call sequence over OpenBLAS) on the host cores, bounded sample."""
-    from oracle.backend import OracleBackend, get_num_threads, openblas_info, set_num_threads
-    from sigma.diffsharp_b200 import workloads as wl
-    from sigma.diffsharp_b200.config import DictBackendProvider, GlobalConfig
-    cores = os.cpu_count() or 1
-    set_num_threads(cores)
-    old = GlobalConfig.BackendProvider
-    GlobalConfig.BackendProvider = DictBackendProvider(OracleBackend(np.float32), OracleBackend(np.float64))
-    try:
-        sample_rows = GLOBAL_BATCH // 8
-        X, Y, Ws, bs = wl.mlp_inputs(LAYERS, GLOBAL_BATCH, row_range=(0, sample_rows))
-        dX, dY = wl.to_DM(X), wl.to_DM(Y)
-        dWs, dbs = [wl.to_DM(w) for w in Ws], [wl.to_DV(b) for b in bs]
-        wl.mlp_grad(dX, dY, dWs, dbs)
-        times = []
-        t_end = time.perf_counter() + 15.0
-        while len(times) < 3 or (time.perf_counter() < t_end and len(times) < 20):
-            t0 = time.perf_counter()
-            wl.mlp_grad(dX, dY, dWs, dbs)
-            times.append(time.perf_counter() - t0)
-        t_step = statistics.median(times) * (GLOBAL_BATCH / sample_rows)
-        return {"value": round(1.0 / t_step, 4), "unit": "steps/s", "cores": get_num_threads(), "kind": "port",
-                "sample": f"{len(times)} timed steps of {sample_rows}/{GLOBAL_BATCH} batch rows, scaled x8 (costs are linear in rows); {openblas_info()}"}
-    finally:
-        GlobalConfig.BackendProvider = old
+    """The oracle (port of the reference's call sequence over OpenBLAS) on the host cores: the FULL config-3 step, >= 3 timed
+    steps (at most 8, bounded by ~15 s), median."""
+    times, threads, info = _cpu_full_step_times(8, budget_s=15.0)
+    t_step = statistics.median(times)
+    return {"value": round(1.0 / t_step, 4), "unit": "steps/s", "cores": threads, "kind": "port", "ms_per_step": round(t_step * 1e3, 1),
+            "sample": f"the full step (all {GLOBAL_BATCH} batch rows), {len(times)} timed steps, median; {info}"}
 
 
 def main():

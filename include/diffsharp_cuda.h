@@ -168,9 +168,15 @@ DSC_API int dsc_flush_l2(dsc_ctx_t ctx);
  * tile when the tiles do not fill the GPU, fuse = in-kernel operand split (0 off, 1 single-CTA
  * kernels, 2 also the 2-CTA 256 x 256 kernel).  -1 = planner decides. */
 DSC_API int dsc_gemm_tune(dsc_ctx_t ctx, int bn, int pair, int split, int fuse);
+/* Which of the calls that follow Mul_M_M in the unchanged sequence (Add_M_M(., rows(b)) -> Map_F_M; the activation's adjoint
+ * chain) the float32 tensor-core kernel applies to the finished tile ITSELF instead of as a second pass over the product:
+ * 0 none, 1 (default) the ones measured to pay — bias rows without activation, ReL, the ReL chain —, 2 all (Tanh, Sigmoid and
+ * their chains too: correct and bit-identical, but the 8 epilogue warps become the bottleneck; kept for the parity tests). */
+DSC_API int dsc_gemm_epilogue(dsc_ctx_t ctx, int mode);
 /* The plan the float32 tensor-core GEMM makes for op(A)(m x k) op(B)(k x n) on a device with sm_count SMs — a pure
  * function (no GPU, no context), exported so that the schedule arithmetic is unit-tested on any machine.
- * a_direct / b_direct: the operand is addressable by TMA in place; bn, pair, split, fuse as in dsc_gemm_tune.
+ * a_direct / b_direct: the operand is addressable by TMA in place (2: and its operand-split companion exists already: no
+ * pre-pass, no in-kernel split for it); bn, pair, split, fuse as in dsc_gemm_tune.
  * out = {eligible, bn, pair, workers, chunks per tile, k-blocks, tiles_m, tiles_n, dp_waves, dp_extra, stream-K units,
  *        perm_s, base, rem, dp_tiles, perm_tiles, K ranges per cluster if the cluster exchange applies, a_fused, b_fused, 0} */
 DSC_API int dsc_gemm_plan(int sm_count, int m, int n, int k, int a_direct, int b_direct, int bn, int pair, int split, int fuse, int32_t out[20]);

@@ -128,6 +128,7 @@ _sig("dsc_graph_launch", ctx_t, C.c_uint64)
 _sig("dsc_graph_destroy", ctx_t, C.c_uint64)
 _sig("dsc_flush_l2", ctx_t)
 _sig("dsc_gemm_tune", ctx_t, C.c_int, C.c_int, C.c_int, C.c_int)
+_sig("dsc_gemm_epilogue", ctx_t, C.c_int)
 _sig("dsc_gemm_debug_stamps", ctx_t, P(C.c_uint64))
 _sig("dsc_gemm_plan", C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P(i32))
 _sig("dsc_buf_alloc", ctx_t, C.c_int, i32, P(buf_t))

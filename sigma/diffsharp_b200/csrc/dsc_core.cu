@@ -385,6 +385,8 @@ int dsc_create(int device, uint32_t flags, dsc_ctx_t* out) {
     {
         const char* e = getenv("DSC_FUSE");   // DSC_FUSE=0: same as DSC_FLAG_NO_FUSE (debugging)
         ctx->fuse = !(flags & DSC_FLAG_NO_FUSE) && !(e && *e == '0');
+        const char* g = getenv("DSC_GEMM_EPILOGUE");
+        if (g && *g >= '0' && *g <= '2') ctx->gemm_epilogue = *g - '0';
         const char* v = getenv("DSC_NVTX");
         ctx->nvtx = (flags & DSC_FLAG_NVTX) || (v && *v == '1');
     }
@@ -788,7 +790,8 @@ int dsc_copy_download(dsc_buf_t h, int32_t off, void* host, int32_t n) {
     if (!host) return fail(DSC_E_INVALID, "copy_download: null host pointer");
     Ctx* ctx = b->ctx;
     if (ctx->capturing) return fail(DSC_E_INVALID, "copy-stream transfers cannot be captured");
-    if (!b->block) return fail(DSC_E_INVALID, "copy_download: the buffer's value is still deferred (read it on the compute stream, or synchronise first)");
+    if (!b->block && b->lazy && b->lazy->result) DSC_TRY(buf_resolve(b));   // computed already (e.g. at the end of a captured step): adopt it, nothing is launched
+    if (!b->block) return fail(DSC_E_INVALID, "copy_download: the buffer's value is still deferred (dsc_flush / dsc_copy_wait_compute first)");
     size_t es = dtype_size(b->dtype);
     const char* src = reinterpret_cast<const char*>(b->block->ptr) + (b->off + off) * es;
     DSC_CUDA_CHECK(cudaMemcpyAsync(host, src, (size_t)n * es, cudaMemcpyDeviceToHost, ctx->copy_stream_down));

@@ -173,6 +173,18 @@ static int gemm_entry(dsc_ctx_t c, int ta, int tb, int32_t m, int32_t n, int32_t
     int eta = ta ? 1 : 0, etb = tb ? 1 : 0;
     take(A, eta, ta ? k : m, ta ? m : k, oa);
     take(B, etb, tb ? n : k, tb ? k : n, ob);
+    if (!Ch) return fail(DSC_E_INVALID, "null output handle pointer");
+    if (ctx->fuse && *Ch == 0 && (int64_t)m * n > 0 && k > 0) {
+        // The product is DEFERRED: the calls that follow it in the unchanged sequence — Add_M_M(., rows(b)) -> Map_F_M in the
+        // forward pass (AD.Float32.fs:2357, :2704), the activation's adjoint chain in the reverse sweep (:4238-4240,
+        // :4280-4281) — become its epilogue; any other consumer, or the next synchronisation point, runs the plain product.
+        LazyNode* nd = lazy_new(ctx, LZ_GEMM, dtype_of<T>::value, m * n);
+        nd->m = m; nd->n = n; nd->k = k; nd->ta = eta; nd->tb = etb;
+        lazy_set_operand(nd, 0, oa);
+        lazy_set_operand(nd, 1, ob);
+        if (bias) lazy_set_operand(nd, 2, bias);
+        return lazy_buf(ctx, nd, Ch);
+    }
     // hold the operands while they are being resolved (a deferred operand may be dropped by its handle meanwhile)
     LazyNode* hold = lazy_new(ctx, LZ_GEMM, dtype_of<T>::value, m * n);
     hold->consumed = true;

@@ -59,6 +59,7 @@
 #include <type_traits>
 
 #include "dsc_internal.cuh"
+#include "dsc_ops.cuh"
 
 namespace dsc {
 namespace tf32x3 {
@@ -297,6 +298,13 @@ struct Params {
     int kcluster;              // > 1: aligned split-K whose K ranges of a tile are the CTAs (pairs) of ONE cluster; the partial
                                // tiles are exchanged through distributed shared memory instead of workspace slots
     unsigned long long* stamps; // null, or 8 slots for %globaltimer at the phase boundaries as CTA 0 sees them (dsc_gemm_debug_stamps)
+    // Epilogue (GemmEpilogue, dsc_internal.cuh): what the calls that FOLLOW Mul_M_M in the unchanged sequence do with the
+    // product, applied to the finished tile in registers — same roundings as the separate kernels (dsc_ops.cuh)
+    int ep_mode, ep_op;
+    const float* ep_vec;       // GEMM_EP_BIAS_ACT: v[j]
+    const float* ep_aux;       // GEMM_EP_CHAIN: p[i, j]
+    float* ep_out2;            // GEMM_EP_BIAS_ACT with an activation: h
+    float* ep_lo;              // operand-split companion of the last output, or null
 };
 __device__ __forceinline__ void stamp(const Params& p, int slot) {
     if (p.stamps != nullptr && blockIdx.x == 0) {
@@ -323,6 +331,141 @@ __device__ __forceinline__ void unit_at(const Params& p, int i, int dp_units, in
     }
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }
+
+// ---- the finished tile leaves the registers ---------------------------------------------------------
+// v = four consecutive elements of row `row` (< m) starting at column `col`, bias[i] of Mul_M_M_Add_V_MCols already added.
+//   GEMM_EP_NONE    : C = v
+//   GEMM_EP_BIAS_ACT: z = v + vec[col..] -> C;  h = f_op(z) -> out2 (op < 0: none)     Add_M_M(., rows(vec)) -> Map_F_M
+//   GEMM_EP_CHAIN   : y = chain_op(v, aux[row, col..]) -> C                             the adjoint chains
+// and, when asked for, lo = dsc_lo_of(last output): the operand-split companion for the GEMM that reads it next.
+// Activations fused here: Tanh, Sigmoid, ReL (the host runs any other op-code as a second pass over C).
+// The epilogue arithmetic is kept OUT of line: the finished tile leaves the registers as fully unrolled straight-line code
+// (the accumulators are register-indexed), and inlining tanhf / coshf per element there grows the kernel past the
+// instruction cache (measured: 2.5x slower products).  One call handles 16 consecutive columns of a row: its loads are issued
+// together, then the math, then the stores.
+struct EpArgs {           // what the out-of-line epilogue needs of Params, by value (registers)
+    float* C;
+    const float* vec;
+    const float* aux;
+    float* out2;
+    float* lo;
+    int n, vec4, mode, op;
+};
+__device__ __forceinline__ EpArgs ep_args(const Params& p) { return EpArgs{p.C, p.ep_vec, p.ep_aux, p.ep_out2, p.ep_lo, p.n, p.vec4, p.ep_mode, p.ep_op}; }
+
+template <int OP, int N>
+__device__ __forceinline__ void ep_bias_act(const EpArgs& p, size_t base, int col, float (&v)[N], bool full) {
+    float b[N];
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) {
+        if (full) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.vec + col) + q);
+            b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[4 * q + j] = (col + 4 * q + j < p.n) ? __ldg(p.vec + col + 4 * q + j) : 0.f;
+        }
+    }
+    float h[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        v[j] = v[j] + b[j];
+        h[j] = OP >= 0 ? unary_op<(OP >= 0 ? OP : DSC_OP_TANH)>(v[j]) : v[j];
+    }
+    if (full) {
+#pragma unroll
+        for (int q = 0; q < N / 4; ++q) {
+            reinterpret_cast<float4*>(p.C + base)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            if (OP >= 0) reinterpret_cast<float4*>(p.out2 + base)[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+            if (p.lo) reinterpret_cast<float4*>(p.lo + base)[q] = make_float4(dsc_lo_of(h[4 * q]), dsc_lo_of(h[4 * q + 1]), dsc_lo_of(h[4 * q + 2]), dsc_lo_of(h[4 * q + 3]));
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+            if (col + j < p.n) {
+                p.C[base + j] = v[j];
+                if (OP >= 0) p.out2[base + j] = h[j];
+                if (p.lo) p.lo[base + j] = dsc_lo_of(h[j]);
+            }
+    }
+}
+template <int KIND, int N>
+__device__ __forceinline__ void ep_chain(const EpArgs& p, size_t base, int col, float (&v)[N], bool full) {
+    float a[N];
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) {
+        if (full) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.aux + base) + q);
+            a[4 * q] = t.x; a[4 * q + 1] = t.y; a[4 * q + 2] = t.z; a[4 * q + 3] = t.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[4 * q + j] = (col + 4 * q + j < p.n) ? __ldg(p.aux + base + 4 * q + j) : 0.f;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] = chain_op<KIND>(v[j], a[j]);
+    if (full) {
+#pragma unroll
+        for (int q = 0; q < N / 4; ++q) {
+            reinterpret_cast<float4*>(p.C + base)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            if (p.lo) reinterpret_cast<float4*>(p.lo + base)[q] = make_float4(dsc_lo_of(v[4 * q]), dsc_lo_of(v[4 * q + 1]), dsc_lo_of(v[4 * q + 2]), dsc_lo_of(v[4 * q + 3]));
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+            if (col + j < p.n) {
+                p.C[base + j] = v[j];
+                if (p.lo) p.lo[base + j] = dsc_lo_of(v[j]);
+            }
+    }
+}
+template <int N>
+__device__ __forceinline__ void ep_dispatch(const EpArgs& p, int row, int col, float (&v)[N]) {
+    const size_t base = (size_t)row * p.n + col;
+    const bool full = p.vec4 && col + N <= p.n;
+    if (p.mode == GEMM_EP_BIAS_ACT) {
+        switch (p.op) {
+            case DSC_OP_TANH: ep_bias_act<DSC_OP_TANH, N>(p, base, col, v, full); break;
+            case DSC_OP_SIGMOID: ep_bias_act<DSC_OP_SIGMOID, N>(p, base, col, v, full); break;
+            case DSC_OP_REL: ep_bias_act<DSC_OP_REL, N>(p, base, col, v, full); break;
+            default: ep_bias_act<-1, N>(p, base, col, v, full); break;
+        }
+    } else {
+        switch (p.op) {
+            case DSC_FUSED_TANH_BWD: ep_chain<DSC_FUSED_TANH_BWD, N>(p, base, col, v, full); break;
+            case DSC_FUSED_SIGMOID_BWD: ep_chain<DSC_FUSED_SIGMOID_BWD, N>(p, base, col, v, full); break;
+            default: ep_chain<DSC_FUSED_RELU_BWD, N>(p, base, col, v, full); break;
+        }
+    }
+}
+// 16 / 4 consecutive elements of row `row` (< m) from column `col`, bias[i] of Mul_M_M_Add_V_MCols already added, under a
+// non-trivial epilogue
+__device__ __noinline__ void store16_ep(EpArgs p, int row, int col, float4 q0, float4 q1, float4 q2, float4 q3) {
+    if (col >= p.n) return;
+    float v[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+    ep_dispatch<16>(p, row, col, v);
+}
+__device__ __noinline__ void store4_ep(EpArgs p, int row, int col, float4 q0) {
+    if (col >= p.n) return;
+    float v[4] = {q0.x, q0.y, q0.z, q0.w};
+    ep_dispatch<4>(p, row, col, v);
+}
+// four consecutive elements: plain store, or the epilogue out of line
+__device__ __forceinline__ void store_quad(const Params& p, int row, int col, float v0, float v1, float v2, float v3) {
+    if (col >= p.n) return;
+    if (p.ep_mode != GEMM_EP_NONE) {
+        store4_ep(ep_args(p), row, col, make_float4(v0, v1, v2, v3));
+        return;
+    }
+    float* dst = p.C + (size_t)row * p.n + col;
+    if (p.vec4 && col + 4 <= p.n) *reinterpret_cast<float4*>(dst) = make_float4(v0, v1, v2, v3);
+    else {
+        dst[0] = v0;
+        if (col + 1 < p.n) dst[1] = v1;
+        if (col + 2 < p.n) dst[2] = v2;
+        if (col + 3 < p.n) dst[3] = v3;
+    }
+}
 
 // ---- in-kernel operand split ---------------------------------------------------------------------
 // lo = rna_tf32(x - trunc_tf32(x)) for one fp32 word as the tensor core will see it: x - hi is exact;
@@ -644,17 +787,17 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                 const int col0 = n0 + half * HALF;
                 if (row < p.m) {
                     const float bv = (p.bias != nullptr) ? p.bias[row] : 0.f;
-                    float* crow = p.C + (size_t)row * p.n;
+                    if (p.ep_mode == GEMM_EP_NONE) {
 #pragma unroll
-                    for (int c = 0; c < HALF; c += 4) {
-                        const int col = col0 + c;
-                        if (p.vec4 && col + 4 <= p.n) {
-                            *reinterpret_cast<float4*>(crow + col) = make_float4(acc[c] + bv, acc[c + 1] + bv, acc[c + 2] + bv, acc[c + 3] + bv);
-                        } else {
+                        for (int c = 0; c < HALF; c += 4) store_quad(p, row, col0 + c, acc[c] + bv, acc[c + 1] + bv, acc[c + 2] + bv, acc[c + 3] + bv);
+                    } else {
+                        const EpArgs ea = ep_args(p);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                if (col + j < p.n) crow[col + j] = acc[c + j] + bv;
-                        }
+                        for (int c = 0; c < HALF; c += 16)
+                            store16_ep(ea, row, col0 + c, make_float4(acc[c] + bv, acc[c + 1] + bv, acc[c + 2] + bv, acc[c + 3] + bv),
+                                       make_float4(acc[c + 4] + bv, acc[c + 5] + bv, acc[c + 6] + bv, acc[c + 7] + bv),
+                                       make_float4(acc[c + 8] + bv, acc[c + 9] + bv, acc[c + 10] + bv, acc[c + 11] + bv),
+                                       make_float4(acc[c + 12] + bv, acc[c + 13] + bv, acc[c + 14] + bv, acc[c + 15] + bv));
                     }
                 }
             } else if (p.kcluster > 1) {
@@ -698,18 +841,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                                 const float4 v = (src == j) ? make_float4(acc[a0], acc[a0 + 1], acc[a0 + 2], acc[a0 + 3]) : recv[(src * P4 + c) * 256];
                                 sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
                             }
-                            if (row < p.m) {
-                                const int cc = n0 + half * HALF + a0;
-                                float* dst = p.C + (size_t)row * p.n + cc;
-                                if (p.vec4 && cc + 4 <= p.n) {
-                                    *reinterpret_cast<float4*>(dst) = make_float4(sum.x + bv, sum.y + bv, sum.z + bv, sum.w + bv);
-                                } else {
-                                    if (cc < p.n) dst[0] = sum.x + bv;
-                                    if (cc + 1 < p.n) dst[1] = sum.y + bv;
-                                    if (cc + 2 < p.n) dst[2] = sum.z + bv;
-                                    if (cc + 3 < p.n) dst[3] = sum.w + bv;
-                                }
-                            }
+                            if (row < p.m) store_quad(p, row, n0 + half * HALF + a0, sum.x + bv, sum.y + bv, sum.z + bv, sum.w + bv);
                         }
                     }
                 };
@@ -765,7 +897,6 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                     // thread t reduces what thread t of every segment parked: its own row, columns half * HALF + 4 c4 ...
                     const int row = m0 + trow;
                     const float bv = (p.bias != nullptr && row < p.m) ? p.bias[row] : 0.f;
-                    float* crow = p.C + (size_t)row * p.n + n0 + half * HALF;
                     for (int c4 = c4_0; c4 < c4_1; c4 += 8) {
                         float4 sum[8];
 #pragma unroll
@@ -789,16 +920,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
                                 if (c4 + q >= c4_1) continue;
-                                const int cc = n0 + half * HALF + (c4 + q) * 4;
-                                float* dst = crow + (c4 + q) * 4;
-                                if (p.vec4 && cc + 4 <= p.n) {
-                                    *reinterpret_cast<float4*>(dst) = make_float4(sum[q].x + bv, sum[q].y + bv, sum[q].z + bv, sum[q].w + bv);
-                                } else {
-                                    if (cc < p.n) dst[0] = sum[q].x + bv;
-                                    if (cc + 1 < p.n) dst[1] = sum[q].y + bv;
-                                    if (cc + 2 < p.n) dst[2] = sum[q].z + bv;
-                                    if (cc + 3 < p.n) dst[3] = sum[q].w + bv;
-                                }
+                                store_quad(p, row, n0 + half * HALF + (c4 + q) * 4, sum[q].x + bv, sum[q].y + bv, sum[q].z + bv, sum[q].w + bv);
                             }
                         }
                     }
@@ -851,15 +973,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                             const int r = m0 + f / F4_PER_ROW, cc = n0 + (f % F4_PER_ROW) * 4;
                             if (r < p.m) {
                                 const float bv = (p.bias != nullptr) ? p.bias[r] : 0.f;
-                                float* dst = p.C + (size_t)r * p.n + cc;
-                                if (p.vec4 && cc + 4 <= p.n) {
-                                    *reinterpret_cast<float4*>(dst) = make_float4(sum[q].x + bv, sum[q].y + bv, sum[q].z + bv, sum[q].w + bv);
-                                } else {
-                                    if (cc < p.n) dst[0] = sum[q].x + bv;
-                                    if (cc + 1 < p.n) dst[1] = sum[q].y + bv;
-                                    if (cc + 2 < p.n) dst[2] = sum[q].z + bv;
-                                    if (cc + 3 < p.n) dst[3] = sum[q].w + bv;
-                                }
+                                store_quad(p, r, cc, sum[q].x + bv, sum[q].y + bv, sum[q].z + bv, sum[q].w + bv);
                             }
                         }
                     }
@@ -1113,6 +1227,7 @@ static int split_blocks(const OperandPlan& o, int rows, int k, int kp) {
 struct PlanIn {
     int sm_count, m, n, k, num_kb, cpt;
     bool a_direct, b_direct;      // operand is addressable by TMA in place (plan_operand)
+    bool a_ready, b_ready;        // ... and its operand-split companion already exists (written by the producing kernel, or by an earlier product)
     int fuse;                     // 0: never split in the kernel; 1: single-CTA kernels may; 2: also the WIDE pair kernel
     int force_bn, force_pair, force_split;
     bool allow_wide;
@@ -1150,12 +1265,13 @@ static bool make_plan(const PlanIn& in, PlanOut& out) {
             const int ctas_per_worker = pr ? 2 : 1;
             const int brows = pr ? c / 2 : c;
             const bool can_fuse = fuse_env && has_converters(c, pr);
-            bool fa = can_fuse && in.a_direct, fb = can_fuse && in.b_direct;
+            bool fa = can_fuse && in.a_direct && !in.a_ready, fb = can_fuse && in.b_direct && !in.b_ready;   // a ready companion is simply loaded
             if (pr) fa = fb = (fa && fb);   // the pair kernel splits both operands in the kernel or neither
             const double bytes_kb = (double)BM * (fa ? 128.0 : 256.0) + (double)brows * (fb ? 128.0 : 256.0);
             const double smem_kb = (double)BM * (fa ? 6.0 : 5.0) + (double)brows * (fb ? 6.0 : 5.0);
             // pre-pass for the operands that are not split in the kernel: 8 bytes per element at ~5 TB/s + launch
-            const double pre = (fa && fb) ? 0.0 : 2000.0 * (3.0 + ((fa ? 0.0 : (double)m * k) + (fb ? 0.0 : (double)n * k)) * 8.0 / 5.0e6);
+            const double pre_elems = ((fa || in.a_ready) ? 0.0 : (double)m * k) + ((fb || in.b_ready) ? 0.0 : (double)n * k);
+            const double pre = pre_elems == 0.0 ? 0.0 : 2000.0 * (3.0 + pre_elems * 8.0 / 5.0e6);
             auto per_kb = [&](double active_workers) {
                 double t = 6.0 * c;
                 if (smem_kb > t) t = smem_kb;
@@ -1253,6 +1369,16 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, MatRef Am
     PlanIn pin;
     pin.sm_count = ctx->sm_count; pin.m = m; pin.n = n; pin.k = k; pin.num_kb = num_kb; pin.cpt = cpt;
     pin.a_direct = pa.direct; pin.b_direct = pb.direct;
+    // Operand-split companions (Block::lo): present when the kernel that produced the matrix wrote one next to it (bias +
+    // activation, adjoint chains, GEMM epilogues) or an earlier product split it and nobody has written the block since.
+    auto companion = [&](const MatRef& M, size_t count, bool direct) -> float* {
+        Block* blk = M.block;
+        if (!direct || !blk || !blk->lo || blk->lo_epoch != ctx->cache_epoch || M.off < blk->lo_begin || M.off + count > blk->lo_end) return nullptr;
+        return reinterpret_cast<float*>(blk->lo->ptr) + M.off;
+    };
+    float* a_comp = companion(Am, (size_t)m * k, pa.direct);
+    float* b_comp = companion(Bm, (size_t)n * k, pb.direct);
+    pin.a_ready = a_comp != nullptr; pin.b_ready = b_comp != nullptr;
     pin.fuse = fuse_env; pin.force_bn = force_bn; pin.force_pair = force_pair; pin.force_split = force_split;
     pin.allow_wide = allow_wide;
     PlanOut pout;
@@ -1273,11 +1399,11 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, MatRef Am
     p.base = sk_units_total / grid;
     p.rem = sk_units_total % grid;
     static const bool debug_plan = [] { const char* e = getenv("DSC_GEMM_DEBUG"); return e && *e == '1'; }();
-    bool a_fused = fuse_env && has_converters(bn, pair) && pa.direct, b_fused = fuse_env && has_converters(bn, pair) && pb.direct;
+    bool a_fused = fuse_env && has_converters(bn, pair) && pa.direct && !a_comp, b_fused = fuse_env && has_converters(bn, pair) && pb.direct && !b_comp;
     if (pair) a_fused = b_fused = (a_fused && b_fused);
     if (debug_plan)
-        fprintf(stderr, "[dsc gemm] m=%d n=%d k=%d ta=%d tb=%d: BN=%d pair=%d grid=%d cpt=%d dp_waves=%d dp_extra=%d sk_units=%d perm_s=%d fused=%d%d\n", m, n, k, ta, tb, bn,
-                (int)pair, grid, cpt, dp_waves, dp_extra, sk_units_total, perm_s, (int)a_fused, (int)b_fused);
+        fprintf(stderr, "[dsc gemm] m=%d n=%d k=%d ta=%d tb=%d: BN=%d pair=%d grid=%d cpt=%d dp_waves=%d dp_extra=%d sk_units=%d perm_s=%d fused=%d%d ready=%d%d ep=%d\n", m, n, k, ta, tb, bn,
+                (int)pair, grid, cpt, dp_waves, dp_extra, sk_units_total, perm_s, (int)a_fused, (int)b_fused, (int)(a_comp != nullptr), (int)(b_comp != nullptr), ep ? ep->mode : 0);
     // Aligned split-K whose K ranges fit one cluster (<= 8 CTAs) and whose clusters are all resident at once:
     // the partial tiles go through distributed shared memory (no workspace round trip, no tickets).
     p.kcluster = 0;
@@ -1300,23 +1426,42 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, MatRef Am
     DSC_TRY(ensure_gemm_tickets(ctx, (size_t)tiles * (pair ? 2 : 1)));
     p.tickets = ctx->gemm_tickets;
 
-    const size_t a_floats = a_fused ? 0 : (pa.ws_floats + 255) & ~size_t(255), b_floats = b_fused ? 0 : (pb.ws_floats + 255) & ~size_t(255);
+    // Where each operand's lo plane lives: a ready companion; a NEW companion attached to the operand's block (direct operands:
+    // the split below fills it and later products of the same matrix find it); or the context workspace (operands TMA cannot
+    // address in place: hi + lo padded planes).
+    auto new_companion = [&](const MatRef& M, size_t count) -> float* {
+        Block* blk = M.block;
+        if (!blk) return nullptr;
+        if (!blk->lo) {
+            Block* lo = nullptr;
+            if (pool_alloc(ctx, blk->bytes, &lo) != DSC_OK) return nullptr;
+            blk->lo = lo;
+        }
+        blk->lo_epoch = ctx->cache_epoch;
+        blk->lo_begin = M.off;
+        blk->lo_end = M.off + count;
+        return reinterpret_cast<float*>(blk->lo->ptr) + M.off;
+    };
+    const bool a_split = !a_fused && !a_comp, b_split = !b_fused && !b_comp;   // this call runs the split for the operand
+    if (a_split && pa.direct) a_comp = new_companion(Am, (size_t)m * k);
+    if (b_split && pb.direct) b_comp = new_companion(Bm, (size_t)n * k);
+    const size_t a_floats = (a_fused || a_comp) ? 0 : (pa.ws_floats + 255) & ~size_t(255), b_floats = (b_fused || b_comp) ? 0 : (pb.ws_floats + 255) & ~size_t(255);
     const size_t planes_bytes = (a_floats + b_floats) * sizeof(float);
     const size_t slot_bytes = (size_t)grid * (pair ? 2 : 1) * 2 * BM * bn * sizeof(float);
     DSC_TRY(ensure_gemm_ws(ctx, planes_bytes + slot_bytes + 2048));
     char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ctx->gemm_ws) + 1023) & ~uintptr_t(1023));
     float* ws = reinterpret_cast<float*>(base);
     // direct: [lo]; planes: [hi | lo]
-    float* a_lo = pa.direct ? ws : ws + (size_t)m * kp;
-    float* b_lo = pb.direct ? ws + a_floats : ws + a_floats + (size_t)n * kp;
+    float* a_lo = a_comp ? a_comp : (pa.direct ? ws : ws + (size_t)m * kp);
+    float* b_lo = b_comp ? b_comp : (pb.direct ? ws + a_floats : ws + a_floats + (size_t)n * kp);
     const float* a_hi = pa.direct ? A : ws;
     const float* b_hi = pb.direct ? B : ws + a_floats;
     p.slots = reinterpret_cast<float*>(base + planes_bytes);
 
-    // ---- (1) split pre-pass: only for the operands the kernel does not split itself ----
-    if (!a_fused || !b_fused) {
-        SplitJob ja{A, pa.direct ? nullptr : ws, a_lo, m, pa.mode, a_fused ? 0 : split_blocks(pa, m, k, kp)};
-        SplitJob jb{B, pb.direct ? nullptr : ws + a_floats, b_lo, n, pb.mode, b_fused ? 0 : split_blocks(pb, n, k, kp)};
+    // ---- (1) split pre-pass: only for the operands that have no lo plane yet and that the kernel does not split itself ----
+    if (a_split || b_split) {
+        SplitJob ja{A, pa.direct ? nullptr : ws, a_lo, m, pa.mode, a_split ? split_blocks(pa, m, k, kp) : 0};
+        SplitJob jb{B, pb.direct ? nullptr : ws + a_floats, b_lo, n, pb.mode, b_split ? split_blocks(pb, n, k, kp) : 0};
         split_pair_kernel<<<ja.blocks + jb.blocks, 256, 0, ctx->stream>>>(ja, jb, k, kp);
         DSC_LAUNCH_CHECK(ctx);
     }
@@ -1324,6 +1469,27 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, MatRef Am
     // ---- (2) tensor-core kernel ----
     p.C = C;
     p.bias = bias;
+    p.ep_mode = GEMM_EP_NONE; p.ep_op = -1; p.ep_vec = nullptr; p.ep_aux = nullptr; p.ep_out2 = nullptr; p.ep_lo = nullptr;
+    bool ep_in_kernel = false;
+    if (ep && ep->mode != GEMM_EP_NONE) {
+        // The kernel can apply bias rows (+ Tanh / Sigmoid / ReL) and the three adjoint chains to the finished tile.  Whether it
+        // SHOULD is a measured decision (dsc_gemm_epilogue): the tile is drained by 8 warps per SM, one thread per row, and
+        // tanhf / coshf per element make those warps — not the tensor pipe — the bottleneck (8192 x 1024 x 1024 + bias + tanh:
+        // 115-125 us fused against 75 + 14.5 us as two kernels, the second one HBM-bound with 64 warps per SM).  Default
+        // (mode 1): only the cheap epilogues run in the kernel — bias rows without activation, ReL and its adjoint chain;
+        // mode 2: all of them (parity tests); mode 0: none.
+        const int mode = ctx->gemm_epilogue;
+        const bool cheap = (ep->mode == GEMM_EP_BIAS_ACT && (ep->op < 0 || ep->op == DSC_OP_REL)) || (ep->mode == GEMM_EP_CHAIN && ep->op == DSC_FUSED_RELU_BWD);
+        const bool able = ep->mode == GEMM_EP_CHAIN || ep->op < 0 || ep->op == DSC_OP_TANH || ep->op == DSC_OP_SIGMOID || ep->op == DSC_OP_REL;
+        if (able && (mode == 2 || (mode == 1 && cheap))) {
+            ep_in_kernel = true;
+            p.ep_mode = ep->mode; p.ep_op = ep->op;
+            p.ep_vec = reinterpret_cast<const float*>(ep->vec);
+            p.ep_aux = reinterpret_cast<const float*>(ep->aux);
+            p.ep_out2 = reinterpret_cast<float*>(ep->out2);
+            p.ep_lo = ep->lo;
+        }
+    }
     p.vec4 = ((n % 4) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
     p.a_mn = pa.mn_major ? 1 : 0;
     p.b_mn = pb.mn_major ? 1 : 0;
@@ -1367,7 +1533,7 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, MatRef Am
     }
     if (s != DSC_OK) return s;
     ctx->stats.gemm_tcgen05++;
-    return (ep && ep->mode != GEMM_EP_NONE) ? 2 : DSC_OK;   // 2: product stored, the caller applies the epilogue as a second pass
+    return (ep && ep->mode != GEMM_EP_NONE && !ep_in_kernel) ? 2 : DSC_OK;   // 2: product stored, the caller applies the epilogue as a second pass
 }
 
 }  // namespace dsc
@@ -1384,6 +1550,7 @@ extern "C" int dsc_gemm_plan(int sm_count, int m, int n, int k, int a_direct, in
     pin.num_kb = kp / BK;
     pin.cpt = (pin.num_kb + kChunkKb - 1) / kChunkKb;
     pin.a_direct = a_direct != 0; pin.b_direct = b_direct != 0;
+    pin.a_ready = a_direct == 2; pin.b_ready = b_direct == 2;   // 2: direct and its operand-split companion exists already
     pin.fuse = fuse < 0 ? 1 : fuse;
     pin.force_bn = bn > 0 ? bn : 0;
     pin.force_pair = pair < 0 ? -1 : (pair != 0);
@@ -1395,7 +1562,7 @@ extern "C" int dsc_gemm_plan(int sm_count, int m, int n, int k, int a_direct, in
     const int tiles_n = (n + po.bn - 1) / po.bn;
     const long tiles = (long)tiles_m * tiles_n;
     auto has_converters = [&](int c, bool pr) { return pr ? (pin.allow_wide && c == 256) : c < 256; };
-    bool a_fused = pin.fuse && has_converters(po.bn, po.pair) && pin.a_direct, b_fused = pin.fuse && has_converters(po.bn, po.pair) && pin.b_direct;
+    bool a_fused = pin.fuse && has_converters(po.bn, po.pair) && pin.a_direct && !pin.a_ready, b_fused = pin.fuse && has_converters(po.bn, po.pair) && pin.b_direct && !pin.b_ready;
     if (po.pair) a_fused = b_fused = (a_fused && b_fused);
     const bool wide = po.pair && po.bn == 256 && a_fused && b_fused;
     const int sp = po.perm_s;
@@ -1414,6 +1581,14 @@ extern "C" int dsc_gemm_debug_stamps(dsc_ctx_t c, uint64_t out[8]) {
     if (!ctx->gemm_stamps) return fail(DSC_E_INVALID, "no GEMM time stamps: set DSC_GEMM_STAMPS=1 before the first product");
     DSC_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     DSC_CUDA_CHECK(cudaMemcpy(out, ctx->gemm_stamps, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return DSC_OK;
+}
+
+extern "C" int dsc_gemm_epilogue(dsc_ctx_t c, int mode) {
+    using namespace dsc;
+    if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
+    if (mode < 0 || mode > 2) return fail(DSC_E_INVALID, "dsc_gemm_epilogue: mode must be 0, 1 or 2");
+    as_ctx(c)->gemm_epilogue = mode;
     return DSC_OK;
 }
 

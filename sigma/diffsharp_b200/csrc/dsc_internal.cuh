@@ -151,6 +151,7 @@ struct Ctx {
     void* gemm_ws = nullptr;
     size_t gemm_ws_bytes = 0;
     int gemm_force_bn = -1, gemm_force_pair = -1, gemm_force_split = -1, gemm_force_fuse = -1;   // dsc_gemm_tune; -1 = planner decides
+    int gemm_epilogue = 1;       // dsc_gemm_epilogue: which epilogues the float32 tensor-core kernel applies itself (0 none, 1 the cheap ones, 2 all)
     unsigned long long* gemm_stamps = nullptr;   // %globaltimer at the phase boundaries of the last tensor-core GEMM (DSC_GEMM_STAMPS=1)
     unsigned int* gemm_tickets = nullptr;   // one arrival counter per output tile (stream-K fix-up), zero between launches
     size_t gemm_tickets_n = 0;
@@ -296,8 +297,6 @@ template <typename T> int ew_rows(Ctx*, int bop, int act, int m, int n, const T*
 template <typename T> int transpose_launch(Ctx* ctx, const T* A, T* B, int m, int n);             // dsc_layout.cu
 template <typename T> int repeat_rows_launch(Ctx* ctx, const T* v, T* out, int m, int n);
 int fill_raw(Ctx* ctx, int dtype, void* base, size_t n, double v);                                // dsc_core.cu
-// lo[i] = rna_tf32(x[i] - trunc_tf32(x[i]))  (dsc_gemm_tf32x3.cu)
-int split_lo_launch(Ctx* ctx, const float* x, float* lo, size_t n);
 
 // ---- typed implementations (one template per op, instantiated for float and double) -------
 // A matrix operand: its device window and the block behind it (the float32 tensor-core GEMM keeps / finds the operand-split

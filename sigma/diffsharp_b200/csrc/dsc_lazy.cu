@@ -175,6 +175,20 @@ static int materialize_typed(LazyNode* nd, Block* out) {
     Ctx* ctx = nd->ctx;
     T* y = reinterpret_cast<T*>(out->ptr);
     const size_t n = (size_t)nd->len;
+    if (nd->kind == LZ_ADD_ROWS && nd->src[0].node && nd->src[0].node->kind == LZ_GEMM && !nd->src[0].node->result) {
+        // z = (A B) + rows(v) with the product still deferred (the output layer: its sum feeds Sub_M_M, not an activation):
+        // the bias joins the product's epilogue and the bare product is never stored
+        LazyNode* g = nd->src[0].node;
+        for (int i = 0; i < g->nsrc; ++i) DSC_TRY(operand_resolve(ctx, g->src[i]));
+        DSC_TRY(operand_resolve(ctx, nd->src[1]));
+        GemmEpilogue ep;
+        ep.mode = GEMM_EP_BIAS_ACT;
+        ep.op = -1;
+        ep.vec = operand_ptr<T>(nd->src[1]);
+        g->consumed = true;
+        return gemm_run<T>(ctx, g->ta, g->tb, g->m, g->n, g->k, operand_mat<T>(g->src[0]), operand_mat<T>(g->src[1]),
+                           g->nsrc > 2 ? operand_ptr<T>(g->src[2]) : nullptr, y, &ep);
+    }
     for (int i = 0; i < nd->nsrc; ++i) DSC_TRY(operand_resolve(ctx, nd->src[i]));
     switch (nd->kind) {
         case LZ_ZERO:
@@ -189,7 +203,8 @@ static int materialize_typed(LazyNode* nd, Block* out) {
         case LZ_SECH: return ew_sech<T>(ctx, operand_ptr<T>(nd->src[0]), y, n);
         case LZ_HAD: return ew_map2<T>(ctx, DSC_OP_MUL, operand_ptr<T>(nd->src[0]), operand_ptr<T>(nd->src[1]), y, n);
         case LZ_SCALAR: return ew_scalar<T>(ctx, nd->op, (T)nd->s, operand_ptr<T>(nd->src[0]), y, n);
-        case LZ_GEMM: return gemm_run<T>(ctx, nd->ta, nd->tb, nd->m, nd->n, nd->k, operand_mat<T>(nd->src[0]), operand_mat<T>(nd->src[1]), operand_ptr<T>(nd->src[2]), y, nullptr);
+        case LZ_GEMM: return gemm_run<T>(ctx, nd->ta, nd->tb, nd->m, nd->n, nd->k, operand_mat<T>(nd->src[0]), operand_mat<T>(nd->src[1]),
+                                         nd->nsrc > 2 ? operand_ptr<T>(nd->src[2]) : nullptr, y, nullptr);
     }
     return fail(DSC_E_INVALID, "unknown deferred operation %d", nd->kind);
 }

@@ -387,3 +387,152 @@ def test_fused_bias_activation_matches_the_unfused_sequence(cuda_provider, cuda_
     for f, u in zip(outs[0], outs[1]):
         assert np.array_equal(f, u)
     assert np.array_equal(outs[0][3], np.tile(v, (m, 1)))
+
+
+# ---- deferred evaluation inside the library (csrc/dsc_lazy.cu) ---------------------------------------------------------
+def _act_loss_grads(act, X, Y, W, b):
+    """grad of Sum(E .* E), E = act(X W + rows(b)) - Y, with respect to W and b, through the AD mirror on the installed backend"""
+    from sigma.diffsharp_b200 import ad, workloads as wl
+    dX, dY = wl.to_DM(X), wl.to_DM(Y)
+
+    def f(Wb):
+        Wm, bv = Wb
+        Z = dX * Wm + ad.DNDArray.OfRows(dX.Rows, bv, ad.Backend(dX))
+        E = act(Z) - dY
+        return ad.had(E, E).Sum()
+    i = ad.GlobalTagger.Next()
+    Wr, br = ad.makeReverse(i, wl.to_DM(W)), ad.makeReverse(i, wl.to_DV(b))
+    L = f((Wr, br))
+    ad.reverseProp(ad.DNumber(1, L.dtype), L)
+    return float(L), Wr.A.ToArray(), br.A.ToArray()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("actname", ["tanh", "sigmoid", "reLU"])
+@pytest.mark.parametrize("shape", [(37, 19, 23), (256, 96, 64)])
+def test_adjoint_chains_fused_equal_unfused(cuda_provider, cuda_provider_nofuse, oracle_provider, use_provider, dtype, actname, shape):
+    """The tanh (AD.Float32.fs:4238-4240), sigmoid (:4281) and ReLU (:4280) adjoint chains, the bias broadcast + activation and
+    had(E, E).Sum() issued by the UNCHANGED call sequence: recognised inside the library and run as single kernels, bit for bit
+    what the same sequence gives with DSC_FLAG_NO_FUSE, and within tolerance of the oracle.  The second shape reaches the
+    float32 tensor-core GEMM (plan pinned so that both contexts accumulate in the same order); there the epilogues are also
+    forced INTO the kernel (dsc_gemm_epilogue 2)."""
+    from sigma.diffsharp_b200 import ad
+    from sigma.diffsharp_b200._lib import check, lib
+    act = getattr(ad, actname)
+    m, k, n = shape
+    rng = np.random.default_rng(m + n)
+    X = rng.standard_normal((m, k)).astype(dtype)
+    Y = rng.standard_normal((m, n)).astype(dtype)
+    W = (rng.standard_normal((k, n)) * 0.3).astype(dtype)
+    b = rng.standard_normal(n).astype(dtype)
+    use_provider(oracle_provider)
+    ref = _act_loss_grads(act, X, Y, W, b)
+    outs = {}
+    for name, prov, epi in (("fused", cuda_provider, 1), ("fused_epilogue_in_kernel", cuda_provider, 2), ("unfused", cuda_provider_nofuse, 1)):
+        check(lib.dsc_gemm_tune(prov.ctx.handle, 128, 0, 1, 0))
+        check(lib.dsc_gemm_epilogue(prov.ctx.handle, epi))
+        try:
+            use_provider(prov)
+            st0 = prov.ctx.stats()["kernel_launches"]
+            outs[name] = _act_loss_grads(act, X, Y, W, b)
+            outs[name + "_launches"] = prov.ctx.stats()["kernel_launches"] - st0
+        finally:
+            check(lib.dsc_gemm_tune(prov.ctx.handle, -1, -1, -1, -1))
+            check(lib.dsc_gemm_epilogue(prov.ctx.handle, 1))
+    tol = RTOL[np.dtype(dtype)]
+    for name in ("fused", "fused_epilogue_in_kernel"):
+        assert outs[name][0] == outs["unfused"][0], name
+        assert np.array_equal(outs[name][1], outs["unfused"][1]) and np.array_equal(outs[name][2], outs["unfused"][2]), name
+    assert abs(outs["fused"][0] - ref[0]) <= 10 * tol * abs(ref[0])      # a sum of squares: both sides carry their own summation error
+    assert rel_err(outs["fused"][1], ref[1]) <= 10 * tol and rel_err(outs["fused"][2], ref[2]) <= 10 * tol
+    assert outs["fused_launches"] < outs["unfused_launches"]              # the chains really ran as fewer kernels
+
+
+def test_deferred_values_behave_like_values(cuda_provider, cuda_provider_nofuse):
+    """A handle whose value is deferred is indistinguishable from a computed one: any consumer materialises it; an in-place
+    write to an operand AFTER the deferring call does not leak into the deferred result; handles that end up sharing one
+    result do not see each other's writes; pending work runs at the next synchronisation point."""
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((48, 20)).astype(np.float32)
+    v = rng.standard_normal(20).astype(np.float32)
+    one = np.ones(48 * 20, np.float32)
+    got = []
+    for prov in (cuda_provider, cuda_provider_nofuse):
+        b = backend(prov, np.float32)
+        dA = ShapedDataBufferView(b.CreateDataBuffer(A.reshape(-1)), 48, 20)
+        T = b.Transpose_M(dA)                                        # deferred
+        C = b.Map_F_M(MapOp.Cosh, None, dA)                          # deferred (head of the tanh chain)
+        S = b.Map_F_S_M(np.float32(1), MapOp.Div, None, C)           # deferred: 1 / cosh
+        R = b.RepeatReshapeCopy_V_MRows(48, b.CreateDataBuffer(v))   # deferred
+        Z = b.Add_M_M(dA, R)                                         # deferred: A + rows(v)
+        H = b.Mul_Had_M_M(dA, dA)                                    # deferred
+        b.Add_V_V_InPlace(b.CreateDataBuffer(one), 0, dA.DataBuffer, 0, 48 * 20)   # A += 1 AFTER the calls above
+        res = [T.to_numpy(), C.to_numpy(), S.to_numpy(), R.to_numpy(), Z.to_numpy(), H.to_numpy(), dA.to_numpy(),
+               T.DataBuffer.GetValues(20, 5).SubData, float(b.Sum_M(H.DataBuffer)), float(b.Sum_M(b.Mul_Had_M_M(dA, dA).DataBuffer))]
+        # zero adjoints: the first accumulation aliases the addend, later writes to either side stay private
+        z = ShapedDataBufferView(b.CreateDataBuffer(b.CreateZeroArray(48 * 20)), 48, 20)
+        b.Add_M_M_InPlace(z, dA)
+        b.Add_M_M_InPlace(z, dA)                                     # z = 2 (A + 1): must not change A
+        ones = ShapedDataBufferView(b.CreateDataBuffer(b.CreateValueArray(48 * 20, 1)), 48, 20)
+        e1 = b.Mul_Had_M_M(ones, dA)                                 # 1 .* A: an alias of A
+        b.Add_M_M_InPlace(e1, dA)                                    # written in place: A itself must not change
+        res += [z.to_numpy(), e1.to_numpy(), dA.to_numpy()]
+        got.append(res)
+    for f, u in zip(got[0], got[1]):
+        assert np.array_equal(f, u)
+    f = got[0]
+    assert np.array_equal(f[0], A.T) and np.array_equal(f[3], np.tile(v, (48, 1))) and np.array_equal(f[4], A + v) and np.array_equal(f[5], A * A)
+    assert np.array_equal(f[6], A + 1) and np.array_equal(f[7], A.T.reshape(-1)[20:25])
+    assert np.array_equal(f[10], 2 * (A + 1)) and np.array_equal(f[11], 2 * (A + 1)) and np.array_equal(f[12], A + 1)
+    # pending compute work runs at the next synchronisation point, not never
+    b = backend(cuda_provider, np.float32)
+    dA = ShapedDataBufferView(b.CreateDataBuffer(A.reshape(-1)), 48, 20)
+    cuda_provider.ctx.sync()
+    n0 = cuda_provider.ctx.stats()["kernel_launches"]
+    keep = b.Mul_Had_M_M(dA, dA)
+    assert cuda_provider.ctx.stats()["kernel_launches"] == n0
+    cuda_provider.ctx.sync()
+    assert cuda_provider.ctx.stats()["kernel_launches"] == n0 + 1
+    assert np.array_equal(keep.to_numpy(), A * A)
+
+
+def test_copy_on_write_counts_live_aliases(cuda_provider):
+    """Regression (round-1 advisor): share, free the alias, take a TRUE view, write — the view must keep sharing storage with
+    its parent (copy-on-write only while aliases are alive); and dsc_copy_upload honours aliases."""
+    import ctypes as C
+    b = backend(cuda_provider, np.float32)
+    x = b.CreateDataBuffer(np.arange(8, dtype=np.float32))
+    h = _lib.buf_t()
+    _lib.check(_lib.lib.dsc_buf_share(x.handle, C.byref(h)))
+    _lib.check(_lib.lib.dsc_buf_free(h.value))                     # the alias is gone again
+    v = x.GetValues(2, 3)
+    one = b.CreateDataBuffer(np.ones(8, np.float32))
+    b.Add_V_V_InPlace(one, 0, x, 0, 8)
+    assert np.array_equal(v.SubData, np.arange(2, 5) + 1)          # written through the parent, seen by the view
+    b.Add_V_V_InPlace(one, 0, v, 0, 3)
+    assert np.array_equal(x.SubData, np.arange(8) + 1 + np.array([0, 0, 1, 1, 1, 0, 0, 0]))   # and the other way round
+    y = b.CreateDataBuffer(np.arange(4, dtype=np.float32))
+    _lib.check(_lib.lib.dsc_buf_share(y.handle, C.byref(h)))
+    alias = CudaDataBuffer(b.ctx, np.float32, h.value, 4)
+    pin = np.full(4, 7, np.float32)
+    _lib.check(_lib.lib.dsc_copy_upload(y.handle, 0, pin.ctypes.data, 4))
+    _lib.check(_lib.lib.dsc_copy_sync(b.ctx.handle))
+    assert np.array_equal(alias.SubData, np.arange(4)) and np.array_equal(y.SubData, pin)
+
+
+def test_host_mirror_of_a_device_buffer(cuda_provider):
+    """ISigmaDiffDataBuffer.Data on the device buffer (Util.fs:136): a cached host array shared by the views of one allocation;
+    host-side writes (`aa.Data.[i] <- ...`) reach the device before its next use; device-side writes drop the mirror."""
+    b = backend(cuda_provider, np.float32)
+    a = np.arange(12, dtype=np.float32)
+    buf = b.CreateDataBuffer(a)
+    d = buf.Data
+    assert d is buf.Data and np.array_equal(d, a)                  # cached: the same array object, no second download
+    d[3] = 100                                                     # host-side write
+    assert np.array_equal(b.Mul_S_V(np.float32(2), buf).SubData, 2 * np.where(np.arange(12) == 3, 100, a))
+    view = buf.GetValues(2, 4)
+    assert view.Data is d and view.Offset == 2                     # the whole underlying array, indexed at Offset
+    view.Data[view.Offset + 1] = -5                                # element 3 again, through the view
+    assert float(b.Sum_V(view)) == 2 - 5 + 4 + 5
+    b.Add_V_V_InPlace(b.CreateDataBuffer(np.ones(12, np.float32)), 0, buf, 0, 12)   # device-side write
+    assert buf.Data is not d and buf.Data[3] == -4 and np.array_equal(buf.SubData, buf.Data)
