@@ -186,9 +186,10 @@ using namespace dsc;
 extern "C" {
 #define DSC_BLAS2_API(P, T)                                                                                          \
     int dsc_##P##gemv(dsc_ctx_t c, int trans, int32_t m, int32_t n, dsc_buf_t A, dsc_buf_t x, dsc_buf_t y, dsc_buf_t* out) { \
+        DSC_NVTX(c, "Mul_M_V/Mul_V_M");                                                                               \
         return gemv_impl<T>(c, trans, m, n, A, x, y, out);                                                            \
     }                                                                                                                 \
-    int dsc_##P##ger(dsc_ctx_t c, dsc_buf_t x, dsc_buf_t y, dsc_buf_t* out) { return ger_impl<T>(c, x, y, out); }
+    int dsc_##P##ger(dsc_ctx_t c, dsc_buf_t x, dsc_buf_t y, dsc_buf_t* out) { DSC_NVTX(c, "Mul_Out_V_V"); return ger_impl<T>(c, x, y, out); }
 DSC_BLAS2_API(s, float)
 DSC_BLAS2_API(d, double)
 }

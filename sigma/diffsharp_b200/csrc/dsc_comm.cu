@@ -124,6 +124,8 @@ struct P2PArgs {
     char* peer[kP2PMaxRanks];  // every rank's symmetric buffer as mapped here
     int nranks, rank;
     size_t region_bytes;
+    unsigned int* err_host;            // mapped pinned host word: set by the kernel when a barrier times out, read by the host WITHOUT a copy
+    unsigned long long timeout_ns;     // 0: wait for ever (like NCCL)
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -143,8 +145,11 @@ __device__ __forceinline__ unsigned int ld_relaxed_sys(const unsigned int* p) {
 
 // All CTAs of this rank have finished the phase -> tell every peer (flag[rank] = value in the peer's
 // header) -> wait until every peer has told us.  `arrivals` is the cumulative CTA count expected at
-// the local counter.  A 20 s timeout turns a lost peer (or ranks that issued different numbers of all-reduces) into an error word instead of a hung GPU;
-// after the first failure the barriers of later calls return at once (dsc_comm_destroy reports the error).
+// the local counter.
+// A peer that does not show up within the time-out (DSC_P2P_TIMEOUT_S, default 30 s; 0 = wait for ever, like NCCL) turns
+// into an ERROR the host sees: the kernel sets a word in mapped pinned host memory and the next dsc_sync / dsc_comm_join /
+// dsc_?allreduce_sum / dsc_comm_destroy on this rank returns DSC_E_NCCL (the sums of that step are invalid).  Later
+// barriers wait again — nothing is skipped silently.
 // Cost matters here (two barriers per all-reduce): ONE system fence per CTA on the way in, the flags of
 // all peers written in parallel by the lanes of one warp with relaxed stores (a release store per peer
 // is a system fence per peer: measured 78 us per all-reduce at 8 ranks against 37 us at 2), relaxed
@@ -167,13 +172,15 @@ __device__ __forceinline__ void p2p_barrier(const P2PArgs& a, unsigned int value
             }
         }
         last = __shfl_sync(0xffffffffu, last, 0);
+        __syncwarp();   // lane 0's system fence is ordered before the other lanes' flag stores (a shuffle alone is not a memory barrier)
         if (last && lane < (unsigned)a.nranks) st_relaxed_sys(reinterpret_cast<unsigned int*>(a.peer[lane]) + a.rank, value);
-        if (lane < (unsigned)a.nranks && ld_relaxed_sys(sync + 2) == 0) {   // once a barrier has failed, later ones do not wait again
+        if (lane < (unsigned)a.nranks) {
             const unsigned long long t0 = globaltimer_ns();
             unsigned int spins = 0;
             while ((int)(ld_relaxed_sys(flags + lane) - value) < 0) {
-                if ((++spins & 1023u) == 0 && (globaltimer_ns() - t0 > 20000000000ull || ld_relaxed_sys(sync + 2) != 0)) {
+                if ((++spins & 1023u) == 0 && a.timeout_ns != 0 && globaltimer_ns() - t0 > a.timeout_ns) {
                     sync[2] = 1;
+                    if (a.err_host) st_relaxed_sys(a.err_host, 1u);
                     break;
                 }
             }
@@ -319,6 +326,46 @@ __global__ void __launch_bounds__(kP2PThreads) allreduce_p2p_kernel(P2PTable<T> 
 
 static int p2p_setup(Ctx* ctx);
 
+// Has a barrier of an earlier peer-memory all-reduce timed out on this rank?  (mapped pinned word: no copy, no synchronisation)
+static int p2p_check_error(Ctx* ctx) {
+    if (ctx->p2p_err_host && *reinterpret_cast<volatile unsigned int*>(ctx->p2p_err_host) != 0)
+        return fail(DSC_E_NCCL, "a peer-memory all-reduce timed out waiting for a peer (the sums of that step are invalid; DSC_P2P_TIMEOUT_S sets the limit)");
+    return DSC_OK;
+}
+
+// The all-reduce kernel meets at grid-wide barriers: every CTA must be resident.  A cooperative launch makes the driver
+// guarantee that (or fail the launch) instead of relying on an idle GPU; the grid is sized from the occupancy query.
+template <typename T>
+static int p2p_launch(Ctx* ctx, P2PTable<T>& pt, P2PArgs& a) {
+    static int max_ctas = -1;
+    if (max_ctas < 0) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, allreduce_p2p_kernel<T>, kP2PThreads, 0) != cudaSuccess || per_sm < 1) {
+            cudaGetLastError();
+            per_sm = 1;
+        }
+        max_ctas = per_sm * ctx->sm_count;
+    }
+    int ctas = ctx->sm_count < kP2PMaxCtas ? ctx->sm_count : kP2PMaxCtas;
+    if (ctas > max_ctas) ctas = max_ctas;
+    static int coop = -1;   // -1 unknown, 1 works, 0 the driver refused (e.g. under this capture mode): plain launch
+    if (coop != 0) {
+        void* args[] = {&pt, &a};
+        cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(allreduce_p2p_kernel<T>), dim3(ctas), dim3(kP2PThreads), args, 0, ctx->stream);
+        if (e == cudaSuccess) {
+            coop = 1;
+            DSC_LAUNCH_CHECK(ctx);
+            return DSC_OK;
+        }
+        cudaGetLastError();
+        if (coop == 1) return fail(DSC_E_CUDA, "cooperative launch of the all-reduce kernel failed: %s", cudaGetErrorString(e));
+        coop = 0;
+    }
+    allreduce_p2p_kernel<T><<<ctas, kP2PThreads, 0, ctx->stream>>>(pt, a);
+    DSC_LAUNCH_CHECK(ctx);
+    return DSC_OK;
+}
+
 template <typename T>
 static int allreduce_impl(dsc_ctx_t c, int32_t count, const dsc_buf_t* bufs) {
     if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
@@ -326,6 +373,7 @@ static int allreduce_impl(dsc_ctx_t c, int32_t count, const dsc_buf_t* bufs) {
     if (count < 0 || (count > 0 && !bufs)) return fail(DSC_E_INVALID, "allreduce: bad buffer list");
     if (ctx->nranks == 1) return DSC_OK;  // a single rank already holds the sum
     if (!ctx->nccl_comm) return fail(DSC_E_NCCL, "allreduce: dsc_comm_init has not been called");
+    DSC_TRY(p2p_check_error(ctx));
     PackTable<T> t;
     t.count = 0;
     t.start[0] = 0;
@@ -362,14 +410,17 @@ static int allreduce_impl(dsc_ctx_t c, int32_t count, const dsc_buf_t* bufs) {
         a.nranks = ctx->nranks;
         a.rank = ctx->rank;
         a.region_bytes = ctx->p2p_region_bytes;
-        // one CTA per SM: all CTAs must be resident at once (they meet at two grid-wide barriers)
-        const int ctas = ctx->sm_count < kP2PMaxCtas ? ctx->sm_count : kP2PMaxCtas;
-        allreduce_p2p_kernel<T><<<ctas, kP2PThreads, 0, ctx->stream>>>(pt, a);
-        DSC_LAUNCH_CHECK(ctx);
+        a.err_host = reinterpret_cast<unsigned int*>(ctx->p2p_err_dev);
+        a.timeout_ns = ctx->p2p_timeout_ns;
+        DSC_TRY(p2p_launch<T>(ctx, pt, a));
         ctx->stats.allreduce_p2p++;
         return DSC_OK;
     }
     ctx->stats.allreduce_nccl++;
+    for (int i = 0; i < count; ++i) {   // these blocks are now in use on the communication stream: not recycled / overwritten before it is joined
+        Buf* b = as_buf(bufs[i]);
+        if (b && b->block) note_other_stream_use(ctx, b->block);
+    }
     if (t.count == 1) {
         DSC_TRY(comm_fork(ctx));
         DSC_NCCL_CHECK(g_nccl.AllReduce(t.ptr[0], t.ptr[0], (size_t)total, dt, NCCL_SUM, ctx->nccl_comm, ctx->comm_stream));
@@ -419,6 +470,8 @@ static int allgather_impl(dsc_ctx_t c, dsc_buf_t sendh, dsc_buf_t recvh) {
         return DSC_OK;
     }
     if (!ctx->nccl_comm) return fail(DSC_E_NCCL, "allgather: dsc_comm_init has not been called");
+    note_other_stream_use(ctx, s->block);
+    note_other_stream_use(ctx, r->block);
     DSC_TRY(comm_fork(ctx));
     const int dt = sizeof(T) == 4 ? NCCL_FLOAT32 : NCCL_FLOAT64;
     DSC_NCCL_CHECK(g_nccl.AllGather(s->ptr<T>(), r->ptr<T>(), (size_t)s->len, dt, ctx->nccl_comm, ctx->comm_stream));
@@ -477,6 +530,20 @@ static int p2p_setup(Ctx* ctx) {
     cudaFree(dev);
     ctx->p2p_ok = ok != 0;
     ctx->p2p_region_bytes = ok ? kP2PRegionBytes : 0;
+    if (ok && !ctx->p2p_err_host) {
+        if (cudaHostAlloc(&ctx->p2p_err_host, 64, cudaHostAllocMapped) == cudaSuccess) {
+            memset(ctx->p2p_err_host, 0, 64);
+            if (cudaHostGetDevicePointer(&ctx->p2p_err_dev, ctx->p2p_err_host, 0) != cudaSuccess) { cudaGetLastError(); ctx->p2p_err_dev = nullptr; }
+        } else {
+            cudaGetLastError();
+            ctx->p2p_err_host = nullptr;
+        }
+    }
+    {
+        const char* e = getenv("DSC_P2P_TIMEOUT_S");
+        const double sec = e ? atof(e) : 30.0;
+        ctx->p2p_timeout_ns = sec <= 0 ? 0ull : (unsigned long long)(sec * 1e9);
+    }
     return DSC_OK;
 }
 
@@ -487,6 +554,8 @@ static void p2p_teardown(Ctx* ctx) {
     }
     if (ctx->p2p_local) cudaFree(ctx->p2p_local);
     ctx->p2p_local = nullptr;
+    if (ctx->p2p_err_host) cudaFreeHost(ctx->p2p_err_host);
+    ctx->p2p_err_host = ctx->p2p_err_dev = nullptr;
     ctx->p2p_ok = false;
     ctx->p2p_region_bytes = 0;
 }
@@ -537,6 +606,7 @@ int dsc_comm_debug_stamps(dsc_ctx_t c, uint64_t out[6]) {
 int dsc_comm_join(dsc_ctx_t c) {
     if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
     Ctx* ctx = as_ctx(c);
+    DSC_TRY(p2p_check_error(ctx));
     if (!ctx->comm_pending) return DSC_OK;
     DSC_CUDA_CHECK(cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
     DSC_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
@@ -552,6 +622,7 @@ int dsc_comm_destroy(dsc_ctx_t c) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamSynchronize(ctx->comm_stream);
         if (ctx->p2p_local) cudaMemcpy(&p2p_err, reinterpret_cast<char*>(ctx->p2p_local) + 256 + 8, 4, cudaMemcpyDeviceToHost);
+        if (ctx->p2p_err_host && *reinterpret_cast<volatile unsigned int*>(ctx->p2p_err_host)) p2p_err = 1;
         p2p_teardown(ctx);
         g_nccl.CommDestroy(ctx->nccl_comm);
         ctx->nccl_comm = nullptr;
@@ -562,8 +633,8 @@ int dsc_comm_destroy(dsc_ctx_t c) {
     return DSC_OK;
 }
 
-int dsc_sallreduce_sum(dsc_ctx_t c, int32_t count, const dsc_buf_t* bufs) { return allreduce_impl<float>(c, count, bufs); }
-int dsc_dallreduce_sum(dsc_ctx_t c, int32_t count, const dsc_buf_t* bufs) { return allreduce_impl<double>(c, count, bufs); }
+int dsc_sallreduce_sum(dsc_ctx_t c, int32_t count, const dsc_buf_t* bufs) { DSC_NVTX(c, "allreduce_sum"); return allreduce_impl<float>(c, count, bufs); }
+int dsc_dallreduce_sum(dsc_ctx_t c, int32_t count, const dsc_buf_t* bufs) { DSC_NVTX(c, "allreduce_sum"); return allreduce_impl<double>(c, count, bufs); }
 int dsc_sallgather(dsc_ctx_t c, dsc_buf_t s, dsc_buf_t r) { return allgather_impl<float>(c, s, r); }
 int dsc_dallgather(dsc_ctx_t c, dsc_buf_t s, dsc_buf_t r) { return allgather_impl<double>(c, s, r); }
 

@@ -4,6 +4,8 @@
 
 #include <algorithm>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "dsc_internal.cuh"
 
 namespace dsc {
@@ -24,6 +26,9 @@ int fail(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+
+void nvtx_push(const char* name) { nvtxRangePushA(name); }
+void nvtx_pop() { nvtxRangePop(); }
 
 // ---- pool ---------------------------------------------------------------------------------
 // Bin sizes: multiples of 512 B up to 1 MiB, multiples of 64 KiB up to 64 MiB, multiples of 2 MiB
@@ -451,7 +456,7 @@ int dsc_sync(dsc_ctx_t c) {
     DSC_TRY(flush_pending(ctx));
     DSC_TRY(dsc_comm_join(c));
     DSC_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    return DSC_OK;
+    return dsc_comm_join(c);   // ... and report a barrier time-out the work just synchronised may have hit
 }
 
 int dsc_get_stats(dsc_ctx_t c, dsc_stats* out) {

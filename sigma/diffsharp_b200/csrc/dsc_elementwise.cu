@@ -813,13 +813,11 @@ static int add_inplace_impl(dsc_ctx_t c, dsc_buf_t dh, dsc_buf_t sh) {
     }
     DSC_TRY(buf_resolve(s));
     DSC_TRY(buf_resolve(d));
-    if (d->block && d->block != s->block && !d->is_view && d->block->views == 0 && d->block->cow > 0 && d->block->refs > 1 && d->block->readers.empty())
+    // The accumulator shares its block with other holders (it became an alias of its first addend: E + E in the loss tail)
+    // and would have to be detached before the write anyway: ONE pass new = old + addend into a fresh block.  The old block
+    // is not written, so deferred operations that still read it need not run first.
+    if (d->block && !d->is_view && d->block->views == 0 && d->block->cow > 0 && d->block->refs > 1)
         return add_out_of_place<T>(ctx, d, s->ptr<T>(), 0, (size_t)d->len);
-    const bool self = d->block == s->block;   // E + E: the addend aliases the accumulator (copy-on-write), read it before it is detached
-    if (self && !d->is_view && d->block->views == 0 && d->block->cow > 0 && d->block->refs > 1) {
-        while (!d->block->readers.empty()) DSC_TRY(lazy_materialize(d->block->readers.back()));
-        return add_out_of_place<T>(ctx, d, s->ptr<T>(), 0, (size_t)d->len);
-    }
     DSC_TRY(buf_writable(ctx, d));
     return ew_map2<T>(ctx, DSC_OP_ADD, d->ptr<T>(), s->ptr<T>(), d->ptr<T>(), (size_t)d->len);
 }
@@ -873,16 +871,16 @@ using namespace dsc;
 
 extern "C" {
 #define DSC_EW_API(P, T)                                                                                                   \
-    int dsc_##P##map(dsc_ctx_t c, int op, dsc_buf_t x, dsc_buf_t* y) { return map_impl<T>(c, op, x, y); }                  \
-    int dsc_##P##map_s(dsc_ctx_t c, int op, T s, dsc_buf_t x, dsc_buf_t* y) { return map_s_impl<T>(c, op, s, x, y); }      \
-    int dsc_##P##map2(dsc_ctx_t c, int op, dsc_buf_t a, dsc_buf_t b, dsc_buf_t* y) { return map2_impl<T>(c, op, a, b, y); } \
-    int dsc_##P##scalar_op(dsc_ctx_t c, int kind, T s, dsc_buf_t x, dsc_buf_t* y) { return scalar_op_impl<T>(c, kind, s, x, y); } \
-    int dsc_##P##add_inplace(dsc_ctx_t c, dsc_buf_t d, dsc_buf_t s) { return add_inplace_impl<T>(c, d, s); }               \
-    int dsc_##P##add_inplace_range(dsc_ctx_t c, dsc_buf_t s, int32_t so, dsc_buf_t d, int32_t dof, int32_t n) {            \
+    int dsc_##P##map(dsc_ctx_t c, int op, dsc_buf_t x, dsc_buf_t* y) { DSC_NVTX(c, "Map_F_V/Map_F_M"); return map_impl<T>(c, op, x, y); }                  \
+    int dsc_##P##map_s(dsc_ctx_t c, int op, T s, dsc_buf_t x, dsc_buf_t* y) { DSC_NVTX(c, "Map_F_S_V/Map_F_S_M"); return map_s_impl<T>(c, op, s, x, y); }      \
+    int dsc_##P##map2(dsc_ctx_t c, int op, dsc_buf_t a, dsc_buf_t b, dsc_buf_t* y) { DSC_NVTX(c, "Map2_F/Add/Sub/Mul_Had"); return map2_impl<T>(c, op, a, b, y); } \
+    int dsc_##P##scalar_op(dsc_ctx_t c, int kind, T s, dsc_buf_t x, dsc_buf_t* y) { DSC_NVTX(c, "Add_S/Sub_S/Mul_S"); return scalar_op_impl<T>(c, kind, s, x, y); } \
+    int dsc_##P##add_inplace(dsc_ctx_t c, dsc_buf_t d, dsc_buf_t s) { DSC_NVTX(c, "Add_M_M_InPlace"); return add_inplace_impl<T>(c, d, s); }               \
+    int dsc_##P##add_inplace_range(dsc_ctx_t c, dsc_buf_t s, int32_t so, dsc_buf_t d, int32_t dof, int32_t n) { DSC_NVTX(c, "Add_V_V_InPlace");            \
         return add_inplace_range_impl<T>(c, s, so, d, dof, n);                                                             \
     }                                                                                                                      \
-    int dsc_##P##fused_bwd(dsc_ctx_t c, int kind, dsc_buf_t dA, dsc_buf_t p, dsc_buf_t* out) { return fused_bwd_impl<T>(c, kind, dA, p, out); } \
-    int dsc_##P##bias_rows_act(dsc_ctx_t c, int op, int32_t m, int32_t n, dsc_buf_t A, dsc_buf_t v, dsc_buf_t* z, dsc_buf_t* h) { \
+    int dsc_##P##fused_bwd(dsc_ctx_t c, int kind, dsc_buf_t dA, dsc_buf_t p, dsc_buf_t* out) { DSC_NVTX(c, "fused_bwd"); return fused_bwd_impl<T>(c, kind, dA, p, out); } \
+    int dsc_##P##bias_rows_act(dsc_ctx_t c, int op, int32_t m, int32_t n, dsc_buf_t A, dsc_buf_t v, dsc_buf_t* z, dsc_buf_t* h) { DSC_NVTX(c, "bias_rows_act"); \
         return bias_rows_act_impl<T>(c, op, m, n, A, v, z, h);                                                             \
     }
 DSC_EW_API(s, float)

@@ -111,9 +111,12 @@ template <>
 int gemm_run<float>(Ctx* ctx, int ta, int tb, int m, int n, int k, MatRef A, MatRef B, const float* bias, float* C, const GemmEpilogue* ep) {
     const float *Ap = reinterpret_cast<const float*>(A.ptr), *Bp = reinterpret_cast<const float*>(B.ptr);
     {
-        int s = gemm_skinny<float>(ctx, ta, tb, m, n, k, Ap, Bp, bias, C);
+        // the output layer: bias rows without activation ride along in the skinny kernel
+        const bool colb = ep && ep->mode == GEMM_EP_BIAS_ACT && ep->op < 0 && !ep->lo;
+        int done = 0;
+        int s = gemm_skinny<float>(ctx, ta, tb, m, n, k, Ap, Bp, bias, C, colb ? reinterpret_cast<const float*>(ep->vec) : nullptr, &done);
         if (s < 0) return s;
-        if (s == 0) return epilogue_pass<float>(ctx, m, n, C, ep);
+        if (s == 0) return done ? DSC_OK : epilogue_pass<float>(ctx, m, n, C, ep);
     }
     if (!(ctx->flags & DSC_FLAG_GEMM_FP32_SIMT)) {
         int s = gemm_tf32x3_tcgen05(ctx, ta, tb, m, n, k, A, B, bias, C, ep);
@@ -128,9 +131,12 @@ template <>
 int gemm_run<double>(Ctx* ctx, int ta, int tb, int m, int n, int k, MatRef A, MatRef B, const double* bias, double* C, const GemmEpilogue* ep) {
     const double *Ap = reinterpret_cast<const double*>(A.ptr), *Bp = reinterpret_cast<const double*>(B.ptr);
     {
-        int s = gemm_skinny<double>(ctx, ta, tb, m, n, k, Ap, Bp, bias, C);
+        // the output layer: bias rows without activation ride along in the skinny kernel
+        const bool colb = ep && ep->mode == GEMM_EP_BIAS_ACT && ep->op < 0 && !ep->lo;
+        int done = 0;
+        int s = gemm_skinny<double>(ctx, ta, tb, m, n, k, Ap, Bp, bias, C, colb ? reinterpret_cast<const double*>(ep->vec) : nullptr, &done);
         if (s < 0) return s;
-        if (s == 0) return epilogue_pass<double>(ctx, m, n, C, ep);
+        if (s == 0) return done ? DSC_OK : epilogue_pass<double>(ctx, m, n, C, ep);
     }
     if (!(ctx->flags & DSC_FLAG_GEMM_F64_SIMT)) {
         int s = gemm_f64_dmma(ctx, ta, tb, m, n, k, Ap, Bp, bias, C);
@@ -174,6 +180,50 @@ static int gemm_entry(dsc_ctx_t c, int ta, int tb, int32_t m, int32_t n, int32_t
     take(A, eta, ta ? k : m, ta ? m : k, oa);
     take(B, etb, tb ? n : k, tb ? k : n, ob);
     if (!Ch) return fail(DSC_E_INVALID, "null output handle pointer");
+    if constexpr (sizeof(T) == 8) {
+        // rows(x) W = rows(x W): the forward-mode sweep with a matrix tangent carries a primal made of m identical rows
+        // (DNDArray.OfRows(m, x), AD.Float64.fs:1846) and multiplies it by every weight matrix — half of the
+        // issued flops.  The DMMA kernel accumulates every output element over k in one fixed order whatever the number of rows,
+        // so ONE row through the same kernel gives bit for bit the row the full product would repeat m times.
+        LazyNode* r = (ctx->fuse && *Ch == 0 && !bias && eta == 0) ? oa.node : nullptr;
+        if (r && r->kind == LZ_ROWS && !r->result && r->m == m && r->n == k && m > 1 && n > 16 && k > 16 && (int64_t)m * n >= 64 * 64 && (int64_t)n >= 64 * 64) {
+            r->refs++;   // keep the node while its vector and B are resolved
+            Operand xv = r->src[0];
+            LazyNode* hold = lazy_new(ctx, LZ_GEMM, DSC_F64, n);
+            hold->consumed = true;
+            lazy_set_operand(hold, 0, xv);
+            lazy_set_operand(hold, 1, ob);
+            int st = DSC_OK;
+            for (int i = 0; i < 2 && st == DSC_OK; ++i) st = operand_resolve(ctx, hold->src[i]);
+            Buf* y = nullptr;
+            dsc_buf_t yh = 0;
+            if (st == DSC_OK) st = out_buf(ctx, DSC_F64, n, &yh, &y);
+            int handled = 1;
+            if (st == DSC_OK) {
+                auto ptr = [](const Operand& o) { return o.node ? reinterpret_cast<const double*>(o.node->result->ptr) + o.node->result_off : reinterpret_cast<const double*>(o.block->ptr) + o.off; };
+                const double* Bp = ptr(hold->src[1]);
+                // the full product would have to be DMMA-eligible too (same kernel family, same accumulation order)
+                const int ldb = etb ? k : n;
+                const bool full_ok = !(ctx->flags & DSC_FLAG_GEMM_F64_SIMT) && !(k & 1) && !(ldb & 1) && !(reinterpret_cast<uintptr_t>(Bp) & 15);
+                handled = full_ok ? gemm_f64_dmma(ctx, 0, etb, 1, n, k, ptr(hold->src[0]), Bp, nullptr, y->ptr<double>()) : 1;
+                if (handled < 0) st = handled;
+            }
+            lazy_unref(hold);
+            if (st == DSC_OK && handled == 0) {
+                LazyNode* nd = lazy_new(ctx, LZ_ROWS, DSC_F64, m * n);
+                nd->m = m; nd->n = n;
+                lazy_set_operand(nd, 0, y);
+                r->consumed = true;
+                lazy_unref(r);
+                dsc_buf_free(yh);
+                return lazy_buf(ctx, nd, Ch);
+            }
+            lazy_unref(r);
+            if (yh) dsc_buf_free(yh);
+            if (st != DSC_OK) return st;
+            // not eligible: fall through to the general path (the replicated rows are materialised)
+        }
+    }
     if (ctx->fuse && *Ch == 0 && (int64_t)m * n > 0 && k > 0) {
         // The product is DEFERRED: the calls that follow it in the unchanged sequence — Add_M_M(., rows(b)) -> Map_F_M in the
         // forward pass (AD.Float32.fs:2357, :2704), the activation's adjoint chain in the reverse sweep (:4238-4240,
@@ -221,9 +271,11 @@ using namespace dsc;
 
 extern "C" {
 int dsc_sgemm(dsc_ctx_t c, int ta, int tb, int32_t m, int32_t n, int32_t k, dsc_buf_t A, dsc_buf_t B, dsc_buf_t bias, dsc_buf_t* C) {
+    DSC_NVTX(c, "Mul_M_M");
     return gemm_entry<float>(c, ta, tb, m, n, k, A, B, bias, C);
 }
 int dsc_dgemm(dsc_ctx_t c, int ta, int tb, int32_t m, int32_t n, int32_t k, dsc_buf_t A, dsc_buf_t B, dsc_buf_t bias, dsc_buf_t* C) {
+    DSC_NVTX(c, "Mul_M_M");
     return gemm_entry<double>(c, ta, tb, m, n, k, A, B, bias, C);
 }
 }

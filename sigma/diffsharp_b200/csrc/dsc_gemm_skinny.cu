@@ -181,12 +181,15 @@ __device__ __forceinline__ void warp_sum16(T (&v)[16], int lane) {
 // K chunk, all issued before the first FMA), B^T sits in shared memory as Bs[j][kk] so the same lane
 // reads the matching 16 bytes of every B column without bank conflicts.  NJ = n rounded up to 4.
 template <typename T, int RPW, int NJ>
-__global__ void __launch_bounds__(256, 2) skinny_rows_vec_kernel(const T* __restrict__ A, const T* __restrict__ B, const T* __restrict__ bias,
-                                                                  T* __restrict__ C, int m, int n, int k, int tb) {
+__global__ void __launch_bounds__(256, RPW >= 4 ? 1 : 2) skinny_rows_vec_kernel(const T* __restrict__ A, const T* __restrict__ B, const T* __restrict__ bias,
+                                                                  const T* __restrict__ bias_col, T* __restrict__ C, int m, int n, int k, int tb) {
     using V = typename V16<T>::type;
     constexpr int W = V16<T>::W;
-    constexpr int ITS = 8;
-    constexpr int KC = 32 * W * ITS;  // 1024 floats / 512 doubles per chunk
+    // vectors of a row in flight per lane: 8 (two rows per warp), 4 with four rows per warp — the same 16 loads in flight, but
+    // every B vector read from shared memory then feeds four rows: the two-row kernel spends 12 LDS.128 per 8 FMA-quads and
+    // is shared-memory bound at ~0.36 of HBM (ncu: short-scoreboard stalls)
+    constexpr int ITS = RPW >= 4 ? 4 : 8;
+    constexpr int KC = 32 * W * ITS;  // floats / doubles per chunk
     constexpr int KCP = KC + W;       // +16 bytes per row
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* Bs = reinterpret_cast<T*>(smem_raw);  // [NJ][KCP]
@@ -260,39 +263,40 @@ __global__ void __launch_bounds__(256, 2) skinny_rows_vec_kernel(const T* __rest
             for (int j = 0; j < 16; ++j) v[j] = j < NJ ? acc[r][j < NJ ? j : 0] : T(0);
             warp_sum16(v, lane);
             const int row = row0 + r;
-            if (!(lane & 1) && j_out < n && row < m) C[(size_t)row * n + j_out] = v[0] + (bias ? bias[row] : T(0));
+            // (dot + bias[i]) + v[j]: the roundings of Mul_M_M[_Add_V_MCols] followed by Add_M_M(., rows(v))
+            if (!(lane & 1) && j_out < n && row < m) {
+                const T g = v[0] + (bias ? bias[row] : T(0));
+                C[(size_t)row * n + j_out] = bias_col ? g + bias_col[j_out] : g;
+            }
         }
     }
 }
 
 // ---- A has M contiguous (ta = 1, stored k x m), 128-bit loads -----------------------------------
-// grid (ceil(m / 32), chunks).  A CTA owns 32 output rows (= 32 columns of the stored A, one
-// 128-byte segment per k-row) and one K chunk.  Warp w, lane l: column vector l / W (W adjacent
-// output rows) and k-lane w*W + l % W of 8W, so the CTA walks 8W k-rows per step.  After the K loop
-// the W k-lanes of a warp are combined with shuffles (lane ends up with one output row), the 8 warps
-// through shared memory in warp order, and the CTA writes one partial per chunk.  Chunks are then
-// summed in two fixed levels by whichever CTA arrives last (groups of 8 chunks, then the groups):
-// one launch, and the summation order does not depend on the arrival order.
+// grid (ceil(m / 128), chunks).  A CTA owns 128 output rows (= 128 columns of the stored A: one 512-byte segment per k-row,
+// read by ONE warp instruction — round 1 read 128-byte segments 4 KB apart and ran at 0.22 of HBM) and one K chunk.
+// Warp w, lane l: column vector l (W adjacent output rows) and k-lane w of 8, so the CTA walks 8 k-rows per step.  After the
+// K loop the 8 warps are combined through shared memory in warp order and the CTA writes one partial per chunk.  Chunks are
+// then summed in two fixed levels by whichever CTA arrives last (groups of 8 chunks, then the groups): one launch, and the
+// summation order does not depend on the arrival order.
 template <typename T, int NJ>
-__global__ void __launch_bounds__(256) skinny_cols_vec_kernel(const T* __restrict__ A, const T* __restrict__ B, const T* __restrict__ bias,
+__global__ void __launch_bounds__(256, 1) skinny_cols_vec_kernel(const T* __restrict__ A, const T* __restrict__ B, const T* __restrict__ bias,
                                                                T* __restrict__ partial, T* __restrict__ partial2, T* __restrict__ C,
                                                                unsigned int* __restrict__ tickets, int m, int n, int k, int tb, int rows_per_chunk) {
     using V = typename V16<T>::type;
     constexpr int W = V16<T>::W;
-    constexpr int COLS = 32;
-    constexpr int KL = 8 * W;   // k-lanes per CTA
-    constexpr int KCH = 256;    // k-rows of B staged per pass
+    constexpr int COLS = 32 * W;   // 128 (float) / 64 (double) output rows per CTA
+    constexpr int KL = 8;          // k-lanes per CTA (one per warp)
+    constexpr int KCH = 256;       // k-rows of B staged per pass
     constexpr int GROUP = 8;
     // the B chunk and the cross-warp reduction buffer share storage (B is dead after the K loop)
-    constexpr int kBsElems = KCH * NJ, kRedElems = 8 * COLS * (NJ + 1);
+    constexpr int kBsElems = KCH * NJ, kRedElems = 4 * 32 * (W * NJ + 1);
     __shared__ __align__(16) T smem_u[kBsElems > kRedElems ? kBsElems : kRedElems];
     T (*Bs)[NJ] = reinterpret_cast<T (*)[NJ]>(smem_u);
-    T (*red)[COLS][NJ + 1] = reinterpret_cast<T (*)[COLS][NJ + 1]>(smem_u);
+    T (*red)[32][W * NJ + 1] = reinterpret_cast<T (*)[32][W * NJ + 1]>(smem_u);
     __shared__ int s_last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int klo = lane % W, cv = lane / W;
-    const int kl = warp * W + klo;
-    const int col0 = blockIdx.x * COLS + cv * W;
+    const int col0 = blockIdx.x * COLS + lane * W;
     const int chunks = gridDim.y;
     const int kbeg = blockIdx.y * rows_per_chunk, kend = min(k, kbeg + rows_per_chunk);
     T acc[W][NJ];
@@ -319,12 +323,12 @@ __global__ void __launch_bounds__(256) skinny_cols_vec_kernel(const T* __restric
         __syncthreads();
         if (col0 < m) {  // m % W == 0: a column vector is entirely inside or outside
             const T* a = A + (size_t)k0 * m + col0;
-#pragma unroll 4
-            for (int kk = kl; kk < kc; kk += KL) {
+#pragma unroll 8
+            for (int kk = warp; kk < kc; kk += KL) {
                 const V av = *reinterpret_cast<const V*>(a + (size_t)kk * m);
 #pragma unroll
                 for (int j = 0; j < NJ; j += W) {
-                    const V bv = *reinterpret_cast<const V*>(&Bs[kk][j]);
+                    const V bv = *reinterpret_cast<const V*>(&Bs[kk][j]);   // same address in every lane: broadcast
 #pragma unroll
                     for (int c = 0; c < W; ++c)
 #pragma unroll
@@ -333,33 +337,39 @@ __global__ void __launch_bounds__(256) skinny_cols_vec_kernel(const T* __restric
             }
         }
     }
-    // combine the W k-lanes of the warp: lane klo keeps output row col0 + klo
-#pragma unroll
-    for (int s = W / 2; s >= 1; s >>= 1) {
-        const bool up = (klo & s) != 0;
-#pragma unroll
-        for (int c = 0; c < s; ++c)
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const T send = up ? acc[c][j] : acc[c + s][j];
-                const T keep = up ? acc[c + s][j] : acc[c][j];
-                acc[c][j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-            }
-    }
-    // combine the 8 warps in warp order
+    // combine the 8 warps (k-lanes) in a fixed tree: (w, w + 4), then (w, w + 2), then (0, 1); warp 0 ends up with the CTA's sums
     __syncthreads();  // every warp is done reading Bs
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) red[warp][cv * W + klo][j] = acc[0][j];
+    for (int half = 4; half >= 1; half >>= 1) {
+        if (warp >= half && warp < 2 * half) {
+#pragma unroll
+            for (int c = 0; c < W; ++c)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) red[warp - half][lane][c * NJ + j] = acc[c][j];
+        }
+        __syncthreads();
+        if (warp < half) {
+#pragma unroll
+            for (int c = 0; c < W; ++c)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) acc[c][j] += red[warp][lane][c * NJ + j];
+        }
+        __syncthreads();
+    }
+    if (warp == 0) {
+#pragma unroll
+        for (int c = 0; c < W; ++c)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) red[0][lane][c * NJ + j] = acc[c][j];
+    }
     __syncthreads();
     const int blk_cols = min(COLS, m - blockIdx.x * COLS);
     const int E = blk_cols * n;  // this CTA's outputs are contiguous in C and in every partial plane
     const size_t blk_off = (size_t)blockIdx.x * COLS * n;
     T* my_out = chunks == 1 ? C + blk_off : partial + (size_t)blockIdx.y * m * n + blk_off;
     for (int e = threadIdx.x; e < E; e += 256) {
-        const int c = e / n, j = e % n;
-        T s = red[0][c][j];
-#pragma unroll
-        for (int w = 1; w < 8; ++w) s += red[w][c][j];
+        const int c = e / n, j = e % n;          // output row c of the block = column vector c / W, element c % W
+        T s = red[0][c / W][(c % W) * NJ + j];
         if (chunks == 1 && bias) s += bias[blockIdx.x * COLS + c];
         my_out[e] = s;
     }
@@ -475,10 +485,10 @@ __global__ void __launch_bounds__(256) tiny_k_kernel(const T* __restrict__ A, co
 }  // namespace skinny
 
 template <typename T, int RPW, int NJ>
-static int launch_rows_vec_inst(Ctx* ctx, int m, int n, int k, int tb, const T* A, const T* B, const T* bias, T* C) {
+static int launch_rows_vec_inst(Ctx* ctx, int m, int n, int k, int tb, const T* A, const T* B, const T* bias, const T* bias_col, T* C) {
     using namespace skinny;
     constexpr int W = 16 / (int)sizeof(T);
-    constexpr int KCP = 32 * W * 8 + W;
+    constexpr int KCP = 32 * W * (RPW >= 4 ? 4 : 8) + W;
     const int smem = NJ * KCP * (int)sizeof(T);
     static bool attr_set = false;
     if (!attr_set) {
@@ -486,36 +496,39 @@ static int launch_rows_vec_inst(Ctx* ctx, int m, int n, int k, int tb, const T* 
         attr_set = true;
     }
     const int tiles = (m + 8 * RPW - 1) / (8 * RPW);
-    const int grid = tiles < ctx->sm_count * 2 ? tiles : ctx->sm_count * 2;
-    skinny_rows_vec_kernel<T, RPW, NJ><<<grid, 256, smem, ctx->stream>>>(A, B, bias, C, m, n, k, tb);
+    // every CTA walks the same number of tiles (no straggler wave): at most two CTAs per SM
+    const int per_cta = (tiles + ctx->sm_count * 2 - 1) / (ctx->sm_count * 2);
+    const int grid = (tiles + per_cta - 1) / per_cta;
+    skinny_rows_vec_kernel<T, RPW, NJ><<<grid, 256, smem, ctx->stream>>>(A, B, bias, bias_col, C, m, n, k, tb);
     DSC_LAUNCH_CHECK(ctx);
     return DSC_OK;
 }
 
 template <typename T, int RPW>
-static int launch_rows_vec_nj(Ctx* ctx, int m, int n, int k, int tb, const T* A, const T* B, const T* bias, T* C) {
-    if (n <= 4) return launch_rows_vec_inst<T, RPW, 4>(ctx, m, n, k, tb, A, B, bias, C);
-    if (n <= 8) return launch_rows_vec_inst<T, RPW, 8>(ctx, m, n, k, tb, A, B, bias, C);
-    if (n <= 12) return launch_rows_vec_inst<T, RPW, 12>(ctx, m, n, k, tb, A, B, bias, C);
-    return launch_rows_vec_inst<T, RPW, 16>(ctx, m, n, k, tb, A, B, bias, C);
+static int launch_rows_vec_nj(Ctx* ctx, int m, int n, int k, int tb, const T* A, const T* B, const T* bias, const T* bias_col, T* C) {
+    if (n <= 4) return launch_rows_vec_inst<T, RPW, 4>(ctx, m, n, k, tb, A, B, bias, bias_col, C);
+    if (n <= 8) return launch_rows_vec_inst<T, RPW, 8>(ctx, m, n, k, tb, A, B, bias, bias_col, C);
+    if (n <= 12) return launch_rows_vec_inst<T, RPW, 12>(ctx, m, n, k, tb, A, B, bias, bias_col, C);
+    return launch_rows_vec_inst<T, RPW, 16>(ctx, m, n, k, tb, A, B, bias, bias_col, C);
 }
 
 template <typename T>
-static int launch_rows_vec(Ctx* ctx, int m, int n, int k, int tb, const T* A, const T* B, const T* bias, T* C) {
-    // two rows per warp once that still leaves >= 2 CTAs per SM (B^T is staged once per CTA)
-    if (m >= ctx->sm_count * 2 * 16) return launch_rows_vec_nj<T, 2>(ctx, m, n, k, tb, A, B, bias, C);
-    return launch_rows_vec_nj<T, 1>(ctx, m, n, k, tb, A, B, bias, C);
+static int launch_rows_vec(Ctx* ctx, int m, int n, int k, int tb, const T* A, const T* B, const T* bias, const T* bias_col, T* C) {
+    // four / two rows per warp once that still leaves >= 2 CTAs per SM (B^T is staged once per CTA and K chunk)
+    if (m >= ctx->sm_count * 32) return launch_rows_vec_nj<T, 4>(ctx, m, n, k, tb, A, B, bias, bias_col, C);
+    if (m >= ctx->sm_count * 2 * 16) return launch_rows_vec_nj<T, 2>(ctx, m, n, k, tb, A, B, bias, bias_col, C);
+    return launch_rows_vec_nj<T, 1>(ctx, m, n, k, tb, A, B, bias, bias_col, C);
 }
 
 template <typename T, int NJ>
 static int launch_cols_vec_inst(Ctx* ctx, int m, int n, int k, int tb, const T* A, const T* B, const T* bias, T* C) {
     using namespace skinny;
     constexpr int W = 16 / (int)sizeof(T);
-    const int gx = (m + 31) / 32;
+    const int gx = (m + 32 * W - 1) / (32 * W);
     // one full wave at 2 CTAs per SM (rounding the chunk count DOWN: a few CTAs more than a wave
-    // would double the run time); every k-lane (8W per CTA) gets at least 4 k-rows
+    // would double the run time); every k-lane (8 per CTA) gets at least 4 k-rows
     int chunks = (ctx->sm_count * 2) / gx;
-    const int max_chunks = (k + 32 * W - 1) / (32 * W);
+    const int max_chunks = (k + 127) / 128;   // every k-lane (one warp) walks at least 16 k-rows
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
     int rows_per_chunk = (k + chunks - 1) / chunks;
@@ -542,13 +555,15 @@ static int launch_cols_vec(Ctx* ctx, int m, int n, int k, int tb, const T* A, co
 
 // returns DSC_OK when handled, 1 when the shape is not a skinny / tiny-K product
 template <typename T>
-int gemm_skinny(Ctx* ctx, int ta, int tb, int m, int n, int k, const T* A, const T* B, const T* bias, T* C) {
+int gemm_skinny(Ctx* ctx, int ta, int tb, int m, int n, int k, const T* A, const T* B, const T* bias, T* C, const T* bias_col, int* bias_col_done) {
     using namespace skinny;
+    if (bias_col_done) *bias_col_done = 0;
     if (k <= NMAX && n >= 64 && (long)m * n >= 65536) {
         constexpr int W = 16 / (int)sizeof(T);
         const int gx = (n + 256 * W - 1) / (256 * W);
-        // ~4 CTAs per SM, slabs of at least 16 rows (the B registers are loaded once per CTA)
-        int gy = (ctx->sm_count * 4 + gx - 1) / gx;
+        // two CTAs per SM, all resident in one wave (512 CTAs at three per SM ran as 1.15 waves: the straggler wave doubled the
+        // time), slabs of at least 16 rows (the B registers are loaded once per CTA)
+        int gy = (ctx->sm_count * 2 + gx - 1) / gx;
         int rows_per_cta = (m + gy - 1) / gy;
         rows_per_cta = (rows_per_cta + 15) / 16 * 16;
         gy = (m + rows_per_cta - 1) / rows_per_cta;
@@ -566,7 +581,8 @@ int gemm_skinny(Ctx* ctx, int ta, int tb, int m, int n, int k, const T* A, const
     const bool a16 = (reinterpret_cast<uintptr_t>(A) & 15) == 0;
     int vec_cols = 1;
     if (!ta && a16 && k % W == 0) {
-        DSC_TRY((launch_rows_vec<T>(ctx, m, n, k, tb, A, B, bias, C)));
+        DSC_TRY((launch_rows_vec<T>(ctx, m, n, k, tb, A, B, bias, bias_col, C)));
+        if (bias_col && bias_col_done) *bias_col_done = 1;
     } else if (ta && a16 && m % W == 0 && (vec_cols = launch_cols_vec<T>(ctx, m, n, k, tb, A, B, bias, C)) != 1) {
         if (vec_cols != DSC_OK) return vec_cols;
     } else if (!ta) {
@@ -598,7 +614,7 @@ int gemm_skinny(Ctx* ctx, int ta, int tb, int m, int n, int k, const T* A, const
     return DSC_OK;
 }
 
-template int gemm_skinny<float>(Ctx*, int, int, int, int, int, const float*, const float*, const float*, float*);
-template int gemm_skinny<double>(Ctx*, int, int, int, int, int, const double*, const double*, const double*, double*);
+template int gemm_skinny<float>(Ctx*, int, int, int, int, int, const float*, const float*, const float*, float*, const float*, int*);
+template int gemm_skinny<double>(Ctx*, int, int, int, int, int, const double*, const double*, const double*, double*, const double*, int*);
 
 }  // namespace dsc

@@ -165,6 +165,9 @@ struct Ctx {
     void* p2p_local = nullptr;          // this rank's symmetric buffer: [flags | sync words | region A | region B]
     void* p2p_peer[8] = {nullptr};      // the same buffer of every rank as mapped into this process (p2p_peer[rank] == p2p_local)
     size_t p2p_region_bytes = 0;        // capacity of region A (= region B)
+    void* p2p_err_host = nullptr;       // mapped pinned word a timed-out barrier sets; p2p_err_dev: the same word as the kernel addresses it
+    void* p2p_err_dev = nullptr;
+    unsigned long long p2p_timeout_ns = 30000000000ull;
     dsc_stats stats{};
     int sm_count = kNumSMs;
     size_t smem_optin = 0;
@@ -206,6 +209,20 @@ int fail(int code, const char* fmt, ...);
                                cudaGetErrorString(_e), __FILE__, __LINE__);                    \
         }                                                                                      \
     } while (0)
+
+// ---- NVTX: one range per C-ABI entry point, named after the Backend<'T> member(s) it serves (DSC_FLAG_NVTX / DSC_NVTX=1) ----
+void nvtx_push(const char* name);   // dsc_core.cu (nvtx3 is header-only and costs nothing when no tool is attached)
+void nvtx_pop();
+struct NvtxRange {
+    bool on;
+    NvtxRange(dsc_ctx_t c, const char* name) : on(c && reinterpret_cast<Ctx*>(c)->magic == kCtxMagic && reinterpret_cast<Ctx*>(c)->nvtx) {
+        if (on) nvtx_push(name);
+    }
+    ~NvtxRange() {
+        if (on) nvtx_pop();
+    }
+};
+#define DSC_NVTX(c, name) ::dsc::NvtxRange _nvtx_range((c), (name))
 
 // ---- handle helpers -----------------------------------------------------------------------
 inline Buf* as_buf(dsc_buf_t h) {
@@ -330,7 +347,10 @@ int gemm_tf32x3_tcgen05(Ctx*, int ta, int tb, int m, int n, int k, MatRef A, Mat
 int gemm_f64_dmma(Ctx*, int ta, int tb, int m, int n, int k, const double* A, const double* B,
                   const double* bias, double* C);
 // n <= 16 products on CUDA cores (dsc_gemm_skinny.cu); same return convention
+// bias_col (may be null): v[j] added to every row after bias[i] — Add_M_M(., rows(v)) folded into the product when the
+// kernel taken supports it (*bias_col_done = 1), otherwise the caller adds it as a second pass
 template <typename T>
-int gemm_skinny(Ctx*, int ta, int tb, int m, int n, int k, const T* A, const T* B, const T* bias, T* C);
+int gemm_skinny(Ctx*, int ta, int tb, int m, int n, int k, const T* A, const T* B, const T* bias, T* C, const T* bias_col = nullptr,
+                int* bias_col_done = nullptr);
 
 }  // namespace dsc

@@ -213,10 +213,10 @@ using namespace dsc;
 
 extern "C" {
 #define DSC_LAPACK_API(P, T)                                                                                              \
-    int dsc_##P##gesv(dsc_ctx_t c, int32_t n, dsc_buf_t A, dsc_buf_t b, dsc_buf_t* x) { return gesv_impl<T>(c, n, A, b, x, "Solve_M_V"); } \
-    int dsc_##P##sysv(dsc_ctx_t c, int32_t n, dsc_buf_t A, dsc_buf_t b, dsc_buf_t* x) { return gesv_impl<T>(c, n, A, b, x, "SolveSymmetric_M_V"); } \
-    int dsc_##P##getri(dsc_ctx_t c, int32_t n, dsc_buf_t A, dsc_buf_t* out) { return getri_impl<T>(c, n, A, out); }         \
-    int dsc_##P##det(dsc_ctx_t c, int32_t n, dsc_buf_t A, T* out) { return det_impl<T>(c, n, A, out); }
+    int dsc_##P##gesv(dsc_ctx_t c, int32_t n, dsc_buf_t A, dsc_buf_t b, dsc_buf_t* x) { DSC_NVTX(c, "Solve_M_V"); return gesv_impl<T>(c, n, A, b, x, "Solve_M_V"); } \
+    int dsc_##P##sysv(dsc_ctx_t c, int32_t n, dsc_buf_t A, dsc_buf_t b, dsc_buf_t* x) { DSC_NVTX(c, "SolveSymmetric_M_V"); return gesv_impl<T>(c, n, A, b, x, "SolveSymmetric_M_V"); } \
+    int dsc_##P##getri(dsc_ctx_t c, int32_t n, dsc_buf_t A, dsc_buf_t* out) { DSC_NVTX(c, "Inverse_M"); return getri_impl<T>(c, n, A, out); }         \
+    int dsc_##P##det(dsc_ctx_t c, int32_t n, dsc_buf_t A, T* out) { DSC_NVTX(c, "Det_M"); return det_impl<T>(c, n, A, out); }
 DSC_LAPACK_API(s, float)
 DSC_LAPACK_API(d, double)
 }

@@ -194,8 +194,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ M, T*
         }
     };
     if (col0 < n) {
-        for (int r = r_begin + threadIdx.y; r < r_end; r += 64) {
-            T x[8][W];
+        auto load8 = [&](int r, T (&x)[8][W]) {   // rows r, r + 8, ..., r + 56 of this thread's column vector
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int rr = r + 8 * u;
@@ -214,10 +213,24 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ M, T*
                     }
                 }
             }
+        };
+        // software pipeline: the loads of the next 64 rows are in flight while the current ones are added (same order of additions)
+        T xa[8][W], xb[8][W];
+        int r = r_begin + threadIdx.y;
+        if (r < r_end) load8(r, xa);
+        for (; r < r_end; r += 128) {
+            if (r + 64 < r_end) load8(r + 64, xb);
 #pragma unroll
             for (int u = 0; u < 8; ++u)
 #pragma unroll
-                for (int w = 0; w < W; ++w) acc[w] += x[u][w];
+                for (int w = 0; w < W; ++w) acc[w] += xa[u][w];
+            if (r + 64 < r_end) {
+                if (r + 128 < r_end) load8(r + 128, xa);
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+#pragma unroll
+                    for (int w = 0; w < W; ++w) acc[w] += xb[u][w];
+            }
         }
     }
     tree();
@@ -261,21 +274,88 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ M, T*
     if (threadIdx.x == 0 && threadIdx.y == 0) tickets[blockIdx.x] = 0;
 }
 
+// Narrow matrices (n <= 32: the 10-column output layer).  The main kernel would run 10 of every 32 lanes; here a CTA takes a
+// contiguous slab of rows as a FLAT array: thread (rl, c) owns column c and row lane rl of RL = 256 / n lanes, so a warp reads
+// ~3 consecutive rows (contiguous bytes).  Row lanes are added in lane order by thread (0, c), slabs in slab order by the CTA
+// that arrives last: one launch, fixed order.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_narrow_kernel(const T* __restrict__ M, T* __restrict__ partial, T* __restrict__ v,
+                                                             unsigned int* __restrict__ ticket, int m, int n, int rows_per_cta, int accumulate) {
+    __shared__ T sm[256];
+    __shared__ int s_last;
+    const int RL = 256 / n;                       // row lanes
+    const int rl = threadIdx.x / n, c = threadIdx.x % n;
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(m, r0 + rows_per_cta);
+    T acc[4] = {T(0), T(0), T(0), T(0)};
+    if (rl < RL) {
+        int r = r0 + rl;
+        for (; r + 3 * RL < r1; r += 4 * RL) {    // 4 independent loads in flight
+            T x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) x[u] = M[(size_t)(r + u * RL) * n + c];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] += x[u];
+        }
+        for (; r < r1; r += RL) acc[0] += M[(size_t)r * n + c];
+    }
+    sm[threadIdx.x] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    __syncthreads();
+    T tot = T(0);
+    if (threadIdx.x < n) {
+        for (int l = 0; l < RL; ++l) tot += sm[l * n + threadIdx.x];
+        if (gridDim.x == 1) v[threadIdx.x] = accumulate ? v[threadIdx.x] + tot : tot;
+        else partial[(size_t)blockIdx.x * n + threadIdx.x] = tot;
+    }
+    if (gridDim.x == 1) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1u);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < n) {
+        T s = T(0);
+        for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(partial + (size_t)b * n + threadIdx.x);
+        v[threadIdx.x] = accumulate ? v[threadIdx.x] + s : s;
+    }
+    if (threadIdx.x == 0) *ticket = 0;
+}
+
 template <typename T>
 int colsum_launch(Ctx* ctx, const T* M, T* v, int m, int n, bool accumulate) {
+    if (n <= 32) {
+        // a CTA takes 4 rows per row lane (one batch of 4 independent loads per thread: the launch is latency-bound, the matrix is
+        // a few hundred KB), more only when that would exceed two CTAs per SM
+        const int RL = 256 / n;
+        int rows_per_cta = 4 * RL;
+        int ctas = (m + rows_per_cta - 1) / rows_per_cta;
+        if (ctas > 2 * ctx->sm_count) {
+            rows_per_cta = (m + 2 * ctx->sm_count - 1) / (2 * ctx->sm_count);
+            ctas = (m + rows_per_cta - 1) / rows_per_cta;
+        }
+        DSC_TRY(ensure_red_scratch(ctx, 256 + (size_t)ctas * n * sizeof(T)));
+        T* partial = reinterpret_cast<T*>(reinterpret_cast<char*>(ctx->red_scratch) + 256);
+        colsum_narrow_kernel<T><<<ctas, 256, 0, ctx->stream>>>(M, partial, v, ctx->tickets, m, n, rows_per_cta, accumulate ? 1 : 0);
+        DSC_LAUNCH_CHECK(ctx);
+        return DSC_OK;
+    }
     constexpr int W = sizeof(T) == 4 ? 4 : 2;
     bool vec = (n % W == 0) && al16(M);
     int cols_per_block = vec ? 32 * W : 32;
     int gx = (n + cols_per_block - 1) / cols_per_block;
-    // slabs of 64 rows (every thread issues its 8 loads at once), more when a slab would hold less
-    // than 16 KB (narrow matrices: the fence + ticket per CTA costs more than its loads) or when
-    // there would be more than 512 partial rows
+    // Row slabs: a CTA walks its slab 64 rows at a time (every thread has 8 loads of 16 bytes in flight).  The slab count is
+    // chosen so that the grid is about four CTAs per SM (all resident): with one CTA per 64-row slab (round 1) a tall matrix put 128 CTAs
+    // on every ticket counter and the launch ran at 0.36 of HBM — the fence + atomic + last-arriver pass per CTA, not the
+    // loads, set the time.  Slabs are multiples of 64 rows and never smaller than 64.
     int rows_per_chunk = 64;
     {
-        const size_t row_bytes = (size_t)(n < cols_per_block ? n : cols_per_block) * sizeof(T);
-        while ((size_t)rows_per_chunk * row_bytes < 16384 && rows_per_chunk < m) rows_per_chunk *= 2;
+        const int want_ctas = 4 * ctx->sm_count;
+        int chunks_want = want_ctas / gx;
+        if (chunks_want < 1) chunks_want = 1;
+        int rpc = (m + chunks_want - 1) / chunks_want;
+        rpc = (rpc + 63) / 64 * 64;
+        if (rpc > rows_per_chunk) rows_per_chunk = rpc;
     }
-    while ((m + rows_per_chunk - 1) / rows_per_chunk > 512) rows_per_chunk *= 2;
     int chunks = (m + rows_per_chunk - 1) / rows_per_chunk;
     if (gx > kNumTickets) return fail(DSC_E_SHAPE, "Add_M_Colwise_V_InPlace: %d columns exceed the supported maximum", n);
     size_t need = 256 + (size_t)chunks * n * sizeof(T);
@@ -450,17 +530,17 @@ using namespace dsc;
 
 extern "C" {
 #define DSC_LAYOUT_API(P, T)                                                                                              \
-    int dsc_##P##transpose(dsc_ctx_t c, int32_t m, int32_t n, dsc_buf_t A, dsc_buf_t* out) { return transpose_impl<T>(c, m, n, A, out); } \
-    int dsc_##P##permute(dsc_ctx_t c, int rank, const int64_t* shape, const int32_t* perm, dsc_buf_t A, dsc_buf_t* out) { \
+    int dsc_##P##transpose(dsc_ctx_t c, int32_t m, int32_t n, dsc_buf_t A, dsc_buf_t* out) { DSC_NVTX(c, "Transpose_M"); return transpose_impl<T>(c, m, n, A, out); } \
+    int dsc_##P##permute(dsc_ctx_t c, int rank, const int64_t* shape, const int32_t* perm, dsc_buf_t A, dsc_buf_t* out) { DSC_NVTX(c, "Permute_M"); \
         return permute_impl<T>(c, rank, shape, perm, A, out);                                                             \
     }                                                                                                                     \
-    int dsc_##P##repeat_rows(dsc_ctx_t c, int32_t m, dsc_buf_t v, dsc_buf_t* out) { return repeat_impl<T, true>(c, m, v, out); } \
-    int dsc_##P##repeat_cols(dsc_ctx_t c, int32_t n, dsc_buf_t v, dsc_buf_t* out) { return repeat_impl<T, false>(c, n, v, out); } \
-    int dsc_##P##colsum_inplace(dsc_ctx_t c, int32_t m, int32_t n, dsc_buf_t M, dsc_buf_t v) { return colsum_impl<T>(c, m, n, M, v); } \
-    int dsc_##P##add_v_mcols(dsc_ctx_t c, int32_t m, int32_t n, dsc_buf_t v, dsc_buf_t M, dsc_buf_t* out) {               \
+    int dsc_##P##repeat_rows(dsc_ctx_t c, int32_t m, dsc_buf_t v, dsc_buf_t* out) { DSC_NVTX(c, "RepeatReshapeCopy_V_MRows"); return repeat_impl<T, true>(c, m, v, out); } \
+    int dsc_##P##repeat_cols(dsc_ctx_t c, int32_t n, dsc_buf_t v, dsc_buf_t* out) { DSC_NVTX(c, "RepeatReshapeCopy_V_MCols"); return repeat_impl<T, false>(c, n, v, out); } \
+    int dsc_##P##colsum_inplace(dsc_ctx_t c, int32_t m, int32_t n, dsc_buf_t M, dsc_buf_t v) { DSC_NVTX(c, "Add_M_Colwise_V_InPlace"); return colsum_impl<T>(c, m, n, M, v); } \
+    int dsc_##P##add_v_mcols(dsc_ctx_t c, int32_t m, int32_t n, dsc_buf_t v, dsc_buf_t M, dsc_buf_t* out) { DSC_NVTX(c, "Add_V_MCols");               \
         return add_v_mcols_impl<T>(c, m, n, v, M, out);                                                                   \
     }                                                                                                                     \
-    int dsc_##P##diag(dsc_ctx_t c, int32_t m, int32_t n, dsc_buf_t A, dsc_buf_t* out) { return diag_impl<T>(c, m, n, A, out); }
+    int dsc_##P##diag(dsc_ctx_t c, int32_t m, int32_t n, dsc_buf_t A, dsc_buf_t* out) { DSC_NVTX(c, "Diagonal_M"); return diag_impl<T>(c, m, n, A, out); }
 DSC_LAYOUT_API(s, float)
 DSC_LAYOUT_API(d, double)
 }

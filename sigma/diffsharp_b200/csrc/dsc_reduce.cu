@@ -7,6 +7,7 @@
 // added in index order by whichever block arrives last), so the result is bit-identical from run
 // to run.  HBM-bound: 128-bit loads, 8 independent accumulators per thread.
 #include <float.h>
+#include <math.h>
 #include <stdlib.h>
 
 #include "dsc_internal.cuh"
@@ -18,13 +19,15 @@ constexpr int kRUnroll = 8;
 constexpr int kMaxPartials = 148 * 4;   // measured (tools/sum_tune.py, 4096^2): 592 -> 4.60 TB/s f32, 1184 -> 4.50, 2368 -> 4.30
 
 enum { R_SUM = 0, R_ASUM = 1, R_SUMSQ = 2, R_AMAX = 3, R_DOT = 4,
-       R_PRODSUM = 5 };   // Sum(a .* b) with the product ROUNDED first: bit-identical to Mul_Had_M_M followed by Sum_M
+       R_PRODSUM = 5,     // Sum(a .* b) with the product ROUNDED first: bit-identical to Mul_Had_M_M followed by Sum_M
+       R_SUMSQ_SCALED = 6 };   // Sum((a * scale)^2): the scaled pass of L2Norm_V when the plain sum of squares over- or underflows
 
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 
 template <int KIND, typename T>
 __device__ __forceinline__ T r_load(T a, T b) {
+    if constexpr (KIND == R_SUMSQ_SCALED) { const T t = a * b; return t * t; }   // b carries the scale
     if constexpr (KIND == R_SUM) return a;
     else if constexpr (KIND == R_ASUM) return a < T(0) ? -a : a;
     else if constexpr (KIND == R_SUMSQ) return a * a;
@@ -65,7 +68,7 @@ __device__ __forceinline__ T block_tree(T v, T* smem) {
 // elementwise kernels: contiguous chunks stream faster than a grid-wide stride).
 template <int KIND, typename T, bool VEC>
 __global__ void __launch_bounds__(kRThreads) reduce_kernel(const T* __restrict__ a, const T* __restrict__ b, size_t n, unsigned int per_cta_items,
-                                                            unsigned int* tickets, T* partials, T* result) {
+                                                            unsigned int* tickets, T* partials, T* result, T scale) {
     __shared__ T smem[kRThreads / 32];
     T acc[kRUnroll];
 #pragma unroll
@@ -90,7 +93,10 @@ __global__ void __launch_bounds__(kRThreads) reduce_kernel(const T* __restrict__
                 if (ok[u]) {
                     va[u] = *reinterpret_cast<const V*>(a + i * W);
                     if constexpr (KIND == R_DOT || KIND == R_PRODSUM) vb[u] = *reinterpret_cast<const V*>(b + i * W);
-                    else vb[u] = va[u];
+                    else if constexpr (KIND == R_SUMSQ_SCALED) {
+#pragma unroll
+                        for (int l = 0; l < W; ++l) (&vb[u].x)[l] = scale;
+                    } else vb[u] = va[u];
                 }
             }
 #pragma unroll
@@ -102,7 +108,7 @@ __global__ void __launch_bounds__(kRThreads) reduce_kernel(const T* __restrict__
         }
         if (blockIdx.x == 0) {  // scalar tail (< W elements)
             const size_t j = nvec * W + threadIdx.x;
-            if (j < n) acc[1] = r_comb<KIND>(acc[1], r_load<KIND>(a[j], (KIND == R_DOT || KIND == R_PRODSUM) ? b[j] : a[j]));
+            if (j < n) acc[1] = r_comb<KIND>(acc[1], r_load<KIND>(a[j], (KIND == R_DOT || KIND == R_PRODSUM) ? b[j] : (KIND == R_SUMSQ_SCALED ? scale : a[j])));
         }
     } else {
         const size_t end = cta_end < n ? cta_end : n;
@@ -110,7 +116,7 @@ __global__ void __launch_bounds__(kRThreads) reduce_kernel(const T* __restrict__
 #pragma unroll
             for (int u = 0; u < kRUnroll; ++u) {
                 const size_t j = base + (size_t)(it * kRUnroll + u) * kRThreads;
-                if (j < end) acc[u] = r_comb<KIND>(acc[u], r_load<KIND>(a[j], (KIND == R_DOT || KIND == R_PRODSUM) ? b[j] : a[j]));
+                if (j < end) acc[u] = r_comb<KIND>(acc[u], r_load<KIND>(a[j], (KIND == R_DOT || KIND == R_PRODSUM) ? b[j] : (KIND == R_SUMSQ_SCALED ? scale : a[j])));
             }
         }
     }
@@ -249,7 +255,7 @@ static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) 
 
 // Launch a reduction leaving the scalar at `result` (device pointer).
 template <int KIND, typename T>
-static int launch_reduce(Ctx* ctx, const T* a, const T* b, size_t n, T* result) {
+static int launch_reduce(Ctx* ctx, const T* a, const T* b, size_t n, T* result, T scale = T(1)) {
     unsigned int* ticket = ctx->tickets;
     T* partials = reinterpret_cast<T*>(reinterpret_cast<char*>(ctx->red_scratch) + 256);
     bool vec = al16(a) && ((KIND != R_DOT && KIND != R_PRODSUM) || al16(b));
@@ -267,8 +273,8 @@ static int launch_reduce(Ctx* ctx, const T* a, const T* b, size_t n, T* result) 
     }
     if (per_cta > 0xffffff00u) return fail(DSC_E_SHAPE, "reduction: input too large");
     const int grid = (int)((items + per_cta - 1) / per_cta);
-    if (vec) reduce_kernel<KIND, T, true><<<grid, kRThreads, 0, ctx->stream>>>(a, b, n, (unsigned int)per_cta, ticket, partials, result);
-    else reduce_kernel<KIND, T, false><<<grid, kRThreads, 0, ctx->stream>>>(a, b, n, (unsigned int)per_cta, ticket, partials, result);
+    if (vec) reduce_kernel<KIND, T, true><<<grid, kRThreads, 0, ctx->stream>>>(a, b, n, (unsigned int)per_cta, ticket, partials, result, scale);
+    else reduce_kernel<KIND, T, false><<<grid, kRThreads, 0, ctx->stream>>>(a, b, n, (unsigned int)per_cta, ticket, partials, result, scale);
     DSC_LAUNCH_CHECK(ctx);
     return DSC_OK;
 }
@@ -382,12 +388,32 @@ static int argext(dsc_ctx_t c, dsc_buf_t xh, int32_t* out, const char* name) {
     return fetch_scalar<int32_t>(ctx, slot, out);
 }
 
+// L2Norm_V (Backend.fs:83; the reference deployment calls ?nrm2, which scales): sqrt(sum x^2) in one pass; when that sum
+// overflowed, or is so small that squares were flushed (the result would be 0 / inf / inaccurate where ?nrm2 is not), a
+// second, scaled pass: s = max|x|, s * sqrt(sum (x / s)^2).  The host decides — the call returns a host scalar anyway.
 template <typename T>
 static int nrm2_impl(dsc_ctx_t c, dsc_buf_t xh, T* out) {
     T ss = T(0);
     DSC_TRY((reduce_scalar<R_SUMSQ, T>(c, xh, 0, &ss, "L2Norm_V")));
-    *out = (T)sqrt((double)ss);
-    if (sizeof(T) == 4) *out = sqrtf((float)ss);
+    const T tiny = sizeof(T) == 4 ? T(1e-30) : T(1e-290);
+    if (ss == ss && ss < T(INFINITY) && ss > tiny) {
+        *out = sizeof(T) == 4 ? (T)sqrtf((float)ss) : (T)sqrt((double)ss);
+        return DSC_OK;
+    }
+    T amax = T(0);
+    DSC_TRY((reduce_scalar<R_AMAX, T>(c, xh, 0, &amax, "L2Norm_V")));
+    if (!(amax > T(0)) || !(amax < T(INFINITY))) {   // all zeros, NaN or an infinite element: ?nrm2 returns 0 / NaN / inf
+        *out = amax == amax ? amax : amax;
+        return DSC_OK;
+    }
+    Ctx* ctx = as_ctx(c);
+    Buf* x;
+    DSC_TRY(in_buf(ctx, dtype_of<T>::value, xh, &x, "L2Norm_V"));
+    T* slot = result_slot<T>(ctx);
+    DSC_TRY((launch_reduce<R_SUMSQ_SCALED, T>(ctx, x->ptr<T>(), nullptr, x->len, slot, T(1) / amax)));
+    T scaled = T(0);
+    DSC_TRY(fetch_scalar<T>(ctx, slot, &scaled));
+    *out = amax * (sizeof(T) == 4 ? (T)sqrtf((float)scaled) : (T)sqrt((double)scaled));
     return DSC_OK;
 }
 
@@ -397,15 +423,15 @@ using namespace dsc;
 
 extern "C" {
 #define DSC_RED_API(P, T)                                                                                           \
-    int dsc_##P##dot(dsc_ctx_t c, dsc_buf_t x, dsc_buf_t y, T* out) { return reduce_scalar<R_DOT, T>(c, x, y, out, "Mul_Dot_V_V"); } \
-    int dsc_##P##asum(dsc_ctx_t c, dsc_buf_t x, T* out) { return reduce_scalar<R_ASUM, T>(c, x, 0, out, "L1Norm_V"); }  \
-    int dsc_##P##nrm2(dsc_ctx_t c, dsc_buf_t x, T* out) { return nrm2_impl<T>(c, x, out); }                          \
-    int dsc_##P##amax(dsc_ctx_t c, dsc_buf_t x, T* out) { return reduce_scalar<R_AMAX, T>(c, x, 0, out, "SupNorm_V"); } \
-    int dsc_##P##sum(dsc_ctx_t c, dsc_buf_t x, T* out) { return reduce_scalar<R_SUM, T>(c, x, 0, out, "Sum_V"); }      \
-    int dsc_##P##argmax(dsc_ctx_t c, dsc_buf_t x, int32_t* out) { return argext<T, true>(c, x, out, "MaxIndex_V"); }   \
-    int dsc_##P##argmin(dsc_ctx_t c, dsc_buf_t x, int32_t* out) { return argext<T, false>(c, x, out, "MinIndex_V"); }  \
-    int dsc_##P##sum_dev(dsc_ctx_t c, dsc_buf_t x, dsc_buf_t* out) { return reduce_dev<R_SUM, T>(c, x, 0, out, "Sum_V"); } \
-    int dsc_##P##dot_dev(dsc_ctx_t c, dsc_buf_t x, dsc_buf_t y, dsc_buf_t* out) { return reduce_dev<R_DOT, T>(c, x, y, out, "Mul_Dot_V_V"); }
+    int dsc_##P##dot(dsc_ctx_t c, dsc_buf_t x, dsc_buf_t y, T* out) { DSC_NVTX(c, "Mul_Dot_V_V"); return reduce_scalar<R_DOT, T>(c, x, y, out, "Mul_Dot_V_V"); } \
+    int dsc_##P##asum(dsc_ctx_t c, dsc_buf_t x, T* out) { DSC_NVTX(c, "L1Norm_V"); return reduce_scalar<R_ASUM, T>(c, x, 0, out, "L1Norm_V"); }  \
+    int dsc_##P##nrm2(dsc_ctx_t c, dsc_buf_t x, T* out) { DSC_NVTX(c, "L2Norm_V"); return nrm2_impl<T>(c, x, out); }                          \
+    int dsc_##P##amax(dsc_ctx_t c, dsc_buf_t x, T* out) { DSC_NVTX(c, "SupNorm_V"); return reduce_scalar<R_AMAX, T>(c, x, 0, out, "SupNorm_V"); } \
+    int dsc_##P##sum(dsc_ctx_t c, dsc_buf_t x, T* out) { DSC_NVTX(c, "Sum_V/Sum_M"); return reduce_scalar<R_SUM, T>(c, x, 0, out, "Sum_V"); }      \
+    int dsc_##P##argmax(dsc_ctx_t c, dsc_buf_t x, int32_t* out) { DSC_NVTX(c, "MaxIndex_V"); return argext<T, true>(c, x, out, "MaxIndex_V"); }   \
+    int dsc_##P##argmin(dsc_ctx_t c, dsc_buf_t x, int32_t* out) { DSC_NVTX(c, "MinIndex_V"); return argext<T, false>(c, x, out, "MinIndex_V"); }  \
+    int dsc_##P##sum_dev(dsc_ctx_t c, dsc_buf_t x, dsc_buf_t* out) { DSC_NVTX(c, "Sum_V/Sum_M (device scalar)"); return reduce_dev<R_SUM, T>(c, x, 0, out, "Sum_V"); } \
+    int dsc_##P##dot_dev(dsc_ctx_t c, dsc_buf_t x, dsc_buf_t y, dsc_buf_t* out) { DSC_NVTX(c, "Mul_Dot_V_V (device scalar)"); return reduce_dev<R_DOT, T>(c, x, y, out, "Mul_Dot_V_V"); }
 DSC_RED_API(s, float)
 DSC_RED_API(d, double)
 }

@@ -143,6 +143,24 @@ def test_c4_full_size_sampled_rows_against_the_oracle(oracle_provider, cuda_prov
     assert rel_err(Jg, ref) <= 1e-12 and rel_err(Jr, ref[rows]) <= 1e-12
 
 
+def test_c4_replicated_primal_is_bit_identical(cuda_provider, cuda_provider_nofuse, use_provider):
+    """config 4 at n = 4096: with deferred evaluation the row-replicated primal (DNDArray.OfRows(m, x)) stays a
+    vector — rows(x) W = rows(x W) through the same DMMA kernel, maps / sums of replicated rows on one row — and only the
+    tangent GEMMs run at full size; the Jacobian rows are bit for bit those of the undeferred sequence, which multiplies the
+    m identical rows out."""
+    n, c0, cnt = 4096, 512, 128
+    W1, b1, W2, b2, x = wl.jacobian_inputs(n)
+    out = []
+    for prov in (cuda_provider, cuda_provider_nofuse):
+        use_provider(prov)
+        st0 = prov.ctx.stats()["gemm_dmma"]
+        J = wl.jacobian_rows(wl.to_DM(W1), wl.to_DV(b1), wl.to_DM(W2), wl.to_DV(b2), wl.to_DV(x), c0, cnt).ToArray()
+        out.append((J, prov.ctx.stats()["gemm_dmma"] - st0))
+    assert np.array_equal(out[0][0], out[1][0])
+    assert out[0][1] == out[1][1] == 4            # four DMMA launches either way: two of them on ONE row when deferred
+    assert rel_err(out[0][0], wl.jacobian_closed_form(W1, b1, W2, b2, x)[c0:c0 + cnt]) <= 1e-12
+
+
 def test_c5_hvp(oracle_provider, cuda_provider, use_provider):
     """config 5: reverse-on-forward Hessian-vector product, float64, small vs oracle, full size vs closed form."""
     x, v, d = wl.hvp_inputs(4096)

@@ -536,3 +536,21 @@ def test_host_mirror_of_a_device_buffer(cuda_provider):
     assert float(b.Sum_V(view)) == 2 - 5 + 4 + 5
     b.Add_V_V_InPlace(b.CreateDataBuffer(np.ones(12, np.float32)), 0, buf, 0, 12)   # device-side write
     assert buf.Data is not d and buf.Data[3] == -4 and np.array_equal(buf.SubData, buf.Data)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_l2norm_at_the_extremes(cuda_provider, dtype):
+    """L2Norm_V where sqrt(sum x^2) over- or underflows but ?nrm2 (scaled) does not: same answers as OpenBLAS through the oracle."""
+    b, o = backend(cuda_provider, dtype), OracleBackend(dtype)
+    big, small = (1e30, 1e-30) if dtype == np.float32 else (1e200, 1e-200)
+    rng = np.random.default_rng(8)
+    base = rng.standard_normal(5001).astype(dtype)
+    for scale in (big, small, 1.0):
+        x = (base * dtype(scale)).astype(dtype)
+        g = float(b.L2Norm_V(b.CreateDataBuffer(x)))
+        r = float(o.L2Norm_V(NativeDataBuffer(x)))
+        exact = float(np.linalg.norm(base.astype(np.float64))) * scale
+        assert np.isfinite(g) and g > 0
+        assert abs(g - r) <= 4 * RTOL[np.dtype(dtype)] * r and abs(g - exact) <= 4 * RTOL[np.dtype(dtype)] * exact
+    assert float(b.L2Norm_V(b.CreateDataBuffer(np.zeros(7, dtype)))) == 0.0
+    assert np.isinf(float(b.L2Norm_V(b.CreateDataBuffer(np.array([1, np.inf, 2], dtype)))))

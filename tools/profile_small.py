@@ -20,12 +20,13 @@ H, dZ, Z3, W3 = mat(rows, 1024), mat(rows, 1024), mat(rows, 10), mat(1024, 10)
 b1 = b.CreateDataBuffer(np.zeros(1024, np.float32))
 b3 = b.CreateDataBuffer(np.zeros(10, np.float32))
 for _ in range(3):
-    b.Mul_M_M(H, W3)                      # skinny rows
-    b.Mul_M_M(Z3, b.Transpose_M(W3))      # tiny k
-    b.Mul_M_M(b.Transpose_M(H), Z3)       # skinny cols
+    keep = [b.Mul_M_M(H, W3),                      # skinny rows
+            b.Mul_M_M(Z3, b.Transpose_M(W3)),      # tiny k
+            b.Mul_M_M(b.Transpose_M(H), Z3)]       # skinny cols  (products are deferred: held until the flush below)
     b.Add_M_Colwise_V_InPlace(dZ, b1)
     b.Add_M_Colwise_V_InPlace(Z3, b3)
-    b._fused(0, dZ.DataBuffer, H.DataBuffer, (rows, 1024))
-    b._out(b._f["sum_dev"], 1, H.DataBuffer.handle)
+    keep.append(b._fused(0, dZ.DataBuffer, H.DataBuffer, (rows, 1024)))
+    keep.append(b._out(b._f["sum_dev"], 1, H.DataBuffer.handle))
+    ctx.flush()
 ctx.sync()
 print("done", ctx.stats())

@@ -12,9 +12,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sigma.diffsharp_b200.backend import CudaBackend, MapOp  # noqa: E402
 from sigma.diffsharp_b200.buffers import CudaContext, ShapedDataBufferView  # noqa: E402
 
-ctx = CudaContext(0)
-b = CudaBackend(np.float32, ctx=ctx, fuse=False)
-bf = CudaBackend(np.float32, ctx=ctx, fuse=True)
+ctx = CudaContext(0)                      # deferred evaluation on: products are held and run when the graph capture ends
+b = bf = CudaBackend(np.float32, ctx=ctx)
 rng = np.random.default_rng(0)
 
 
@@ -28,11 +27,15 @@ def vec(n, sets=3):
 
 def time_graph(fns, reps=5):
     for f in fns:
-        f()
+        keep0 = f()
+        ctx.flush()
     ctx.sync()
     ctx.graph_begin()
     try:
-        keep = [f() for f in fns]
+        keep = []
+        for f in fns:
+            keep.append(f())
+            ctx.flush()                   # one call's kernels after the other, as in the step
     finally:
         g = ctx.graph_end()
     e0, e1 = ctx.event(), ctx.event()
