@@ -324,14 +324,17 @@ def other_configs(provider, comm, rank, world, peaks):
         return J
     ms, J = timed(c4, 3, warm=1)
     tangent_gflop = 2 * 2.0 * n * n * (c1 - c0) / 1e9           # tangent GEMMs only
-    issued_gflop = 2 * tangent_gflop                            # the faithful sequence also runs the replicated-primal GEMMs
+    # the call sequence also multiplies the row-replicated primal by both weight matrices; the library computes
+    # rows(x) W as rows(x W): ONE row through the same DMMA kernel (a 128-row tile is issued for it), bit-identical
+    issued_gflop = tangent_gflop + 2 * 2.0 * n * n * 128 / 1e9
     sample = J.ToArray()[:4]
     ref = wl.jacobian_closed_form(W1, b1, W2, b2, x)[c0:c0 + 4]
     out["C4_jacobian_f64"] = {
         "ms": round(ms, 3), "rows_per_gpu": c1 - c0, "jacobians_per_s": round(1e3 / ms, 3),
         "algorithmic_TFLOP/s_per_gpu": round(tangent_gflop / ms, 2), "issued_TFLOP/s_per_gpu": round(issued_gflop / ms, 2),
         "peak": round(peaks["fp64_tflops"], 1), "frac_issued": round(issued_gflop / ms / peaks["fp64_tflops"], 3),
-        "max_rel_err_vs_closed_form": float(np.abs(sample - ref).max() / np.abs(ref).max()), "scaling": "strong (n = 4096 fixed)"}
+        "max_rel_err_vs_closed_form": float(np.abs(sample - ref).max() / np.abs(ref).max()), "scaling": "strong (n = 4096 fixed)",
+        "note": "algorithmic = the tangent GEMMs (SURVEY 8d); the replicated-primal products of the call sequence run on one row (deferred evaluation, bit-identical)"}
     del full, J, tangent
 
     def graph_timed(fn, backends, iters):

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Launches the f32 GEMM shapes of the config-3 step (rows x 1024 x 1024 forward, weight adjoint with
-K = rows) a few times: the target of ncu captures (python tools/profile_gemm.py [rows])."""
+"""Launches the five float32 tensor-core products of the config-3 step (forward 784 / 1024, input adjoint, the two weight
+adjoints with K = rows) a few times, in step order and with the operand-split companions handled as in the step (dropped at
+the start of every iteration): the target of ncu captures (python tools/profile_gemm.py [rows])."""
 import os
 import sys
 
@@ -15,9 +16,16 @@ ctx = CudaContext(0)
 b = CudaBackend(np.float32, ctx=ctx)
 rng = np.random.default_rng(0)
 mat = lambda m, n: ShapedDataBufferView(b.CreateDataBuffer((rng.random(m * n) * 2 - 1).astype(np.float32)), m, n)  # noqa: E731
-H, dZ, W2 = mat(rows, 1024), mat(rows, 1024), mat(1024, 1024)
+X, H, dZ, W1, W2 = mat(rows, 784), mat(rows, 1024), mat(rows, 1024), mat(784, 1024), mat(1024, 1024)
 for _ in range(3):
-    b.Mul_M_M(H, W2)                     # forward
-    b.Mul_M_M(b.Transpose_M(H), dZ)      # weight adjoint
+    ctx.invalidate_caches()
+    keep = []
+    for f in (lambda: b.Mul_M_M(X, W1),                       # forward, layer 1
+              lambda: b.Mul_M_M(H, W2),                       # forward, layer 2
+              lambda: b.Mul_M_M(dZ, b.Transpose_M(W2)),       # input adjoint
+              lambda: b.Mul_M_M(b.Transpose_M(H), dZ),        # weight adjoint, layer 2
+              lambda: b.Mul_M_M(b.Transpose_M(X), dZ)):       # weight adjoint, layer 1
+        keep.append(f())
+        ctx.flush()                                           # products are deferred: run this one now
 ctx.sync()
 print("done", ctx.stats())
