@@ -374,6 +374,7 @@ static int allreduce_impl(dsc_ctx_t c, int32_t count, const dsc_buf_t* bufs) {
     if (ctx->nranks == 1) return DSC_OK;  // a single rank already holds the sum
     if (!ctx->nccl_comm) return fail(DSC_E_NCCL, "allreduce: dsc_comm_init has not been called");
     DSC_TRY(p2p_check_error(ctx));
+    DSC_TRY(co_schedule_pending_gemms(ctx));   // the weight adjoints about to be summed are usually still-deferred products: run them side by side
     PackTable<T> t;
     t.count = 0;
     t.start[0] = 0;

@@ -437,6 +437,14 @@ int dsc_destroy(dsc_ctx_t c) {
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     if (ctx->gemm_ws) cudaFree(ctx->gemm_ws);
     if (ctx->gemm_tickets) cudaFree(ctx->gemm_tickets);
+    if (ctx->lane_gemm_ws) cudaFree(ctx->lane_gemm_ws);
+    if (ctx->lane_gemm_tickets) cudaFree(ctx->lane_gemm_tickets);
+    if (ctx->lane_stream) {
+        cudaStreamSynchronize(ctx->lane_stream);
+        cudaEventDestroy(ctx->ev_lane_fork);
+        cudaEventDestroy(ctx->ev_lane_done);
+        cudaStreamDestroy(ctx->lane_stream);
+    }
     if (ctx->comm_stage) cudaFree(ctx->comm_stage);
     cudaEventDestroy(ctx->ev_compute);
     cudaEventDestroy(ctx->ev_comm);

@@ -5,6 +5,10 @@
 //   f32: tcgen05/TMEM/TMA 3xTF32 kernel (dsc_gemm_tf32x3.cu) when eligible, else this kernel.
 //   f64: DMMA kernel (dsc_gemm_dmma.cu) when eligible, else this kernel.
 // There is no host fallback: every path is a device kernel of this library.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "dsc_internal.cuh"
 
 namespace dsc {
@@ -262,6 +266,71 @@ static int gemm_entry(dsc_ctx_t c, int ta, int tb, int32_t m, int32_t n, int32_t
         }
     }
     lazy_unref(hold);
+    return st;
+}
+
+// ---- two compute lanes for small pending products -------------------------------------------------------------------------
+static void lane_swap(Ctx* ctx) {   // the lane's stream / workspace / tickets become the context's current ones (and back)
+    std::swap(ctx->stream, ctx->lane_stream);
+    std::swap(ctx->gemm_ws, ctx->lane_gemm_ws);
+    std::swap(ctx->gemm_ws_bytes, ctx->lane_gemm_ws_bytes);
+    std::swap(ctx->gemm_tickets, ctx->lane_gemm_tickets);
+    std::swap(ctx->gemm_tickets_n, ctx->lane_gemm_tickets_n);
+}
+
+static bool co_schedulable(Ctx* ctx, const LazyNode* nd) {
+    if (nd->kind != LZ_GEMM || nd->dtype != DSC_F32 || nd->result || nd->consumed || nd->refs <= 0 || nd->nsrc != 2) return false;
+    if (nd->m < 128 || nd->n < 32 || nd->k < 32 || nd->n <= 16 || nd->k <= 16) return false;                 // tensor-core shapes only
+    if (((nd->m + 127) / 128) * ((nd->n + 127) / 128) > ctx->sm_count / 2) return false;                  // it would fill the GPU by itself
+    for (int i = 0; i < 2; ++i)
+        if (nd->src[i].node || !nd->src[i].block) return false;                                          // operands are plain device windows
+    return true;
+}
+
+int co_schedule_pending_gemms(Ctx* ctx) {
+    static const bool off = [] { const char* e = getenv("DSC_GEMM_LANES"); return e && *e == '0'; }();
+    if (off || !ctx->fuse || (ctx->flags & DSC_FLAG_GEMM_FP32_SIMT)) return DSC_OK;
+    std::vector<LazyNode*> todo;
+    for (LazyNode* nd : ctx->pending)
+        if (co_schedulable(ctx, nd)) todo.push_back(nd);
+    if (todo.size() < 2) return DSC_OK;
+    if (!ctx->lane_stream) {
+        DSC_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->lane_stream, cudaStreamNonBlocking));
+        DSC_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_lane_fork, cudaEventDisableTiming));
+        DSC_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_lane_done, cudaEventDisableTiming));
+    }
+    for (LazyNode* nd : todo) nd->refs++;
+    int st = DSC_OK;
+    for (size_t i = 0; i + 1 < todo.size() && st == DSC_OK; i += 2) {
+        LazyNode *a = todo[i], *b = todo[i + 1];
+        if (a->result || b->result) continue;
+        // an operand the two products share must already have its operand-split companion: otherwise both lanes would create
+        // and read it concurrently
+        bool shared_unsplit = false;
+        for (int x = 0; x < 2; ++x)
+            for (int y = 0; y < 2; ++y)
+                if (a->src[x].block == b->src[y].block && !(a->src[x].block->lo && a->src[x].block->lo_epoch == ctx->cache_epoch)) shared_unsplit = true;
+        if (shared_unsplit) continue;
+        // the operands of the lane's product stay referenced until the lanes have joined: a block released meanwhile could be
+        // handed to compute-stream work while the lane still reads it
+        Block* held[2] = {b->src[0].block, b->src[1].block};
+        for (Block* h : held) h->refs++;
+        ctx->gemm_sm_budget = ctx->sm_count / 2;
+        st = cudaEventRecord(ctx->ev_lane_fork, ctx->stream) == cudaSuccess ? DSC_OK : fail(DSC_E_CUDA, "lane fork failed");
+        if (st == DSC_OK) {
+            lane_swap(ctx);
+            st = cudaStreamWaitEvent(ctx->stream, ctx->ev_lane_fork, 0) == cudaSuccess ? DSC_OK : fail(DSC_E_CUDA, "lane fork failed");
+            if (st == DSC_OK) st = lazy_materialize(b);
+            if (st == DSC_OK && cudaEventRecord(ctx->ev_lane_done, ctx->stream) != cudaSuccess) st = fail(DSC_E_CUDA, "lane join failed");
+            lane_swap(ctx);
+        }
+        if (st == DSC_OK) st = lazy_materialize(a);
+        if (cudaStreamWaitEvent(ctx->stream, ctx->ev_lane_done, 0) != cudaSuccess && st == DSC_OK) st = fail(DSC_E_CUDA, "lane join failed");
+        ctx->gemm_sm_budget = 0;
+        for (Block* h : held) block_release(h);
+        if (st == DSC_OK) ctx->stats_co_scheduled++;
+    }
+    for (LazyNode* nd : todo) lazy_unref(nd);
     return st;
 }
 

@@ -1367,7 +1367,8 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, MatRef Am
     const bool allow_wide = ctx->gemm_force_fuse == 2;
     auto has_converters = [allow_wide](int c, bool pr) { return pr ? (allow_wide && c == 256) : c < 256; };
     PlanIn pin;
-    pin.sm_count = ctx->sm_count; pin.m = m; pin.n = n; pin.k = k; pin.num_kb = num_kb; pin.cpt = cpt;
+    pin.sm_count = (ctx->gemm_sm_budget > 0 && ctx->gemm_sm_budget < ctx->sm_count) ? ctx->gemm_sm_budget : ctx->sm_count;
+    pin.m = m; pin.n = n; pin.k = k; pin.num_kb = num_kb; pin.cpt = cpt;
     pin.a_direct = pa.direct; pin.b_direct = pb.direct;
     // Operand-split companions (Block::lo): present when the kernel that produced the matrix wrote one next to it (bias +
     // activation, adjoint chains, GEMM epilogues) or an earlier product split it and nobody has written the block since.

@@ -178,6 +178,18 @@ struct Ctx {
     uint64_t other_stream_seq = 0;       // counts copies / collectives queued off the compute stream (see Block::last_other_stream_use)
     uint64_t other_stream_joined = 0;    // value of other_stream_seq the compute stream is known to be ordered after
     bool nvtx = false;                   // DSC_FLAG_NVTX: one NVTX range per C-ABI entry
+    // Second compute lane: two independent, small float32 tensor-core products that are both pending (the weight adjoints of
+    // a batch shard: neither fills the GPU, each is mostly fixed cost) run CONCURRENTLY — one on the compute stream, one on
+    // this stream, each planned for half of the SMs, with its own workspace and tickets (co_schedule_pending_gemms).
+    cudaStream_t lane_stream = nullptr;
+    cudaEvent_t ev_lane_fork = nullptr, ev_lane_done = nullptr;
+    void* lane_gemm_ws = nullptr;
+    size_t lane_gemm_ws_bytes = 0;
+    unsigned int* lane_gemm_tickets = nullptr;
+    size_t lane_gemm_tickets_n = 0;
+    int gemm_sm_budget = 0;              // > 0: the planner of the float32 GEMM may use this many SMs only
+    bool lane_pending = false;           // work queued on the lane stream that the compute stream has not been ordered after
+    uint64_t stats_co_scheduled = 0;
 };
 
 // ---- error plumbing -----------------------------------------------------------------------
@@ -270,6 +282,7 @@ void lazy_set_result(LazyNode* nd, Block* blk, size_t off);    // a fused consum
 int buf_resolve(Buf* b);                                       // make b a plain device window
 int operand_resolve(Ctx* ctx, Operand& o);                     // make o a plain device window (materialises its node)
 int flush_pending(Ctx* ctx);                                   // run every deferred compute node nobody has consumed
+int co_schedule_pending_gemms(Ctx* ctx);                       // pairs of small pending float32 products: one per compute lane, concurrently (dsc_gemm.cu)
 inline LazyNode* lazy_of(const Buf* b) { return (b && !b->block) ? b->lazy : nullptr; }
 inline LazyNode* lazy_of(const Buf* b, int kind) { LazyNode* n = lazy_of(b); return (n && n->kind == kind && !n->result) ? n : nullptr; }
 void buf_adopt(Buf* b, Block* blk, size_t off, bool cow);      // b := window over blk (takes a new reference)

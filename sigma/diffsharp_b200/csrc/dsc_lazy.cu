@@ -235,6 +235,7 @@ void lazy_set_result(LazyNode* nd, Block* blk, size_t off) {
 }
 
 int flush_pending(Ctx* ctx) {
+    DSC_TRY(co_schedule_pending_gemms(ctx));
     // materialising a node removes it (and possibly others) from the list: walk a snapshot, holding the nodes
     std::vector<LazyNode*> todo;
     for (LazyNode* nd : ctx->pending)

@@ -554,3 +554,29 @@ def test_l2norm_at_the_extremes(cuda_provider, dtype):
         assert abs(g - r) <= 4 * RTOL[np.dtype(dtype)] * r and abs(g - exact) <= 4 * RTOL[np.dtype(dtype)] * exact
     assert float(b.L2Norm_V(b.CreateDataBuffer(np.zeros(7, dtype)))) == 0.0
     assert np.isinf(float(b.L2Norm_V(b.CreateDataBuffer(np.array([1, np.inf, 2], dtype)))))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape,perm", [((2, 3, 4), (2, 0, 1)), ((5, 7), (1, 0)), ((4, 1, 6, 3), (3, 1, 0, 2)), ((3, 4, 5, 2, 2), (4, 0, 3, 1, 2)),
+                                        ((64, 33), (0, 1)), ((17, 9, 11), (1, 2, 0)), ((128, 96, 3), (2, 1, 0))])
+def test_permute_and_reshape_bit_exact(cuda_provider, dtype, shape, perm):
+    """Permute_M (Backend.fs:128, call site AD.Float32.fs:2773) against numpy.transpose for ranks 2..5, and Reshape_M
+    (Backend.fs:129, :2780): same storage, new shape — bit exact, and the reshaped view feeds other ops correctly."""
+    b, o = backend(cuda_provider, dtype), OracleBackend(dtype)
+    a = np.random.default_rng(len(shape)).standard_normal(shape).astype(dtype)
+    v = ShapedDataBufferView(b.CreateDataBuffer(a.reshape(-1)), *shape)
+    p = b.Permute_M(v, list(perm))
+    assert tuple(p.Shape) == tuple(shape[i] for i in perm)
+    assert np.array_equal(p.DataBuffer.SubData.reshape(p.Shape), np.transpose(a, perm))
+    hp = o.Permute_M(ShapedDataBufferView(NativeDataBuffer(a.reshape(-1)), *shape), list(perm))
+    assert np.array_equal(p.DataBuffer.SubData, hp.DataBuffer.SubData)
+    n = a.size
+    rows = shape[0]
+    r = b.Reshape_M(v, [n // rows, rows])
+    assert r.DataBuffer is v.DataBuffer and tuple(r.Shape) == (n // rows, rows)            # the same buffer, no copy
+    assert np.array_equal(b.Transpose_M(r).to_numpy(), a.reshape(n // rows, rows).T)
+    flat = b.ReshapeCopy_MRows_V(r)                                                         # Backend.fs:109: a COPY
+    back = b.ReshapeCopy_V_MRows(rows, flat)                                                # Backend.fs:134
+    assert np.array_equal(flat.SubData, a.reshape(-1)) and tuple(back.Shape) == (rows, n // rows)
+    b.Add_V_V_InPlace(b.CreateDataBuffer(np.ones(n, dtype)), 0, flat, 0, n)
+    assert np.array_equal(v.DataBuffer.SubData, a.reshape(-1))                              # the source is untouched by writes to the copy
