@@ -306,6 +306,8 @@ DSC_API int dsc_comm_join(dsc_ctx_t ctx); /* compute stream waits for everything
 /* %globaltimer (ns) at the phase boundaries of the last peer-memory all-reduce as CTA 0 saw them:
  * start, packed, barrier 1, reduced + broadcast, barrier 2, unpacked (tools/allreduce_bench.py). */
 DSC_API int dsc_comm_debug_stamps(dsc_ctx_t ctx, uint64_t out[6]);
+/* the same for the last call (back = 0) or the one before it (back = 1): a step issues two all-reduces (dist.py) */
+DSC_API int dsc_comm_debug_stamps_at(dsc_ctx_t ctx, int back, uint64_t out[6]);
 DSC_API int dsc_comm_destroy(dsc_ctx_t ctx);
 
 #ifdef __cplusplus

@@ -155,6 +155,7 @@ _sig("dsc_comm_unique_id", C.c_void_p)
 _sig("dsc_comm_init", ctx_t, C.c_int, C.c_int, C.c_void_p)
 _sig("dsc_comm_join", ctx_t)
 _sig("dsc_comm_debug_stamps", ctx_t, P(C.c_uint64))
+_sig("dsc_comm_debug_stamps_at", ctx_t, C.c_int, P(C.c_uint64))
 _sig("dsc_comm_destroy", ctx_t)
 
 for _p, _T in (("s", C.c_float), ("d", C.c_double)):

@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kP2PThreads) allreduce_p2p_kernel(P2PTable<T> 
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x, gsize = (long long)gridDim.x * blockDim.x;
     const long long nvec = total / W;
     const long long per = (nvec + a.nranks - 1) / a.nranks;   // vectors per slice (the last slice may be short)
-    unsigned long long* stamps = reinterpret_cast<unsigned long long*>(local + 512);   // phase boundaries as CTA 0 sees them (dsc_comm_debug_stamps)
+    unsigned long long* stamps = reinterpret_cast<unsigned long long*>(local + 512 + 64 * (epoch & 1u));   // phase boundaries as CTA 0 sees them, of the last two calls (dsc_comm_debug_stamps)
     const bool stamp = blockIdx.x == 0 && threadIdx.x == 0;
     if (stamp) stamps[0] = globaltimer_ns();
     // 0. scatter this rank's contribution: slice q -> rank q, region A, slot [rank].
@@ -336,7 +336,23 @@ static int p2p_check_error(Ctx* ctx) {
 // The all-reduce kernel meets at grid-wide barriers: every CTA must be resident.  A cooperative launch makes the driver
 // guarantee that (or fail the launch) instead of relying on an idle GPU; the grid is sized from the occupancy query.
 template <typename T>
-static int p2p_launch(Ctx* ctx, P2PTable<T>& pt, P2PArgs& a) {
+static int p2p_launch(Ctx* ctx, P2PTable<T>& pt, P2PArgs& a, bool beside_compute) {
+    if (beside_compute) {
+        // On the second compute lane the all-reduce runs BESIDE the backward products of the compute stream: a small grid that
+        // fits on the SMs the concurrent GEMM leaves free (its persistent grid is tiles x K-ranges, 112-128 of 148 SMs for the
+        // step's products; a GEMM CTA's registers and shared memory leave no room for a second resident CTA).  Measured on two
+        // GPUs (tools/lane_ar_sweep.sh): 32 x 512 and 96 x 256 threads give the shortest step, 64 x 128 the longest.
+        static const int lane_ctas = [] { const char* e = getenv("DSC_P2P_LANE_CTAS"); int v = e ? atoi(e) : 32; return v < 1 ? 1 : (v > kP2PMaxCtas ? kP2PMaxCtas : v); }();
+        static const int lane_threads = [] { const char* e = getenv("DSC_P2P_LANE_THREADS"); int v = e ? atoi(e) : 512; return v < 32 ? 32 : (v > kP2PThreads ? kP2PThreads : v / 32 * 32); }();
+        void* args[] = {&pt, &a};
+        cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(allreduce_p2p_kernel<T>), dim3(lane_ctas), dim3(lane_threads), args, 0, ctx->stream);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            allreduce_p2p_kernel<T><<<lane_ctas, lane_threads, 0, ctx->stream>>>(pt, a);
+        }
+        DSC_LAUNCH_CHECK(ctx);
+        return DSC_OK;
+    }
     static int max_ctas = -1;
     if (max_ctas < 0) {
         int per_sm = 0;
@@ -375,20 +391,51 @@ static int allreduce_impl(dsc_ctx_t c, int32_t count, const dsc_buf_t* bufs) {
     if (!ctx->nccl_comm) return fail(DSC_E_NCCL, "allreduce: dsc_comm_init has not been called");
     DSC_TRY(p2p_check_error(ctx));
     DSC_TRY(co_schedule_pending_gemms(ctx));   // the weight adjoints about to be summed are usually still-deferred products: run them side by side
+    // Adjoints that were all produced on the second compute lane (weight-adjoint products and bias column sums of the layers
+    // whose reverse sweep is already behind the compute stream) are summed over the ranks ON that lane: the collective then
+    // overlaps whatever the compute stream still has to do (the first layer's backward products).  Every rank issues the same
+    // sequence of collectives on the same buffers whichever stream each of them picks, and a rank's collectives stay ordered
+    // among themselves (the next one on the compute stream joins the lane first).
+    bool on_lane = false;
+    if (ctx->lanes_enabled && ctx->p2p_ok && !ctx->on_lane && !ctx->comm_pending && lane_busy(ctx) && count > 0) {
+        on_lane = true;
+        long long total = 0;
+        int live = 0;
+        for (int i = 0; i < count && on_lane; ++i) {
+            Buf* b = as_buf(bufs[i]);
+            if (!b || b->ctx != ctx || b->dtype != dtype_of<T>::value) { on_lane = false; break; }
+            if (b->len == 0) continue;
+            Block* blk = b->block ? b->block : ((b->lazy && b->lazy->result) ? b->lazy->result : nullptr);
+            if (!blk || blk->lane_w <= ctx->lane_joined || blk->w_seq != 0 || !blk->readers.empty() || blk->views > 0 || b->is_view) on_lane = false;
+            total += b->len + 4;
+            live++;
+        }
+        if (live == 0 || (size_t)total * sizeof(T) + 16 * kP2PMaxRanks > ctx->p2p_region_bytes) on_lane = false;
+    }
+    if (lane_debug()) fprintf(stderr, "[dsc lane] all-reduce of %d buffers: %s\n", count, on_lane ? "on the lane" : "on the compute stream");
+    if (on_lane) DSC_TRY(lane_enter(ctx, nullptr, 0, false));
+    else DSC_TRY(lane_join(ctx));   // collectives of one rank never overlap each other
     PackTable<T> t;
     t.count = 0;
     t.start[0] = 0;
-    for (int i = 0; i < count; ++i) {
+    Block* touched[kMaxPack];
+    int st = DSC_OK;
+    for (int i = 0; i < count && st == DSC_OK; ++i) {
         Buf* b;
-        DSC_TRY(in_buf(ctx, dtype_of<T>::value, bufs[i], &b, "allreduce: buffer"));
-        if (b->len == 0) continue;
-        DSC_TRY(buf_writable(ctx, b));  // in-place collective
-        if (t.count == kMaxPack) return fail(DSC_E_INVALID, "allreduce: more than %d buffers in one call", kMaxPack);
+        st = in_buf(ctx, dtype_of<T>::value, bufs[i], &b, "allreduce: buffer");
+        if (st != DSC_OK || b->len == 0) continue;
+        st = buf_writable(ctx, b);  // in-place collective
+        if (st != DSC_OK) break;
+        if (t.count == kMaxPack) { st = fail(DSC_E_INVALID, "allreduce: more than %d buffers in one call", kMaxPack); break; }
+        touched[t.count] = b->block;
         t.ptr[t.count] = b->ptr<T>();
         t.start[t.count + 1] = t.start[t.count] + b->len;
         t.count++;
     }
-    if (t.count == 0) return DSC_OK;
+    if (st != DSC_OK || t.count == 0) {
+        if (on_lane) lane_leave(ctx, nullptr, 0, touched, t.count);
+        return st;
+    }
     const int dt = sizeof(T) == 4 ? NCCL_FLOAT32 : NCCL_FLOAT64;
     const long long total = t.start[t.count];
     if (ctx->p2p_ok && (size_t)(total + 4 * t.count) * sizeof(T) + 16 * kP2PMaxRanks <= ctx->p2p_region_bytes) {
@@ -413,10 +460,12 @@ static int allreduce_impl(dsc_ctx_t c, int32_t count, const dsc_buf_t* bufs) {
         a.region_bytes = ctx->p2p_region_bytes;
         a.err_host = reinterpret_cast<unsigned int*>(ctx->p2p_err_dev);
         a.timeout_ns = ctx->p2p_timeout_ns;
-        DSC_TRY(p2p_launch<T>(ctx, pt, a));
-        ctx->stats.allreduce_p2p++;
-        return DSC_OK;
+        st = p2p_launch<T>(ctx, pt, a, on_lane);
+        if (on_lane) lane_leave(ctx, nullptr, 0, touched, t.count);
+        if (st == DSC_OK) ctx->stats.allreduce_p2p++;
+        return st;
     }
+    if (on_lane) return fail(DSC_E_INVALID, "allreduce: lane path without peer memory");   // not reachable: on_lane requires p2p_ok and the payload to fit
     ctx->stats.allreduce_nccl++;
     for (int i = 0; i < count; ++i) {   // these blocks are now in use on the communication stream: not recycled / overwritten before it is joined
         Buf* b = as_buf(bufs[i]);
@@ -595,14 +644,21 @@ int dsc_comm_init(dsc_ctx_t c, int nranks, int rank, const uint8_t idbytes[128])
     return p2p_setup(ctx);
 }
 
-int dsc_comm_debug_stamps(dsc_ctx_t c, uint64_t out[6]) {
+int dsc_comm_debug_stamps_at(dsc_ctx_t c, int back, uint64_t out[6]) {
     if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
     Ctx* ctx = as_ctx(c);
     if (!ctx->p2p_local) return fail(DSC_E_NCCL, "the peer-memory all-reduce is not set up");
+    if (back < 0 || back > 1 || !out) return fail(DSC_E_INVALID, "dsc_comm_debug_stamps_at: back must be 0 (the last call) or 1 (the one before)");
+    DSC_TRY(flush_pending(ctx));
     DSC_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    DSC_CUDA_CHECK(cudaMemcpy(out, reinterpret_cast<char*>(ctx->p2p_local) + 512, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    unsigned int epoch = 0;   // the NEXT call's epoch: the last one ran with epoch - 1
+    DSC_CUDA_CHECK(cudaMemcpy(&epoch, reinterpret_cast<char*>(ctx->p2p_local) + 256 + 4, sizeof(epoch), cudaMemcpyDeviceToHost));
+    const unsigned int slot = (epoch - 1u - (unsigned)back) & 1u;
+    DSC_CUDA_CHECK(cudaMemcpy(out, reinterpret_cast<char*>(ctx->p2p_local) + 512 + 64 * slot, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return DSC_OK;
 }
+
+int dsc_comm_debug_stamps(dsc_ctx_t c, uint64_t out[6]) { return dsc_comm_debug_stamps_at(c, 0, out); }
 
 int dsc_comm_join(dsc_ctx_t c) {
     if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");

@@ -170,6 +170,8 @@ int buf_writable(Ctx* ctx, Buf* b, bool on_compute_stream) {
     // a write issued on the compute stream must come after copies / collectives that touch the block on the other streams
     // (a write issued on a copy stream is ordered by that stream and by the caller's events)
     if (on_compute_stream && old->last_other_stream_use > ctx->other_stream_joined) DSC_TRY(join_other_streams(ctx));
+    DSC_TRY(lane_gate_write(ctx, old));   // ... and after lane operations that read or wrote it
+    if (old->lo) DSC_TRY(lane_gate_write(ctx, old->lo));
     if (old->cow > 0 && old->refs > 1) {
         // copy-on-write: other handles (or deferred results) hold this block and must keep seeing the old value
         Block* nb = nullptr;
@@ -244,7 +246,7 @@ int in_buf_peek(Ctx* ctx, int dtype, dsc_buf_t h, Buf** res, const char* what) {
     if (!b) return fail(DSC_E_INVALID, "%s is not a live buffer handle", what);
     if (b->ctx != ctx) return fail(DSC_E_INVALID, "%s belongs to another context", what);
     if (b->dtype != dtype) return fail(DSC_E_DTYPE, "%s has the wrong dtype", what);
-    *res = b;
+    *res = b;   // no data is touched yet: the callers reach it through buf_resolve / operand_resolve / buf_writable, which order the compute stream after the second lane where needed
     return DSC_OK;
 }
 
@@ -263,6 +265,17 @@ int ensure_red_scratch(Ctx* ctx, size_t bytes) {
     DSC_CUDA_CHECK(cudaMalloc(&ctx->red_scratch, bytes));
     DSC_CUDA_CHECK(cudaMemsetAsync(ctx->red_scratch, 0, bytes, ctx->stream));
     ctx->red_scratch_bytes = bytes;
+    if (ctx->lane_red_scratch_bytes < bytes) {   // the second compute lane's scratch keeps pace (see ensure_gemm_ws)
+        if (ctx->lane_red_scratch) {
+            DSC_CUDA_CHECK(cudaDeviceSynchronize());
+            cudaFree(ctx->lane_red_scratch);
+        }
+        ctx->lane_red_scratch = nullptr;
+        ctx->lane_red_scratch_bytes = 0;
+        DSC_CUDA_CHECK(cudaMalloc(&ctx->lane_red_scratch, bytes));
+        DSC_CUDA_CHECK(cudaMemsetAsync(ctx->lane_red_scratch, 0, bytes, ctx->stream));
+        ctx->lane_red_scratch_bytes = bytes;
+    }
     return DSC_OK;
 }
 
@@ -279,6 +292,18 @@ int ensure_gemm_ws(Ctx* ctx, size_t bytes) {
     size_t want = (bytes + (8u << 20) - 1) & ~size_t((8u << 20) - 1);
     DSC_CUDA_CHECK(cudaMalloc(&ctx->gemm_ws, want));
     ctx->gemm_ws_bytes = want;
+    // The other compute lane runs a subset of the products this one has seen: keep its workspace as large, so that a pair of
+    // products co-scheduled for the first time while a graph is being captured never has to grow anything.
+    if (ctx->lane_gemm_ws_bytes < want) {
+        if (ctx->lane_gemm_ws) {
+            DSC_CUDA_CHECK(cudaDeviceSynchronize());
+            cudaFree(ctx->lane_gemm_ws);
+        }
+        ctx->lane_gemm_ws = nullptr;
+        ctx->lane_gemm_ws_bytes = 0;
+        DSC_CUDA_CHECK(cudaMalloc(&ctx->lane_gemm_ws, want));
+        ctx->lane_gemm_ws_bytes = want;
+    }
     return DSC_OK;
 }
 
@@ -297,6 +322,17 @@ int ensure_gemm_tickets(Ctx* ctx, size_t count) {
     DSC_CUDA_CHECK(cudaMalloc(&ctx->gemm_tickets, want * sizeof(unsigned int)));
     DSC_CUDA_CHECK(cudaMemsetAsync(ctx->gemm_tickets, 0, want * sizeof(unsigned int), ctx->stream));
     ctx->gemm_tickets_n = want;
+    if (ctx->lane_gemm_tickets_n < want) {   // see ensure_gemm_ws: the other lane keeps pace
+        if (ctx->lane_gemm_tickets) {
+            DSC_CUDA_CHECK(cudaDeviceSynchronize());
+            cudaFree(ctx->lane_gemm_tickets);
+        }
+        ctx->lane_gemm_tickets = nullptr;
+        ctx->lane_gemm_tickets_n = 0;
+        DSC_CUDA_CHECK(cudaMalloc(&ctx->lane_gemm_tickets, want * sizeof(unsigned int)));
+        DSC_CUDA_CHECK(cudaMemsetAsync(ctx->lane_gemm_tickets, 0, want * sizeof(unsigned int), ctx->stream));
+        ctx->lane_gemm_tickets_n = want;
+    }
     return DSC_OK;
 }
 
@@ -409,6 +445,12 @@ int dsc_create(int device, uint32_t flags, dsc_ctx_t* out) {
     if (s != DSC_OK) return s;
     DSC_CUDA_CHECK(cudaMalloc(&ctx->tickets, kNumTickets * sizeof(unsigned int)));
     DSC_CUDA_CHECK(cudaMemsetAsync(ctx->tickets, 0, kNumTickets * sizeof(unsigned int), ctx->stream));
+    DSC_CUDA_CHECK(cudaMalloc(&ctx->lane_tickets, kNumTickets * sizeof(unsigned int)));
+    DSC_CUDA_CHECK(cudaMemsetAsync(ctx->lane_tickets, 0, kNumTickets * sizeof(unsigned int), ctx->stream));
+    {
+        const char* e = getenv("DSC_LANES");   // DSC_LANES=0: every kernel on the compute stream (debugging / measurements)
+        ctx->lanes_enabled = ctx->fuse && !(e && *e == '0');
+    }
     *out = reinterpret_cast<dsc_ctx_t>(ctx);
     return DSC_OK;
 }
@@ -419,6 +461,7 @@ int dsc_destroy(dsc_ctx_t c) {
     if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
     Ctx* ctx = as_ctx(c);
     cudaSetDevice(ctx->device);
+    lane_join(ctx);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->comm_stream);
     cudaStreamSynchronize(ctx->copy_stream);
@@ -439,6 +482,8 @@ int dsc_destroy(dsc_ctx_t c) {
     if (ctx->gemm_tickets) cudaFree(ctx->gemm_tickets);
     if (ctx->lane_gemm_ws) cudaFree(ctx->lane_gemm_ws);
     if (ctx->lane_gemm_tickets) cudaFree(ctx->lane_gemm_tickets);
+    if (ctx->lane_red_scratch) cudaFree(ctx->lane_red_scratch);
+    if (ctx->lane_tickets) cudaFree(ctx->lane_tickets);
     if (ctx->lane_stream) {
         cudaStreamSynchronize(ctx->lane_stream);
         cudaEventDestroy(ctx->ev_lane_fork);
@@ -563,11 +608,12 @@ int dsc_graph_begin(dsc_ctx_t c) {
     if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
     Ctx* ctx = as_ctx(c);
     if (ctx->capturing) return fail(DSC_E_INVALID, "already capturing");
-    DSC_TRY(flush_pending(ctx));
+    DSC_TRY(flush_pending(ctx));   // joins the second compute lane as well
     DSC_TRY(join_other_streams(ctx));
     DSC_TRY(dsc_comm_join(c));
     DSC_CUDA_CHECK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
     ctx->capturing = true;
+    ctx->lane_fork_seq = 0;   // the lane is not part of this capture until its first fork
     ctx->cache_epoch++;   // operand-split companions computed before the capture are not trusted inside it: a replay must recompute what depends on replaced inputs
     ctx->cur_arena = ctx->next_arena++;
     ctx->arena_pool = Pool();
@@ -591,6 +637,7 @@ int dsc_graph_end(dsc_ctx_t c, dsc_graph_t* out) {
         }
     }
     ctx->cache_epoch++;   // ... and companions computed inside it describe the capture-time values only
+    ctx->lane_fork_seq = 0;
     if (ctx->comm_pending) {
         // join the communication stream back into the origin stream before ending the capture
         cudaEventRecord(ctx->ev_comm, ctx->comm_stream);
@@ -952,6 +999,7 @@ int dsc_set_fuse(dsc_ctx_t c, int on) {
 int dsc_invalidate_caches(dsc_ctx_t c) {
     if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
     as_ctx(c)->cache_epoch++;
+    if (!as_ctx(c)->capturing) as_ctx(c)->lane_fork_seq = 0;   // stale companions may be rewritten: the second lane's next operation forks afresh
     return DSC_OK;
 }
 

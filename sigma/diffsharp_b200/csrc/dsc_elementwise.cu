@@ -353,6 +353,8 @@ static float* attach_lo(Ctx* ctx, Block* blk, size_t off, size_t len) {
         Block* lo = nullptr;
         if (pool_alloc(ctx, blk->bytes, &lo) != DSC_OK) return nullptr;   // no companion: the GEMM will split on first use
         blk->lo = lo;
+    } else if (lane_gate_write(ctx, blk->lo) != DSC_OK) {   // an old companion the second compute lane may still be reading
+        return nullptr;
     }
     blk->lo_epoch = ctx->cache_epoch;
     blk->lo_begin = off;
@@ -700,6 +702,10 @@ static int map2_impl(dsc_ctx_t c, int op, dsc_buf_t ah, dsc_buf_t bh, dsc_buf_t*
             }
         }
     }
+    // x + empty, empty + x, x - empty (the reverse sweep pushes DVector.Zero / DNDArray.Zero as "no contribution" and then adds
+    // it, AD.Float32.fs:3919,3956,4257): the result is x — a copy-on-write alias instead of a copy
+    if (ctx->fuse && *yh == 0 && a->len != b->len && ((b->len == 0 && (op == DSC_OP_ADD || op == DSC_OP_SUB)) || (a->len == 0 && op == DSC_OP_ADD)))
+        return alias_of(ctx, a->len ? a : b, yh);
     DSC_TRY(buf_resolve(a));
     DSC_TRY(buf_resolve(b));
     // Empty operand = additive identity: the reverse sweep pushes DVector.Zero / DNDArray.Zero as "no

@@ -151,6 +151,8 @@ int gemm_run<double>(Ctx* ctx, int ta, int tb, int m, int n, int k, MatRef A, Ma
     return epilogue_pass<double>(ctx, m, n, C, ep);
 }
 
+static int try_sink_product(Ctx* ctx, LazyNode* nd);
+
 template <typename T>
 static int gemm_entry(dsc_ctx_t c, int ta, int tb, int32_t m, int32_t n, int32_t k, dsc_buf_t Ah, dsc_buf_t Bh, dsc_buf_t biash, dsc_buf_t* Ch) {
     if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
@@ -237,6 +239,16 @@ static int gemm_entry(dsc_ctx_t c, int ta, int tb, int32_t m, int32_t n, int32_t
         lazy_set_operand(nd, 0, oa);
         lazy_set_operand(nd, 1, ob);
         if (bias) lazy_set_operand(nd, 2, bias);
+        if (!bias && eta != (ta ? 1 : 0)) {   // A was a pending transpose: a weight adjoint — a sink of the reverse sweep
+            nd->refs++;
+            nd->sink = true;
+            const int ss = try_sink_product(ctx, nd);
+            nd->refs--;
+            if (ss < 0) {
+                lazy_unref(nd);
+                return ss;
+            }
+        }
         return lazy_buf(ctx, nd, Ch);
     }
     // hold the operands while they are being resolved (a deferred operand may be dropped by its handle meanwhile)
@@ -270,14 +282,6 @@ static int gemm_entry(dsc_ctx_t c, int ta, int tb, int32_t m, int32_t n, int32_t
 }
 
 // ---- two compute lanes for small pending products -------------------------------------------------------------------------
-static void lane_swap(Ctx* ctx) {   // the lane's stream / workspace / tickets become the context's current ones (and back)
-    std::swap(ctx->stream, ctx->lane_stream);
-    std::swap(ctx->gemm_ws, ctx->lane_gemm_ws);
-    std::swap(ctx->gemm_ws_bytes, ctx->lane_gemm_ws_bytes);
-    std::swap(ctx->gemm_tickets, ctx->lane_gemm_tickets);
-    std::swap(ctx->gemm_tickets_n, ctx->lane_gemm_tickets_n);
-}
-
 static bool co_schedulable(Ctx* ctx, const LazyNode* nd) {
     if (nd->kind != LZ_GEMM || nd->dtype != DSC_F32 || nd->result || nd->consumed || nd->refs <= 0 || nd->nsrc != 2) return false;
     if (nd->m < 128 || nd->n < 32 || nd->k < 32 || nd->n <= 16 || nd->k <= 16) return false;                 // tensor-core shapes only
@@ -287,18 +291,51 @@ static bool co_schedulable(Ctx* ctx, const LazyNode* nd) {
     return true;
 }
 
+// Run the deferred product `nd` on the second compute lane (operands: plain device windows).  sm_budget > 0 limits the SMs its
+// planner may use.
+static int run_on_lane(Ctx* ctx, LazyNode* nd, int sm_budget) {
+    // what it reads: the operand blocks and their operand-split companions; an operand that has no (valid) companion yet gets
+    // one from this product's pre-pass — written on the lane: compute-stream products that meet it later wait for the lane
+    // (lane_gate_read in the GEMM)
+    Block* ops[3];
+    bool had_lo[3];
+    int nops = 0;
+    Block* reads[8];
+    int nr = 0;
+    for (int i = 0; i < nd->nsrc && i < 3; ++i) {
+        Block* b = nd->src[i].node ? nd->src[i].node->result : nd->src[i].block;
+        if (!b) continue;
+        ops[nops] = b;
+        had_lo[nops] = b->lo && b->lo_epoch == ctx->cache_epoch;
+        reads[nr++] = b;
+        if (had_lo[nops]) reads[nr++] = b->lo;
+        b->refs++;   // materialising releases the node's own operand references
+        nops++;
+    }
+    int st = lane_enter(ctx, reads, nr, false);
+    Block* writes[4];
+    int nw = 0;
+    if (st == DSC_OK) {
+        const int saved = ctx->gemm_sm_budget;
+        ctx->gemm_sm_budget = sm_budget;
+        st = lazy_materialize(nd);
+        ctx->gemm_sm_budget = saved;
+        if (st == DSC_OK && nd->result) writes[nw++] = nd->result;
+        for (int i = 0; i < nops; ++i)
+            if (!had_lo[i] && ops[i]->lo && ops[i]->lo_epoch == ctx->cache_epoch) writes[nw++] = ops[i]->lo;
+        lane_leave(ctx, reads, nr, writes, nw);
+    }
+    for (int i = 0; i < nops; ++i) block_release(ops[i]);
+    return st;
+}
+
 int co_schedule_pending_gemms(Ctx* ctx) {
     static const bool off = [] { const char* e = getenv("DSC_GEMM_LANES"); return e && *e == '0'; }();
-    if (off || !ctx->fuse || (ctx->flags & DSC_FLAG_GEMM_FP32_SIMT)) return DSC_OK;
+    if (off || !ctx->fuse || !ctx->lanes_enabled || ctx->on_lane || (ctx->flags & DSC_FLAG_GEMM_FP32_SIMT)) return DSC_OK;
     std::vector<LazyNode*> todo;
     for (LazyNode* nd : ctx->pending)
         if (co_schedulable(ctx, nd)) todo.push_back(nd);
     if (todo.size() < 2) return DSC_OK;
-    if (!ctx->lane_stream) {
-        DSC_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->lane_stream, cudaStreamNonBlocking));
-        DSC_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_lane_fork, cudaEventDisableTiming));
-        DSC_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_lane_done, cudaEventDisableTiming));
-    }
     for (LazyNode* nd : todo) nd->refs++;
     int st = DSC_OK;
     for (size_t i = 0; i + 1 < todo.size() && st == DSC_OK; i += 2) {
@@ -311,27 +348,59 @@ int co_schedule_pending_gemms(Ctx* ctx) {
             for (int y = 0; y < 2; ++y)
                 if (a->src[x].block == b->src[y].block && !(a->src[x].block->lo && a->src[x].block->lo_epoch == ctx->cache_epoch)) shared_unsplit = true;
         if (shared_unsplit) continue;
-        // the operands of the lane's product stay referenced until the lanes have joined: a block released meanwhile could be
-        // handed to compute-stream work while the lane still reads it
-        Block* held[2] = {b->src[0].block, b->src[1].block};
-        for (Block* h : held) h->refs++;
-        ctx->gemm_sm_budget = ctx->sm_count / 2;
-        st = cudaEventRecord(ctx->ev_lane_fork, ctx->stream) == cudaSuccess ? DSC_OK : fail(DSC_E_CUDA, "lane fork failed");
+        st = run_on_lane(ctx, b, ctx->sm_count / 2);
         if (st == DSC_OK) {
-            lane_swap(ctx);
-            st = cudaStreamWaitEvent(ctx->stream, ctx->ev_lane_fork, 0) == cudaSuccess ? DSC_OK : fail(DSC_E_CUDA, "lane fork failed");
-            if (st == DSC_OK) st = lazy_materialize(b);
-            if (st == DSC_OK && cudaEventRecord(ctx->ev_lane_done, ctx->stream) != cudaSuccess) st = fail(DSC_E_CUDA, "lane join failed");
-            lane_swap(ctx);
+            const int saved = ctx->gemm_sm_budget;
+            ctx->gemm_sm_budget = ctx->sm_count / 2;
+            st = lazy_materialize(a);
+            ctx->gemm_sm_budget = saved;
         }
-        if (st == DSC_OK) st = lazy_materialize(a);
-        if (cudaStreamWaitEvent(ctx->stream, ctx->ev_lane_done, 0) != cudaSuccess && st == DSC_OK) st = fail(DSC_E_CUDA, "lane join failed");
-        ctx->gemm_sm_budget = 0;
-        for (Block* h : held) block_release(h);
         if (st == DSC_OK) ctx->stats_co_scheduled++;
     }
     for (LazyNode* nd : todo) lazy_unref(nd);
     return st;
+}
+
+// A product whose A operand was a pending Transpose_M is the weight adjoint of a reverse sweep (Transpose(a.P) * d.A,
+// AD.Float32.fs:4131-4143): its only consumer is the accumulation into the parameter's adjoint.  While the compute stream still
+// has another product pending (the input adjoint d.A * Transpose(b.P) of the same tape node, issued just before it), it runs at
+// once on the second compute lane instead of waiting for the end of the sweep: tensor-core products that are both small share
+// the SMs half and half, skinny ones (the output layer) simply run beside the compute stream.
+static int try_sink_product(Ctx* ctx, LazyNode* nd) {
+    if (!ctx->lanes_enabled || ctx->on_lane || nd->dtype != DSC_F32 || nd->nsrc != 2) return 1;
+    for (int i = 0; i < 2; ++i)
+        if (nd->src[i].node || !nd->src[i].block) return 1;
+    LazyNode* partner = nullptr;   // the newest other product still pending on the compute stream
+    for (LazyNode* o : ctx->pending)
+        if (o != nd && o->kind == LZ_GEMM && !o->result && !o->consumed && o->dtype == DSC_F32) partner = o;
+    if (lane_debug()) fprintf(stderr, "[dsc lane] weight adjoint %d x %d x %d: %s\n", nd->m, nd->n, nd->k, partner ? "a product is pending on the compute stream" : "nothing pending: runs now on the compute stream");
+    if (!partner) {
+        // nothing to run beside: the product still is a sink — no consumer will fold into its epilogue — so it starts now
+        // instead of at the end of the sweep (behind the column sums the calls that follow it issue)
+        nd->refs++;
+        const int st = lazy_materialize(nd);
+        lazy_unref(nd);
+        return st;
+    }
+    const bool skinny = nd->n <= 16 || nd->k <= 16 || nd->m <= 16;
+    if (skinny) {
+        if ((int64_t)nd->m * nd->n > (1 << 20)) return 1;
+        return run_on_lane(ctx, nd, 0);
+    }
+    if (ctx->flags & DSC_FLAG_GEMM_FP32_SIMT) return 1;
+    auto small = [&](const LazyNode* x) { return x->m >= 128 && x->n >= 32 && x->k >= 32 && ((x->m + 127) / 128) * ((x->n + 127) / 128) <= ctx->sm_count / 2; };
+    if (!small(nd) || !small(partner)) return 1;   // one of them fills the GPU by itself: nothing to gain side by side
+    DSC_TRY(run_on_lane(ctx, nd, ctx->sm_count / 2));
+    ctx->main_gemm_half_once = true;   // the partner takes the other half when the compute stream reaches it
+    ctx->stats_co_scheduled++;
+    if (partner->sink && !partner->src[0].node && !partner->src[1].node && partner->nsrc == 2) {
+        // the partner is a weight adjoint as well (it found nothing to run beside when it was issued): it starts now
+        partner->refs++;
+        const int st = lazy_materialize(partner);
+        lazy_unref(partner);
+        return st;
+    }
+    return DSC_OK;
 }
 
 }  // namespace dsc

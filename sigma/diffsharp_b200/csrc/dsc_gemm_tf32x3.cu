@@ -1368,6 +1368,12 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, MatRef Am
     auto has_converters = [allow_wide](int c, bool pr) { return pr ? (allow_wide && c == 256) : c < 256; };
     PlanIn pin;
     pin.sm_count = (ctx->gemm_sm_budget > 0 && ctx->gemm_sm_budget < ctx->sm_count) ? ctx->gemm_sm_budget : ctx->sm_count;
+    if (!ctx->on_lane && ctx->main_gemm_half_once) {
+        // the second compute lane has just been given a product planned for half of the SMs (its partner of the same tape node):
+        // this one takes the other half if the lane is still running it
+        ctx->main_gemm_half_once = false;
+        if (lane_busy(ctx) && ctx->gemm_sm_budget == 0) pin.sm_count = ctx->sm_count / 2;
+    }
     pin.m = m; pin.n = n; pin.k = k; pin.num_kb = num_kb; pin.cpt = cpt;
     pin.a_direct = pa.direct; pin.b_direct = pb.direct;
     // Operand-split companions (Block::lo): present when the kernel that produced the matrix wrote one next to it (bias +
@@ -1375,6 +1381,7 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, MatRef Am
     auto companion = [&](const MatRef& M, size_t count, bool direct) -> float* {
         Block* blk = M.block;
         if (!direct || !blk || !blk->lo || blk->lo_epoch != ctx->cache_epoch || M.off < blk->lo_begin || M.off + count > blk->lo_end) return nullptr;
+        if (lane_gate_read(ctx, blk->lo) != DSC_OK) return nullptr;   // a companion the second compute lane wrote
         return reinterpret_cast<float*>(blk->lo->ptr) + M.off;
     };
     float* a_comp = companion(Am, (size_t)m * k, pa.direct);
@@ -1437,6 +1444,8 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, MatRef Am
             Block* lo = nullptr;
             if (pool_alloc(ctx, blk->bytes, &lo) != DSC_OK) return nullptr;
             blk->lo = lo;
+        } else if (lane_gate_write(ctx, blk->lo) != DSC_OK) {
+            return nullptr;
         }
         blk->lo_epoch = ctx->cache_epoch;
         blk->lo_begin = M.off;

@@ -42,6 +42,11 @@ struct Block {
     uint64_t lo_epoch = 0;
     size_t lo_begin = 0, lo_end = 0;
     uint64_t last_other_stream_use = 0;   // ctx->other_stream_seq of the last copy / collective queued OFF the compute stream
+    // Ordering against the second compute lane (see Ctx::lane_*).  w_seq: 0 = written on the compute stream at a time not yet
+    // pinned; otherwise the value of ctx->order_seq pinned the first time a lane operation looked at the block (every write
+    // issued through the compute stream resets it to 0).  lane_w / lane_r: ctx->lane_seq of the last lane operation that
+    // wrote / read the block.
+    uint64_t w_seq = 0, lane_w = 0, lane_r = 0;
 };
 
 // Device twin of ISigmaDiffDataBuffer<'T> (reference Util.fs:133-141): a window over a Block, or a value whose
@@ -102,6 +107,7 @@ struct LazyNode {
     Block* result = nullptr;    // set once materialised (the node holds one reference)
     size_t result_off = 0;
     bool consumed = false;      // some consumer has taken this value (or its operands, fused): not flushed at sync points
+    bool sink = false;          // LZ_GEMM: a weight adjoint (A was a pending transpose) — nothing will fold into its epilogue
     int pending_idx = -1;       // position in ctx->pending, -1 when not listed
 };
 
@@ -181,8 +187,26 @@ struct Ctx {
     // Second compute lane: two independent, small float32 tensor-core products that are both pending (the weight adjoints of
     // a batch shard: neither fills the GPU, each is mostly fixed cost) run CONCURRENTLY — one on the compute stream, one on
     // this stream, each planned for half of the SMs, with its own workspace and tickets (co_schedule_pending_gemms).
+    //
+    // The same lane also runs the SINKS of a reverse sweep ahead of the compute stream: weight-adjoint products (their A
+    // operand is a pending transpose, AD.Float32.fs:4131-4143), the column sums of the bias adjoints (:4255) and the
+    // all-reduce of adjoints that were produced there (dsc_lane.cu).  Nothing on the compute stream waits for them until a
+    // consumer touches their result (lane_gate_read / lane_gate_write) or a synchronisation point joins the lane, so in a
+    // captured step they become a parallel branch of the graph: the adjoint all-reduce of the later layers overlaps the
+    // backward products of the first one.
     cudaStream_t lane_stream = nullptr;
     cudaEvent_t ev_lane_fork = nullptr, ev_lane_done = nullptr;
+    uint64_t order_seq = 0;              // counter behind Block::w_seq pins and lane forks
+    uint64_t lane_fork_seq = 0;          // the lane is ordered after every compute-stream write pinned at or below this value
+    uint64_t lane_seq = 0;               // lane operations issued
+    uint64_t lane_joined = 0;            // ... of which the compute stream is ordered after this many
+    std::vector<Block*> lane_held;       // blocks lane operations touch: referenced (never recycled) until the next join
+    bool on_lane = false;                // the context's stream / scratch members currently name the lane's (lane_enter .. lane_leave)
+    bool main_gemm_half_once = false;    // a tensor-core product has just gone to the lane with half of the SMs: the next one on the compute stream takes the other half
+    bool lanes_enabled = true;           // DSC_LANES=0 switches the sink lane off
+    void* lane_red_scratch = nullptr;    // the lane's own reduction scratch and tickets (column sums, skinny products)
+    size_t lane_red_scratch_bytes = 0;
+    unsigned int* lane_tickets = nullptr;
     void* lane_gemm_ws = nullptr;
     size_t lane_gemm_ws_bytes = 0;
     unsigned int* lane_gemm_tickets = nullptr;
@@ -283,6 +307,26 @@ int buf_resolve(Buf* b);                                       // make b a plain
 int operand_resolve(Ctx* ctx, Operand& o);                     // make o a plain device window (materialises its node)
 int flush_pending(Ctx* ctx);                                   // run every deferred compute node nobody has consumed
 int co_schedule_pending_gemms(Ctx* ctx);                       // pairs of small pending float32 products: one per compute lane, concurrently (dsc_gemm.cu)
+// ---- the sink lane (dsc_lane.cu) ----
+void lane_swap(Ctx* ctx);                                      // the lane's stream / workspace / scratch become the context's current ones (and back)
+// Can a lane operation that reads `reads` (written on the compute stream) start without a new fork, i.e. is the lane already
+// ordered after the last write of every one of them?  (Pins unpinned blocks: a block looked at for the first time now is not.)
+bool lane_sees(Ctx* ctx, Block* const* reads, int n);
+// Begin a lane operation: fork from the compute stream if some block in `reads` is not yet visible to the lane (or force_fork:
+// in-place writes to blocks the compute stream may still be reading), then make the lane current.  lane_leave stamps the
+// blocks read / written, holds them until the next join and makes the compute stream current again.
+int lane_enter(Ctx* ctx, Block* const* reads, int n, bool force_fork);
+void lane_leave(Ctx* ctx, Block* const* reads, int nr, Block* const* writes, int nw);
+int lane_join(Ctx* ctx);                                       // the compute stream waits for everything issued on the lane
+inline bool lane_busy(const Ctx* ctx) { return ctx->lane_seq > ctx->lane_joined; }
+bool lane_debug();                                             // DSC_LANE_DEBUG=1: every lane decision on stderr
+// compute-stream work is about to read / write blk
+inline int lane_gate_read(Ctx* ctx, Block* blk) { return (blk && !ctx->on_lane && blk->lane_w > ctx->lane_joined) ? lane_join(ctx) : DSC_OK; }
+inline int lane_gate_write(Ctx* ctx, Block* blk) {
+    if (!blk || ctx->on_lane) return DSC_OK;
+    blk->w_seq = 0;
+    return (blk->lane_w > ctx->lane_joined || blk->lane_r > ctx->lane_joined) ? lane_join(ctx) : DSC_OK;
+}
 inline LazyNode* lazy_of(const Buf* b) { return (b && !b->block) ? b->lazy : nullptr; }
 inline LazyNode* lazy_of(const Buf* b, int kind) { LazyNode* n = lazy_of(b); return (n && n->kind == kind && !n->result) ? n : nullptr; }
 void buf_adopt(Buf* b, Block* blk, size_t off, bool cow);      // b := window over blk (takes a new reference)

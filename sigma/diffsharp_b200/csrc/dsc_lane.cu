@@ -1,0 +1,124 @@
+// The second compute lane: a stream that runs the SINKS of a reverse sweep beside the compute stream.
+//
+// In the call sequence the unchanged AD layer issues for a reverse sweep (AD.Float32.fs:4118-4257) three kinds of calls
+// produce values nobody reads again before the sweep ends — they only land in the adjoint of a parameter:
+//   * the weight-adjoint product  Transpose(a.P) * d.A        (:4131-4143, the A operand is a pending Transpose_M),
+//   * the bias-adjoint column sum Add_M_Colwise_V_InPlace      (:4255),
+//   * (new surface) the all-reduce of those adjoints over the ranks.
+// On one stream they sit in the critical path of the sweep (the next layer's input adjoint waits behind the previous layer's
+// weight adjoint).  Here they are issued on a second stream — forked from the compute stream only where a true data
+// dependency requires it — and joined back only when somebody touches their result (lane_gate_read / lane_gate_write at
+// every handle access) or at a synchronisation point.  Captured in the step's CUDA graph the lane is a parallel branch: the
+// adjoint all-reduce of the later layers overlaps the backward products of the first layer, and small products that cannot
+// fill 148 SMs run two at a time on half of the SMs each.
+//
+// Ordering rules (all host-side bookkeeping, no device synchronisation):
+//   * Block::w_seq pins the position of a block's last compute-stream write in ctx->order_seq the first time a lane operation
+//     looks at it; a fork sets ctx->lane_fork_seq.  A lane operation whose inputs are all pinned at or below lane_fork_seq
+//     starts without a new fork — which is what lets the column sums and the all-reduce issued at the END of the sweep start
+//     right behind the weight adjoint issued in its middle.
+//   * Block::lane_w / lane_r stamp lane writes / reads; compute-stream readers of a lane-written block and writers of a
+//     lane-touched block join first.  Blocks a lane operation touches stay referenced until the next join, so the pool never
+//     hands them to compute-stream work the lane could still race with.
+//   * the lane has its own GEMM workspace, tickets and reduction scratch.
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "dsc_internal.cuh"
+
+namespace dsc {
+
+void lane_swap(Ctx* ctx) {
+    std::swap(ctx->stream, ctx->lane_stream);
+    std::swap(ctx->gemm_ws, ctx->lane_gemm_ws);
+    std::swap(ctx->gemm_ws_bytes, ctx->lane_gemm_ws_bytes);
+    std::swap(ctx->gemm_tickets, ctx->lane_gemm_tickets);
+    std::swap(ctx->gemm_tickets_n, ctx->lane_gemm_tickets_n);
+    std::swap(ctx->red_scratch, ctx->lane_red_scratch);
+    std::swap(ctx->red_scratch_bytes, ctx->lane_red_scratch_bytes);
+    std::swap(ctx->tickets, ctx->lane_tickets);
+    ctx->on_lane = !ctx->on_lane;
+}
+
+static int lane_ensure(Ctx* ctx) {
+    if (ctx->lane_stream) return DSC_OK;
+    DSC_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->lane_stream, cudaStreamNonBlocking));
+    DSC_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_lane_fork, cudaEventDisableTiming));
+    DSC_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_lane_done, cudaEventDisableTiming));
+    return DSC_OK;
+}
+
+bool lane_debug() {
+    static const bool on = [] { const char* e = getenv("DSC_LANE_DEBUG"); return e && *e == '1'; }();
+    return on;
+}
+
+static uint64_t pin(Ctx* ctx, Block* b) {
+    if (b->w_seq == 0) b->w_seq = ++ctx->order_seq;
+    return b->w_seq;
+}
+
+bool lane_sees(Ctx* ctx, Block* const* reads, int n) {
+    bool ok = ctx->lane_stream != nullptr && ctx->lane_fork_seq != 0;   // (the inputs are pinned in any case: a fork that follows covers them)
+    for (int i = 0; i < n; ++i) {
+        Block* b = reads[i];
+        if (!b) continue;
+        if (b->lane_w > ctx->lane_joined && b->w_seq == 0) continue;   // written by the lane itself (stream order)
+        const bool fresh = b->w_seq == 0;
+        if (pin(ctx, b) > ctx->lane_fork_seq) ok = false;
+        if (lane_debug()) fprintf(stderr, "[dsc lane]   read %p: %s at %llu, lane fork %llu\n", b->ptr, fresh ? "pinned now" : "pinned", (unsigned long long)b->w_seq, (unsigned long long)ctx->lane_fork_seq);
+    }
+    return ok;
+}
+
+int lane_enter(Ctx* ctx, Block* const* reads, int n, bool force_fork) {
+    if (ctx->on_lane) return fail(DSC_E_INVALID, "lane_enter: already on the lane");
+    DSC_TRY(lane_ensure(ctx));
+    const bool fork = force_fork || !lane_sees(ctx, reads, n);
+    if (lane_debug()) fprintf(stderr, "[dsc lane] enter: %s\n", fork ? "fork" : "no fork");
+    if (fork) {
+        DSC_CUDA_CHECK(cudaEventRecord(ctx->ev_lane_fork, ctx->stream));
+        DSC_CUDA_CHECK(cudaStreamWaitEvent(ctx->lane_stream, ctx->ev_lane_fork, 0));
+        ctx->lane_fork_seq = ++ctx->order_seq;   // everything pinned so far (the inputs above included) is visible to the lane
+    }
+    lane_swap(ctx);
+    return DSC_OK;
+}
+
+void lane_leave(Ctx* ctx, Block* const* reads, int nr, Block* const* writes, int nw) {
+    if (ctx->on_lane) lane_swap(ctx);
+    const uint64_t seq = ++ctx->lane_seq;
+    for (int i = 0; i < nr; ++i)
+        if (reads[i]) {
+            reads[i]->lane_r = seq;
+            reads[i]->refs++;
+            ctx->lane_held.push_back(reads[i]);
+        }
+    for (int i = 0; i < nw; ++i)
+        if (writes[i]) {
+            writes[i]->lane_w = seq;
+            writes[i]->w_seq = 0;
+            writes[i]->refs++;
+            ctx->lane_held.push_back(writes[i]);
+        }
+}
+
+int lane_join(Ctx* ctx) {
+    if (ctx->on_lane) return fail(DSC_E_INVALID, "lane_join while on the lane");
+    if (ctx->lane_seq == ctx->lane_joined) return DSC_OK;
+    int st = DSC_OK;
+    if (cudaEventRecord(ctx->ev_lane_done, ctx->lane_stream) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, ctx->ev_lane_done, 0) != cudaSuccess) {
+        cudaGetLastError();
+        st = fail(DSC_E_CUDA, "joining the second compute lane failed");
+    }
+    if (lane_debug()) fprintf(stderr, "[dsc lane] join (%llu operations)\n", (unsigned long long)(ctx->lane_seq - ctx->lane_joined));
+    ctx->lane_joined = ctx->lane_seq;
+    ctx->main_gemm_half_once = false;
+    std::vector<Block*> held;
+    held.swap(ctx->lane_held);
+    for (Block* b : held) block_release(b);
+    return st;
+}
+
+}  // namespace dsc

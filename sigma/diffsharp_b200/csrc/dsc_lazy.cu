@@ -121,20 +121,23 @@ void buf_adopt(Buf* b, Block* blk, size_t off, bool cow) {
 }
 
 int buf_resolve(Buf* b) {
-    if (b->block || b->len == 0 || !b->lazy) return DSC_OK;
+    if (b->block) return lane_gate_read(b->ctx, b->block);   // a value the second compute lane produced is about to be used by compute-stream work
+    if (b->len == 0 || !b->lazy) return DSC_OK;
     LazyNode* nd = b->lazy;
     DSC_TRY(lazy_materialize(nd));
     // other handles (or deferred operations) may still resolve to the same block: this handle then is a copy-on-write holder
     buf_adopt(b, nd->result, nd->result_off, nd->refs > 1);
     b->lazy = nullptr;
     lazy_unref(nd);
-    return DSC_OK;
+    return lane_gate_read(b->ctx, b->block);   // the value may have been produced on the second compute lane
 }
 
 int operand_resolve(Ctx* ctx, Operand& o) {
-    (void)ctx;
-    if (o.node) DSC_TRY(lazy_materialize(o.node));
-    return DSC_OK;
+    if (o.node) {
+        DSC_TRY(lazy_materialize(o.node));
+        return lane_gate_read(ctx, o.node->result);
+    }
+    return lane_gate_read(ctx, o.block);
 }
 
 template <typename T>
@@ -248,7 +251,9 @@ int flush_pending(Ctx* ctx) {
         if (status == DSC_OK && !nd->result && !nd->consumed && nd->refs > 1) status = lazy_materialize(nd);
         lazy_unref(nd);
     }
-    return status;
+    // a synchronisation point of the compute stream covers what the second compute lane was given as well
+    const int js = lane_join(ctx);
+    return status != DSC_OK ? status : js;
 }
 
 }  // namespace dsc

@@ -45,6 +45,30 @@ def _worker(rank, world, port, out):
     L, dW, db = D.sharded_mlp_grad(comm, wl.to_DM(X), wl.to_DM(Y), [wl.to_DM(w) for w in Ws], [wl.to_DV(b) for b in bs])
     comm.join()
     grads = [a.ToArray().copy() for a in dW + db]
+    # the same at a size whose products run on the tensor cores and whose weight adjoints, bias column sums and first
+    # all-reduce go to the second compute lane (csrc/dsc_lane.cu): eagerly, and as a replayed CUDA graph of the step
+    layers2, B2 = [160, 256, 192, 10], 512
+    q0, q1 = D.shard_range(B2, rank, world)
+    X2, Y2, Ws2, bs2 = wl.mlp_inputs(layers2, B2, seed=7, row_range=(q0, q1))
+    dX2, dY2, dWs2, dbs2 = wl.to_DM(X2), wl.to_DM(Y2), [wl.to_DM(w) for w in Ws2], [wl.to_DV(b) for b in bs2]
+    for _ in range(2):
+        _, dW2, db2 = D.sharded_mlp_grad(comm, dX2, dY2, dWs2, dbs2)
+        comm.join()
+        grads2 = [a.ToArray().copy() for a in dW2 + db2]
+    backend = prov.GetBackend(np.float32(0)).BackendHandle
+    backend.capture_scalars = []
+    prov.ctx.graph_begin()
+    try:
+        _, gW2, gb2 = D.sharded_mlp_grad(comm, dX2, dY2, dWs2, dbs2)
+    finally:
+        g2 = prov.ctx.graph_end()
+        backend.capture_scalars = None
+    for _ in range(3):
+        prov.ctx.graph_launch(g2)
+    prov.ctx.sync()
+    grads2g = [a.ToArray().copy() for a in gW2 + gb2]
+    del gW2, gb2
+    prov.ctx.graph_destroy(g2)
     # the all-reduce is deterministic and replayable: repeat it eagerly and from a CUDA graph on fresh
     # copies of known data and compare against world * data (exact: every rank contributes the same values)
     st = prov.ctx.stats()
@@ -86,7 +110,7 @@ def _worker(rank, world, port, out):
     comm.join()
     Jfull = full.SubData.reshape(n, n)
     if rank == 0:
-        out.put((float(L), grads, Jfull, used_p2p, st1["allreduce_nccl"]))
+        out.put((float(L), grads, Jfull, used_p2p, st1["allreduce_nccl"], grads2, grads2g))
     D.barrier()
     comm.close()
     dist.destroy_process_group()
@@ -101,7 +125,7 @@ def test_two_gpu_sharded_gradient_and_jacobian():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    L0, grads, Jfull, used_p2p, used_nccl = q.get()
+    L0, grads, Jfull, used_p2p, used_nccl, grads2, grads2g = q.get()
     print(f"all-reduces: peer-memory {used_p2p}, NCCL {used_nccl}")
     assert used_p2p + used_nccl > 0
     for p in procs:
@@ -118,6 +142,12 @@ def test_two_gpu_sharded_gradient_and_jacobian():
         for g, a in zip(grads, dW + db):
             ref = a.ToArray()
             assert np.abs(g - ref).max() <= 1e-5 * np.abs(ref).max()
+        X, Y, Ws, bs = wl.mlp_inputs([160, 256, 192, 10], 512, seed=7)
+        _, dW, db = wl.mlp_grad(wl.to_DM(X), wl.to_DM(Y), [wl.to_DM(w) for w in Ws], [wl.to_DV(b) for b in bs])
+        for g, gg, a in zip(grads2, grads2g, dW + db):
+            ref = a.ToArray()
+            assert np.abs(g - ref).max() <= 1e-5 * np.abs(ref).max()
+            assert np.array_equal(g, gg)   # the replayed graph (lane branches included) gives the bits of the eager step
         W1, b1, W2, b2, x = wl.jacobian_inputs(64)
         ref = wl.jacobian_closed_form(W1, b1, W2, b2, x)
         assert np.abs(Jfull - ref).max() <= 1e-12 * np.abs(ref).max()
