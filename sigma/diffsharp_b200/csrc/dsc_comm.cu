@@ -324,6 +324,278 @@ __global__ void __launch_bounds__(kP2PThreads) allreduce_p2p_kernel(P2PTable<T> 
     if (blockIdx.x == 0 && threadIdx.x == 0) sync[1] = epoch + 1u;
 }
 
+// ---- flag-in-data all-reduce (the default) ----------------------------------------------------------------------------
+// The barrier kernel above pays two grid-wide, system-scope barriers per call: ~8 us each on an NVSwitch node even when
+// the data phases take 2 us (profiles/README.md), i.e. 16 of the 23 us of a 3 MB all-reduce.  This kernel has no barrier.
+// Every 128-byte line that crosses NVLink carries 120 bytes of payload and an 8-byte flag (the call's sequence number) in
+// its last word; the eight lanes of a line group store it with one coalesced 128-byte store, which the fabric delivers
+// whole (the property NCCL's LL128 protocol rests on), and the receiver polls the line itself until the flag is the one it
+// waits for — the same load that sees the flag has the payload.  Same data flow as the barrier kernel (scatter slices,
+// add the N slots in rank order 0..N-1 — bit-identical on every rank and from run to run —, broadcast, unpack), but the
+// phases of different warps overlap and the only latency on the path is the one-way flight of a line.
+//   region A of rank q : N slots x lpr lines (slot s = the lines of slice q sent by rank s)
+//   region B           : the TL result lines
+// Re-use across calls needs no barrier either: a rank can only have finished call k (and start writing call k + 1) after
+// it received every result line of call k, hence after every peer has read all slots of call k; and nobody can produce a
+// result line of call k + 1 before every rank has sent its call-k+1 slots, i.e. has finished unpacking call k.
+constexpr int kLLPayloadWords = 15;   // 8-byte words of payload per 128-byte line
+
+__device__ __forceinline__ void st_line16(void* p, unsigned long long a, unsigned long long b) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void ld_line16(const void* p, unsigned long long& a, unsigned long long& b) {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+
+// The segment (buffer) of the call that packed 8-byte word w falls into, kept in registers: the walk over the packed space
+// is monotone, so the table in parameter space is searched only when a line crosses into another buffer.
+template <typename T>
+struct LLCursor {
+    long long e0 = 0, e1 = 0;   // element range [e0, e1) of the current segment in the packed space (e1 = start of the next one)
+    long long len = 0;          // valid elements (the rest up to e1 is alignment gap)
+    T* ptr = nullptr;
+    bool al8 = false;           // ptr is 8-byte aligned: a fully valid word moves with one 8-byte access
+    __device__ __forceinline__ void seek(const P2PTable<T>& t, long long e) {
+        if (e >= e0 && e < e1) return;
+        int lo = 0, hi = t.count - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (t.start[mid] <= e) lo = mid; else hi = mid - 1;
+        }
+        e0 = t.start[lo];
+        e1 = t.start[lo + 1];
+        len = t.len[lo];
+        ptr = t.ptr[lo];
+        al8 = (reinterpret_cast<uintptr_t>(ptr) & 7) == 0;
+    }
+    // pointer to the first element of word w and the number of valid elements there (0 past the end / in a gap)
+    __device__ __forceinline__ T* locate(const P2PTable<T>& t, long long w, long long total, int& valid) {
+        constexpr int EPW = 8 / (int)sizeof(T);
+        const long long e = w * EPW;
+        valid = 0;
+        if (e >= total) return nullptr;
+        seek(t, e);
+        const long long i = e - e0, left = len - i;
+        valid = left <= 0 ? 0 : (left >= EPW ? EPW : (int)left);
+        return ptr + i;
+    }
+};
+template <typename T>
+__device__ __forceinline__ unsigned long long ll_load(const T* p, int valid, bool al8) {
+    if constexpr (sizeof(T) == 8) {
+        return valid > 0 ? (unsigned long long)__double_as_longlong(*p) : 0ull;
+    } else {
+        if (al8 && valid == 2) return *reinterpret_cast<const unsigned long long*>(p);
+        const unsigned int a = valid > 0 ? __float_as_uint(p[0]) : 0u;
+        const unsigned int b = valid > 1 ? __float_as_uint(p[1]) : 0u;
+        return (unsigned long long)a | ((unsigned long long)b << 32);
+    }
+}
+template <typename T>
+__device__ __forceinline__ void ll_store(T* p, int valid, bool al8, unsigned long long v) {
+    if constexpr (sizeof(T) == 8) {
+        if (valid > 0) *p = __longlong_as_double((long long)v);
+    } else {
+        if (al8 && valid == 2) { *reinterpret_cast<unsigned long long*>(p) = v; return; }
+        if (valid > 0) p[0] = __uint_as_float((unsigned int)v);
+        if (valid > 1) p[1] = __uint_as_float((unsigned int)(v >> 32));
+    }
+}
+template <typename T>
+__device__ __forceinline__ unsigned long long ll_add(unsigned long long x, unsigned long long y) {
+    if constexpr (sizeof(T) == 8) {
+        return (unsigned long long)__double_as_longlong(__longlong_as_double((long long)x) + __longlong_as_double((long long)y));
+    } else {
+        const float a = __uint_as_float((unsigned int)x) + __uint_as_float((unsigned int)y);
+        const float b = __uint_as_float((unsigned int)(x >> 32)) + __uint_as_float((unsigned int)(y >> 32));
+        return (unsigned long long)__float_as_uint(a) | ((unsigned long long)__float_as_uint(b) << 32);
+    }
+}
+
+// Poll U line groups (16 bytes per lane each) until the flag lane of every active group reads `seq`.  All 32 lanes take
+// part; the U loads are issued back to back, so U lines are in flight per lane, and only the lines still missing are
+// re-read.  Returns false after the time-out (the error word is set; the caller carries on with what it has).
+template <int U>
+__device__ __forceinline__ bool ll_wait_lines(const char* const (&p)[U], const bool (&active)[U], bool flag_lane, unsigned long long seq, const P2PArgs& a,
+                                              unsigned int* sync, unsigned long long (&x0)[U], unsigned long long (&x1)[U]) {
+    bool ready[U];   // warp-uniform
+#pragma unroll
+    for (int u = 0; u < U; ++u) ready[u] = false;
+    unsigned int spins = 0;
+    unsigned long long t0 = 0;
+    for (;;) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (!ready[u] && active[u]) ld_line16(p[u], x0[u], x1[u]);
+        bool all = true;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (!ready[u]) {
+                ready[u] = __all_sync(0xffffffffu, !active[u] || !flag_lane || x1[u] == seq);
+                all = all && ready[u];
+            }
+        if (all) return true;
+        if ((++spins & 1023u) == 0 && a.timeout_ns != 0) {
+            if (t0 == 0) t0 = globaltimer_ns();
+            else if (globaltimer_ns() - t0 > a.timeout_ns) {
+                sync[2] = 1;
+                if (a.err_host) st_relaxed_sys(a.err_host, 1u);
+                return false;
+            }
+        }
+    }
+}
+
+template <typename T, int U>   // U: line groups in flight per lane in the scatter and unpack phases
+__global__ void __launch_bounds__(kP2PThreads) allreduce_ll_kernel(P2PTable<T> t, P2PArgs a) {
+    constexpr int EPW = 8 / (int)sizeof(T);
+    char* local = a.peer[a.rank];
+    unsigned int* sync = reinterpret_cast<unsigned int*>(local + 256);
+    const unsigned int epoch = sync[1];                        // bumped by the last CTA to leave: every CTA has read it by then
+    const unsigned long long seq = (unsigned long long)epoch + 1ull;   // never 0: the regions start out zeroed
+    const long long total_words = t.start[t.count] / EPW;      // segments start on 16-byte boundaries: a whole number of words
+    const long long TL = (total_words + kLLPayloadWords - 1) / kLLPayloadWords;
+    const long long lpr = (TL + a.nranks - 1) / a.nranks;      // lines per slice
+    const long long span = lpr * a.nranks;
+    const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+    const bool flag_lane = sub == 7;
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    unsigned long long* stamps = reinterpret_cast<unsigned long long*>(local + 512 + 64 * (epoch & 1u));
+    const bool stamp = blockIdx.x == 0 && threadIdx.x == 0;
+    if (stamp) stamps[0] = globaltimer_ns();
+    // 0. scatter: line g of the packed buffers -> rank g / lpr, region A, slot [rank].  Every rank starts its walk at a
+    //    different slice (rank r with slice r + 1): at any moment the N ranks write into N different destinations.
+    const long long total_e = t.start[t.count];
+    LLCursor<T> cur;
+    for (long long g0 = warp_id * 4 * U; g0 < span; g0 += nwarps * 4 * U) {   // 4 U consecutive lines per warp and round
+        unsigned long long w0[U], w1[U];
+        char* dst[U];
+        const T* s0[U];
+        const T* s1[U];
+        int v0[U], v1[U];
+        bool a0[U], a1[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {   // addresses first ...
+            const long long gi = g0 + u * 4 + grp;
+            long long g = gi + (long long)((a.rank + 1) % a.nranks) * lpr;
+            if (g >= span) g -= span;
+            dst[u] = nullptr;
+            s0[u] = s1[u] = nullptr;
+            v0[u] = v1[u] = 0;
+            a0[u] = a1[u] = false;
+            if (gi < span && g < TL) {
+                const int q = (int)(g / lpr);
+                const long long w = g * kLLPayloadWords + sub * 2;
+                s0[u] = cur.locate(t, w, total_e, v0[u]);
+                a0[u] = cur.al8;
+                if (!flag_lane) {
+                    s1[u] = cur.locate(t, w + 1, total_e, v1[u]);
+                    a1[u] = cur.al8;
+                }
+                dst[u] = a.peer[q] + kP2PHeaderBytes + (((long long)a.rank * lpr + (g - q * lpr)) << 7) + sub * 16;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {   // ... then every load of the round (2 U words in flight per lane) ...
+            w0[u] = ll_load<T>(s0[u], v0[u], a0[u]);
+            w1[u] = flag_lane ? seq : ll_load<T>(s1[u], v1[u], a1[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)     // ... then the stores
+            if (dst[u]) st_line16(dst[u], w0[u], w1[u]);
+    }
+    if (stamp) stamps[1] = stamps[2] = globaltimer_ns();
+    // 2. our slice: wait for the line of every rank (all N in flight), add the N lines in rank order, store the result line
+    //    into region B of every rank (destinations in rotated order)
+    {
+        const long long first = lpr * a.rank;
+        const long long mine = max(0ll, min(lpr, TL - first));
+        const char* slots = local + kP2PHeaderBytes;
+        bool alive = true;
+        for (long long l0 = warp_id * 4; l0 < mine && alive; l0 += nwarps * 4) {
+            const long long loc = l0 + grp;
+            const bool active = loc < mine;
+            const char* src[kP2PMaxRanks];
+            bool act[kP2PMaxRanks];
+            unsigned long long x0[kP2PMaxRanks], x1[kP2PMaxRanks];
+#pragma unroll
+            for (int r = 0; r < kP2PMaxRanks; ++r) {
+                act[r] = active && r < a.nranks;
+                src[r] = slots + (((long long)r * lpr + loc) << 7) + sub * 16;
+                x0[r] = x1[r] = 0;
+            }
+            alive = ll_wait_lines<kP2PMaxRanks>(src, act, flag_lane, seq, a, sync, x0, x1);
+            if (active) {
+                unsigned long long acc0 = x0[0], acc1 = x1[0];
+#pragma unroll
+                for (int r = 1; r < kP2PMaxRanks; ++r)
+                    if (r < a.nranks) {
+                        acc0 = ll_add<T>(acc0, x0[r]);
+                        if (!flag_lane) acc1 = ll_add<T>(acc1, x1[r]);
+                    }
+                if (flag_lane) acc1 = seq;
+#pragma unroll
+                for (int j = 0; j < kP2PMaxRanks; ++j)
+                    if (j < a.nranks) {
+                        int q = a.rank + 1 + j;
+                        q = q >= a.nranks ? q - a.nranks : q;
+                        st_line16(a.peer[q] + kP2PHeaderBytes + a.region_bytes + ((first + loc) << 7) + sub * 16, acc0, acc1);
+                    }
+            }
+        }
+    }
+    if (stamp) stamps[3] = stamps[4] = globaltimer_ns();
+    // 4. unpack: every result line, as it arrives, into the buffers
+    {
+        const char* res = local + kP2PHeaderBytes + a.region_bytes;
+        bool alive = true;
+        for (long long g0 = warp_id * 4 * U; g0 < TL && alive; g0 += nwarps * 4 * U) {
+            const char* src[U];
+            bool act[U];
+            unsigned long long x0[U], x1[U];
+            T* d0[U];
+            T* d1[U];
+            int v0[U], v1[U];
+            bool a0[U], a1[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {   // destinations first: the lines may still be on their way
+                const long long g = g0 + u * 4 + grp;
+                act[u] = g < TL;
+                src[u] = res + (g << 7) + sub * 16;
+                x0[u] = x1[u] = 0;
+                d0[u] = d1[u] = nullptr;
+                v0[u] = v1[u] = 0;
+                a0[u] = a1[u] = false;
+                if (act[u]) {
+                    const long long w = g * kLLPayloadWords + sub * 2;
+                    d0[u] = cur.locate(t, w, total_e, v0[u]);
+                    a0[u] = cur.al8;
+                    if (!flag_lane) {
+                        d1[u] = cur.locate(t, w + 1, total_e, v1[u]);
+                        a1[u] = cur.al8;
+                    }
+                }
+            }
+            alive = ll_wait_lines<U>(src, act, flag_lane, seq, a, sync, x0, x1);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                ll_store<T>(d0[u], v0[u], a0[u], x0[u]);
+                ll_store<T>(d1[u], v1[u], a1[u], x1[u]);
+            }
+        }
+    }
+    if (stamp) stamps[5] = globaltimer_ns();
+    // the last CTA to leave bumps the epoch (every CTA read it on entry) and resets the departure counter
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&sync[0], 1u) == gridDim.x - 1u) {
+            sync[0] = 0;
+            sync[1] = epoch + 1u;
+        }
+    }
+}
+
 static int p2p_setup(Ctx* ctx);
 
 // Has a barrier of an earlier peer-memory all-reduce timed out on this rank?  (mapped pinned word: no copy, no synchronisation)
@@ -335,28 +607,27 @@ static int p2p_check_error(Ctx* ctx) {
 
 // The all-reduce kernel meets at grid-wide barriers: every CTA must be resident.  A cooperative launch makes the driver
 // guarantee that (or fail the launch) instead of relying on an idle GPU; the grid is sized from the occupancy query.
+// Does a payload of `bytes` (16-byte padded segments) fit the symmetric regions?  (flag-in-data lines carry 120 of 128 bytes;
+// the slices are rounded up to whole lines per rank)
+static bool p2p_fits(const Ctx* ctx, size_t bytes) {
+    return bytes + bytes / 15 + 128 * (size_t)(kP2PMaxRanks + 2) <= ctx->p2p_region_bytes;
+}
+
+// DSC_P2P_PROTO=barrier selects the two-barrier kernel (every rank must use the same protocol); default: flag in data
+static bool p2p_use_ll() {
+    static const bool ll = [] { const char* e = getenv("DSC_P2P_PROTO"); return !(e && (*e == 'b' || *e == 'B')); }();
+    return ll;
+}
+
 template <typename T>
-static int p2p_launch(Ctx* ctx, P2PTable<T>& pt, P2PArgs& a, bool beside_compute) {
-    if (beside_compute) {
-        // On the second compute lane the all-reduce runs BESIDE the backward products of the compute stream: a small grid that
-        // fits on the SMs the concurrent GEMM leaves free (its persistent grid is tiles x K-ranges, 112-128 of 148 SMs for the
-        // step's products; a GEMM CTA's registers and shared memory leave no room for a second resident CTA).  Measured on two
-        // GPUs (tools/lane_ar_sweep.sh): 32 x 512 and 96 x 256 threads give the shortest step, 64 x 128 the longest.
-        static const int lane_ctas = [] { const char* e = getenv("DSC_P2P_LANE_CTAS"); int v = e ? atoi(e) : 32; return v < 1 ? 1 : (v > kP2PMaxCtas ? kP2PMaxCtas : v); }();
-        static const int lane_threads = [] { const char* e = getenv("DSC_P2P_LANE_THREADS"); int v = e ? atoi(e) : 512; return v < 32 ? 32 : (v > kP2PThreads ? kP2PThreads : v / 32 * 32); }();
-        void* args[] = {&pt, &a};
-        cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(allreduce_p2p_kernel<T>), dim3(lane_ctas), dim3(lane_threads), args, 0, ctx->stream);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            allreduce_p2p_kernel<T><<<lane_ctas, lane_threads, 0, ctx->stream>>>(pt, a);
-        }
-        DSC_LAUNCH_CHECK(ctx);
-        return DSC_OK;
-    }
+static int p2p_launch(Ctx* ctx, P2PTable<T>& pt, P2PArgs& a) {
+    // one line group in flight per lane: measured on 2 GPUs (7.45 MB), 2 and 4 in flight were slower (23.2 / 25.5 us against
+    // 20.9 us): the phases are bound by the NVLink writes outstanding per SM, not by the loads of a lane
+    void* const kernel = p2p_use_ll() ? reinterpret_cast<void*>(allreduce_ll_kernel<T, 1>) : reinterpret_cast<void*>(allreduce_p2p_kernel<T>);
     static int max_ctas = -1;
     if (max_ctas < 0) {
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, allreduce_p2p_kernel<T>, kP2PThreads, 0) != cudaSuccess || per_sm < 1) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p2p_use_ll() ? allreduce_ll_kernel<T, 1> : allreduce_p2p_kernel<T>, kP2PThreads, 0) != cudaSuccess || per_sm < 1) {
             cudaGetLastError();
             per_sm = 1;
         }
@@ -367,7 +638,7 @@ static int p2p_launch(Ctx* ctx, P2PTable<T>& pt, P2PArgs& a, bool beside_compute
     static int coop = -1;   // -1 unknown, 1 works, 0 the driver refused (e.g. under this capture mode): plain launch
     if (coop != 0) {
         void* args[] = {&pt, &a};
-        cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(allreduce_p2p_kernel<T>), dim3(ctas), dim3(kP2PThreads), args, 0, ctx->stream);
+        cudaError_t e = cudaLaunchCooperativeKernel(kernel, dim3(ctas), dim3(kP2PThreads), args, 0, ctx->stream);
         if (e == cudaSuccess) {
             coop = 1;
             DSC_LAUNCH_CHECK(ctx);
@@ -377,7 +648,11 @@ static int p2p_launch(Ctx* ctx, P2PTable<T>& pt, P2PArgs& a, bool beside_compute
         if (coop == 1) return fail(DSC_E_CUDA, "cooperative launch of the all-reduce kernel failed: %s", cudaGetErrorString(e));
         coop = 0;
     }
-    allreduce_p2p_kernel<T><<<ctas, kP2PThreads, 0, ctx->stream>>>(pt, a);
+    {
+        void* args[] = {&pt, &a};
+        cudaError_t e = cudaLaunchKernel(kernel, dim3(ctas), dim3(kP2PThreads), args, 0, ctx->stream);
+        if (e != cudaSuccess) return fail(DSC_E_CUDA, "launch of the all-reduce kernel failed: %s", cudaGetErrorString(e));
+    }
     DSC_LAUNCH_CHECK(ctx);
     return DSC_OK;
 }
@@ -391,34 +666,14 @@ static int allreduce_impl(dsc_ctx_t c, int32_t count, const dsc_buf_t* bufs) {
     if (!ctx->nccl_comm) return fail(DSC_E_NCCL, "allreduce: dsc_comm_init has not been called");
     DSC_TRY(p2p_check_error(ctx));
     DSC_TRY(co_schedule_pending_gemms(ctx));   // the weight adjoints about to be summed are usually still-deferred products: run them side by side
-    // Adjoints that were all produced on the second compute lane (weight-adjoint products and bias column sums of the layers
-    // whose reverse sweep is already behind the compute stream) are summed over the ranks ON that lane: the collective then
-    // overlaps whatever the compute stream still has to do (the first layer's backward products).  Every rank issues the same
-    // sequence of collectives on the same buffers whichever stream each of them picks, and a rank's collectives stay ordered
-    // among themselves (the next one on the compute stream joins the lane first).
-    bool on_lane = false;
-    if (ctx->lanes_enabled && ctx->p2p_ok && !ctx->on_lane && !ctx->comm_pending && lane_busy(ctx) && count > 0) {
-        on_lane = true;
-        long long total = 0;
-        int live = 0;
-        for (int i = 0; i < count && on_lane; ++i) {
-            Buf* b = as_buf(bufs[i]);
-            if (!b || b->ctx != ctx || b->dtype != dtype_of<T>::value) { on_lane = false; break; }
-            if (b->len == 0) continue;
-            Block* blk = b->block ? b->block : ((b->lazy && b->lazy->result) ? b->lazy->result : nullptr);
-            if (!blk || blk->lane_w <= ctx->lane_joined || blk->w_seq != 0 || !blk->readers.empty() || blk->views > 0 || b->is_view) on_lane = false;
-            total += b->len + 4;
-            live++;
-        }
-        if (live == 0 || (size_t)total * sizeof(T) + 16 * kP2PMaxRanks > ctx->p2p_region_bytes) on_lane = false;
-    }
-    if (lane_debug()) fprintf(stderr, "[dsc lane] all-reduce of %d buffers: %s\n", count, on_lane ? "on the lane" : "on the compute stream");
-    if (on_lane) DSC_TRY(lane_enter(ctx, nullptr, 0, false));
-    else DSC_TRY(lane_join(ctx));   // collectives of one rank never overlap each other
+    // The collective runs on the compute stream, on every SM: measured (tools/step_timeline.py, 2 GPUs), an all-reduce confined
+    // to the few SMs a concurrent GEMM leaves free pushes ~5 GB/s per SM over NVLink (outstanding remote writes per SM), i.e.
+    // 40-46 us for the 4.2 MB of the later layers on 32 SMs against 17 us on all of them — running it beside the first layer's
+    // backward products (and the first layer's own all-reduce behind it) lost to ONE all-reduce of everything after the sweep.
+    DSC_TRY(lane_join(ctx));
     PackTable<T> t;
     t.count = 0;
     t.start[0] = 0;
-    Block* touched[kMaxPack];
     int st = DSC_OK;
     for (int i = 0; i < count && st == DSC_OK; ++i) {
         Buf* b;
@@ -427,18 +682,14 @@ static int allreduce_impl(dsc_ctx_t c, int32_t count, const dsc_buf_t* bufs) {
         st = buf_writable(ctx, b);  // in-place collective
         if (st != DSC_OK) break;
         if (t.count == kMaxPack) { st = fail(DSC_E_INVALID, "allreduce: more than %d buffers in one call", kMaxPack); break; }
-        touched[t.count] = b->block;
         t.ptr[t.count] = b->ptr<T>();
         t.start[t.count + 1] = t.start[t.count] + b->len;
         t.count++;
     }
-    if (st != DSC_OK || t.count == 0) {
-        if (on_lane) lane_leave(ctx, nullptr, 0, touched, t.count);
-        return st;
-    }
+    if (st != DSC_OK || t.count == 0) return st;
     const int dt = sizeof(T) == 4 ? NCCL_FLOAT32 : NCCL_FLOAT64;
     const long long total = t.start[t.count];
-    if (ctx->p2p_ok && (size_t)(total + 4 * t.count) * sizeof(T) + 16 * kP2PMaxRanks <= ctx->p2p_region_bytes) {
+    if (ctx->p2p_ok && p2p_fits(ctx, (size_t)(total + 4 * t.count) * sizeof(T))) {
         // one kernel over peer memory on the compute stream (ordered after the producers by stream order)
         if (ctx->comm_pending) {   // a collective issued through NCCL may still be writing these buffers
             DSC_CUDA_CHECK(cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
@@ -460,12 +711,10 @@ static int allreduce_impl(dsc_ctx_t c, int32_t count, const dsc_buf_t* bufs) {
         a.region_bytes = ctx->p2p_region_bytes;
         a.err_host = reinterpret_cast<unsigned int*>(ctx->p2p_err_dev);
         a.timeout_ns = ctx->p2p_timeout_ns;
-        st = p2p_launch<T>(ctx, pt, a, on_lane);
-        if (on_lane) lane_leave(ctx, nullptr, 0, touched, t.count);
+        st = p2p_launch<T>(ctx, pt, a);
         if (st == DSC_OK) ctx->stats.allreduce_p2p++;
         return st;
     }
-    if (on_lane) return fail(DSC_E_INVALID, "allreduce: lane path without peer memory");   // not reachable: on_lane requires p2p_ok and the payload to fit
     ctx->stats.allreduce_nccl++;
     for (int i = 0; i < count; ++i) {   // these blocks are now in use on the communication stream: not recycled / overwritten before it is joined
         Buf* b = as_buf(bufs[i]);

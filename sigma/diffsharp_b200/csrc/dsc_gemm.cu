@@ -389,7 +389,12 @@ static int try_sink_product(Ctx* ctx, LazyNode* nd) {
     }
     if (ctx->flags & DSC_FLAG_GEMM_FP32_SIMT) return 1;
     auto small = [&](const LazyNode* x) { return x->m >= 128 && x->n >= 32 && x->k >= 32 && ((x->m + 127) / 128) * ((x->n + 127) / 128) <= ctx->sm_count / 2; };
-    if (!small(nd) || !small(partner)) return 1;   // one of them fills the GPU by itself: nothing to gain side by side
+    // One rank: side by side only pays when neither product fills the GPU by itself (the weight adjoints of a large batch pair
+    // up with each other at the end of the sweep instead, co_schedule_pending_gemms).  Several ranks: the weight adjoint always
+    // goes ahead on the lane — what is gained is not the packing but the all-reduce of the finished layers' adjoints, which
+    // then overlaps the rest of the sweep.
+    if (nd->m < 128 || nd->n < 32 || nd->k < 32) return 1;
+    if (ctx->nranks == 1 && (!small(nd) || !small(partner))) return 1;
     DSC_TRY(run_on_lane(ctx, nd, ctx->sm_count / 2));
     ctx->main_gemm_half_once = true;   // the partner takes the other half when the compute stream reaches it
     ctx->stats_co_scheduled++;

@@ -4,10 +4,9 @@ One process per GPU.  The reference has no distributed code; this 
 
   * reverse-mode MLP loss gradient: rank r owns the contiguous batch-row block
     [r*B/g, (r+1)*B/g); weights are replicated; every rank runs the identical AD program on its
-    block; the weight/bias adjoints (``W.A`` / ``b.A``) are summed over the ranks by ``dsc_?allreduce_sum``
-    (one kernel over peer memory; NCCL when peer access is unavailable): one call for the layers whose
-    adjoints are finished early in the reverse sweep — it overlaps the rest of the sweep — and one for the
-    first layer.
+    block; the weight/bias adjoints (``W.A`` / ``b.A``) are summed over the ranks with ONE exchange step,
+    ``dsc_?allreduce_sum`` (one kernel over peer memory, flag-in-data lines over NVLink; NCCL when peer
+    access is unavailable).
   * forward-mode Jacobian: rank r owns the identity-tangent rows [r*n/g, (r+1)*n/g); no
     communication until the final all-gather (``dsc_?allgather``).
 
@@ -150,11 +149,8 @@ def sharded_mlp_grad(comm, X_shard, Y_shard, Ws, bs):
     of every weight and bias adjoint.  Returns (local loss D, [dW], [db]) with GLOBAL adjoints."""
     from . import workloads as wl
     L, dW, db = wl.mlp_grad(X_shard, Y_shard, Ws, bs)
-    # Two collectives, in the order the reverse sweep finishes the layers: the adjoints of every layer but the first are
-    # complete while the first layer's backward products still run, so their all-reduce (issued by the library on its second
-    # compute lane, see csrc/dsc_lane.cu) overlaps that work; only the first layer's adjoints are summed after the sweep.
-    # Every rank issues the same two calls on the same buffers.
-    if len(dW) > 1:
-        comm.allreduce_sum([a.Buffer.DataBuffer for a in dW[1:]] + [a.Buffer for a in db[1:]])
-    comm.allreduce_sum([dW[0].Buffer.DataBuffer, db[0].Buffer])
+    # ONE collective for all adjoints after the sweep.  Measured alternative (profiles/README.md): summing the later layers'
+    # adjoints on a second stream while the first layer's backward products run — an all-reduce confined to the SMs a GEMM
+    # leaves free is NVLink-starved and ended later than this one.
+    comm.allreduce_sum([a.Buffer.DataBuffer for a in dW] + [a.Buffer for a in db])
     return L, dW, db

@@ -78,7 +78,7 @@ def main():
         import ctypes as C
         from sigma.diffsharp_b200._lib import check, lib
         names = ["pack", "barrier", "reduce+broadcast", "barrier", "unpack"]
-        for back, label in ((1, "first all-reduce (later layers)"), (0, "second all-reduce (first layer)")):
+        for back, label in ((1, "the all-reduce before the last"), (0, "the last all-reduce")):
             st = (C.c_uint64 * 6)()
             check(lib.dsc_comm_debug_stamps_at(ctx.handle, back, st))
             if rank == 0:
