@@ -1487,7 +1487,9 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, MatRef Am
         // tanhf / coshf per element make those warps — not the tensor pipe — the bottleneck (8192 x 1024 x 1024 + bias + tanh:
         // 115-125 us fused against 75 + 14.5 us as two kernels, the second one HBM-bound with 64 warps per SM).  Default
         // (mode 1): only the cheap epilogues run in the kernel — bias rows without activation, ReL and its adjoint chain;
-        // mode 2: all of them (parity tests); mode 0: none.
+        // mode 2: all of them (parity tests); mode 0: none.  Re-measured in round 2 on the one-wave products of a batch
+        // shard (1024 x 1024 x 1024, at most one tile per CTA): bias + tanh in the kernel 26.4 us against 19.8 + 4.2 us,
+        // the tanh adjoint chain 38.7 us against 25.5 + 4.4 us — the transcendental epilogues stay separate kernels.
         const int mode = ctx->gemm_epilogue;
         const bool cheap = (ep->mode == GEMM_EP_BIAS_ACT && (ep->op < 0 || ep->op == DSC_OP_REL)) || (ep->mode == GEMM_EP_CHAIN && ep->op == DSC_FUSED_RELU_BWD);
         const bool able = ep->mode == GEMM_EP_CHAIN || ep->op < 0 || ep->op == DSC_OP_TANH || ep->op == DSC_OP_SIGMOID || ep->op == DSC_OP_REL;
