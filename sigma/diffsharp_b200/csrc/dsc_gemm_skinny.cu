@@ -425,6 +425,9 @@ __global__ void __launch_bounds__(256, 1) skinny_cols_vec_kernel(const T* __rest
 }
 
 // ---- tiny K (k <= NMAX): C(m x n) = A(m x k) op(B)(k x n), output-write bound -----------------
+// (Measured in round 2 and not adopted: applying the activation's adjoint chain to the finished element in this kernel instead
+// of in the stream kernel that follows — 18.6 us against 6.5 + 4.3 us at 1024 rows, 49.4 us against 17.2 + 19.3 us at 8192:
+// a thread walks its slab row by row, so the coshf / division latency of the chain is exposed instead of hidden by 64 warps.)
 // (the input adjoint of the output layer: dZ (B x 10) * W3^T (10 x 1024)).  A thread keeps the KP
 // (= k rounded up to 4) B-values of its 4 (2 for double) output columns in registers and walks the
 // rows of its CTA's slab; the slab's A rows are staged in shared memory and read back as 16-byte
