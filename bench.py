@@ -461,6 +461,7 @@ def run_ours(args):
     ctx.sync(); D.barrier()
     eager_ms = D.max_over_ranks(ctx.elapsed_ms(e0, e1)) / args.steps
     launches_per_step = (ctx.stats()["kernel_launches"] - s0["kernel_launches"]) // args.steps
+    lane_ops_per_step = (ctx.stats()["lane_ops"] - s0["lane_ops"]) // args.steps
 
     # ---- capture the step's call sequence once, replay it as a CUDA graph ----
     backend.capture_scalars = []
@@ -702,7 +703,7 @@ def run_ours(args):
                       "h2d_bytes_per_step": h2d_job, "d2h_bytes_per_step": d2h,
                       "mode": "the same, but the step is driven op by op through the plugin interface (no graph, no copy/compute overlap)"},
         "gpu_launches": int(launches_per_step * args.steps),
-        "launches_per_step": int(launches_per_step),
+        "launches_per_step": int(launches_per_step), "second_lane_launches_per_step": int(lane_ops_per_step),
         "step_gflop": STEP_GFLOP, "step_tflops": round(STEP_GFLOP / world / graph_ms, 2),
         "loss": loss_graph, "loss_e2e": loss_e2e, "loss_e2e_eager": loss_e2e_eager, "adjoints_identical_on_all_ranks": adjoints_identical,
         "adjoints_match_1gpu": adjoints_match_1gpu,

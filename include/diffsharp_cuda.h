@@ -126,6 +126,7 @@ typedef struct dsc_stats {
     uint64_t gemm_simt;           /* GEMMs served by the CUDA-core kernels                          */
     uint64_t allreduce_p2p;       /* all-reduces served by the peer-memory (NVLink P2P) kernel      */
     uint64_t allreduce_nccl;      /* all-reduces served by NCCL                                     */
+    uint64_t lane_ops;            /* operations issued on the second compute lane (sinks of reverse sweeps) */
 } dsc_stats;
 
 /* ---------------------------------------------------------------- lifecycle ---------------- */

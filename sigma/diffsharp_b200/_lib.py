@@ -60,7 +60,7 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "kernel_launches", "memcpy_h2d_bytes", "memcpy_d2h_bytes", "pool_bytes_reserved",
         "pool_bytes_in_use", "pool_hits", "pool_misses", "gemm_tcgen05", "gemm_dmma", "gemm_simt",
-        "allreduce_p2p", "allreduce_nccl")]
+        "allreduce_p2p", "allreduce_nccl", "lane_ops")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -519,6 +519,7 @@ int dsc_get_stats(dsc_ctx_t c, dsc_stats* out) {
     ctx->stats.pool_bytes_in_use = ctx->pool.in_use;
     ctx->stats.pool_hits = ctx->pool.hits;
     ctx->stats.pool_misses = ctx->pool.misses;
+    ctx->stats.lane_ops = ctx->lane_seq;
     *out = ctx->stats;
     return DSC_OK;
 }

@@ -580,3 +580,50 @@ def test_permute_and_reshape_bit_exact(cuda_provider, dtype, shape, perm):
     assert np.array_equal(flat.SubData, a.reshape(-1)) and tuple(back.Shape) == (rows, n // rows)
     b.Add_V_V_InPlace(b.CreateDataBuffer(np.ones(n, dtype)), 0, flat, 0, n)
     assert np.array_equal(v.DataBuffer.SubData, a.reshape(-1))                              # the source is untouched by writes to the copy
+
+
+def test_second_lane_hazards(cuda_provider, cuda_provider_nofuse):
+    """The sinks of a reverse sweep run on the library's second stream (csrc/dsc_lane.cu).  Whatever the host does next —
+    read the weight adjoint at once, overwrite an operand in place, accumulate column sums into a non-empty vector, capture
+    nothing — the results are those of the one-stream, unfused sequence, bit for bit."""
+    rng = np.random.default_rng(11)
+    m, k, n = 256, 384, 320          # small enough that two products share the GPU, large enough for the tensor-core kernel
+    A, W, dC, X = (rng.standard_normal(s).astype(np.float32) for s in ((m, k), (k, n), (m, n), (m, n)))
+
+    def run(prov):
+        b = backend(prov, np.float32)
+        mat = lambda a: ShapedDataBufferView(b.CreateDataBuffer(a.reshape(-1).copy()), *a.shape)  # noqa: E731
+        dA, dW_, ddC, dX = mat(A), mat(W), mat(dC), mat(X)
+        out = {}
+        # the adjoint pair of C = A W, in the order the AD layer issues it (AD.Float32.fs:4127-4143): d.A W^T first (stays
+        # pending: it may still get an epilogue), then A^T d.A (a sink: goes ahead on the second lane)
+        gA = b.Mul_M_M(ddC, b.Transpose_M(dW_))
+        gW = b.Mul_M_M(b.Transpose_M(dA), ddC)
+        b.Add_M_M_InPlace(ddC, dX)                           # an operand of both products is overwritten right away
+        out["gW"] = gW.DataBuffer.SubData.copy()             # ... and the sink is read at once
+        out["gA"] = gA.DataBuffer.SubData.copy()
+        out["dC"] = ddC.DataBuffer.SubData.copy()
+        # column sums: into a fresh zero vector (stored) and into a non-empty accumulator (added), twice
+        gA2 = b.Mul_M_M(ddC, b.Transpose_M(dW_))
+        gW2 = b.Mul_M_M(b.Transpose_M(dA), ddC)
+        acc = b.CreateDataBuffer(np.zeros(n, np.float32))
+        b.Add_M_Colwise_V_InPlace(ddC, acc)
+        b.Add_M_Colwise_V_InPlace(dX, acc)
+        out["cs"] = acc.SubData.copy()
+        # the weight adjoint accumulated twice into the same parameter adjoint (a shared weight)
+        Wadj = b.CreateDataBuffer(np.zeros(k * n, np.float32))
+        Wv = ShapedDataBufferView(Wadj, k, n)
+        b.Add_M_M_InPlace(Wv, gW2)
+        b.Add_M_M_InPlace(Wv, gW)
+        out["Wadj"] = Wadj.SubData.copy()
+        out["gA2"] = gA2.DataBuffer.SubData.copy()
+        return out
+
+    lane0 = cuda_provider.ctx.stats()["lane_ops"]
+    got, want = run(cuda_provider), run(cuda_provider_nofuse)
+    assert cuda_provider.ctx.stats()["lane_ops"] >= lane0 + 2      # both weight adjoints did go to the second lane
+    assert cuda_provider_nofuse.ctx.stats()["lane_ops"] == 0
+    for key in want:
+        assert np.array_equal(got[key], want[key]), key
+    ref = (A.T.astype(np.float64) @ dC.astype(np.float64))
+    assert np.abs(got["gW"].reshape(k, n) - ref).max() <= 1e-5 * np.abs(ref).max()
