@@ -39,6 +39,12 @@
  * kernel with the chain's own sequence of roundings; any other use of the handle (another op, a download, a view) computes
  * the value with exactly the kernel the call would have launched.  Results are bit-identical to the undeferred sequence
  * (DSC_FLAG_NO_FUSE); deferred work that nobody consumed runs at the next dsc_sync / dsc_event_record / dsc_graph_end.
+ *
+ * Second compute lane.  The sinks of a reverse sweep — the weight-adjoint product Transpose(a.P) * d.A (AD.Float32.fs:4131-4143)
+ * and the bias column sums Add_M_Colwise_V_InPlace (:4255) — are issued on a second stream of the context, forked from the
+ * compute stream only where a data dependency requires it and joined when a consumer touches their result or at a
+ * synchronisation point; captured in a CUDA graph they are a parallel branch.  Invisible to the caller (same results, bit for
+ * bit; DSC_LANES=0 keeps everything on the compute stream); dsc_stats.lane_ops counts the operations issued there.
  */
 #ifndef DIFFSHARP_CUDA_H
 #define DIFFSHARP_CUDA_H
