@@ -98,6 +98,21 @@ def _worker(rank, world, port, out):
                 comm.allreduce_sum(bufs); comm.join()
             for b, h in zip(bufs, host):
                 assert np.array_equal(b.SubData, h * np.float32(world ** 3)), "eager"
+    # float64 buffers, a window that starts at an odd element (not 8- or 16-byte aligned: the element-wise paths of the
+    # kernel) and a one-element buffer, in ONE call per dtype
+    h64 = [rng.standard_normal(n) for n in (5, 1025, 1)]
+    b64 = [CudaDataBuffer.from_host(prov.ctx, h) for h in h64]
+    comm.allreduce_sum(b64); comm.join()
+    for b, h in zip(b64, h64):
+        assert np.array_equal(b.SubData, h * world), "float64"
+    base = rng.standard_normal(4099).astype(np.float32)
+    whole = CudaDataBuffer.from_host(prov.ctx, base)
+    odd = whole.GetValues(3, 4001)                      # shares storage with `whole`, starts 12 bytes into it
+    one = CudaDataBuffer.from_host(prov.ctx, np.array([1.5], np.float32))
+    comm.allreduce_sum([odd, one]); comm.join()
+    want = base.copy()
+    want[3:4004] *= np.float32(world)
+    assert np.array_equal(whole.SubData, want) and one.SubData[0] == np.float32(1.5 * world), "odd window"
     st1 = prov.ctx.stats()
     used_p2p = st1["allreduce_p2p"] - st["allreduce_p2p"]
     # config-4 shape in miniature: tangent rows sharded, all-gather at the end
