@@ -42,6 +42,8 @@ def main():
                         "duration_us": float(r[col["gpu__time_duration.sum"]].replace(",", "")),
                         "dram_read_bytes": rd, "dram_write_bytes": wr, "traffic_bytes": rd + wr,
                         "tensor_pipe_active_pct": float(r[col["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]]),
+                        "dram_throughput_pct_of_peak": float(r[col["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]]),
+                        "achieved_dram_GBps": round((rd + wr) / float(r[col["gpu__time_duration.sum"]].replace(",", "")) / 1e3, 1),
                         "l2_hit_pct": float(r[col["lts__t_sector_hit_rate.pct"]])})
     json.dump({"report": rep, "command": "ncu --set full --clock-control none --import-source on", "launches": summary}, open(out + ".json", "w"), indent=1)
     for s in summary:
