@@ -354,7 +354,21 @@ static int reduce_dev(dsc_ctx_t c, dsc_buf_t xh, dsc_buf_t yh, dsc_buf_t* outh, 
         int s = x->len > 0 ? sum_of_product<T>(ctx, x, &pa, &pb) : 1;
         if (s < 0) return s;
         if (s == DSC_OK) {
+            const bool fresh = *outh == 0;
             DSC_TRY(out_buf(ctx, dtype_of<T>::value, 1, outh, &o));
+            // had(E, E).Sum() left on the device is a sink (the loss of a captured step: nobody reads it before the step
+            // ends): it is taken on the second compute lane, beside the reverse sweep that starts from E
+            LazyNode* h = lazy_of(x, LZ_HAD);
+            Block* rd[2] = {nullptr, nullptr};
+            if (h) {
+                for (int i = 0; i < 2; ++i) rd[i] = h->src[i].node ? h->src[i].node->result : h->src[i].block;
+            }
+            if (fresh && ctx->lanes_enabled && !ctx->on_lane && rd[0] && rd[1] && x->len >= 4096 && lane_enter(ctx, rd, 2, false) == DSC_OK) {
+                const int st = launch_reduce<R_PRODSUM, T>(ctx, pa, pb, x->len, o->ptr<T>());
+                Block* wr[1] = {o->block};
+                lane_leave(ctx, rd, 2, wr, 1);
+                return st;
+            }
             return launch_reduce<R_PRODSUM, T>(ctx, pa, pb, x->len, o->ptr<T>());
         }
     }
