@@ -377,6 +377,10 @@ static int try_sink_product(Ctx* ctx, LazyNode* nd) {
     if (!partner) {
         // nothing to run beside: the product still is a sink — no consumer will fold into its epilogue — so it starts now
         // instead of at the end of the sweep (behind the column sums the calls that follow it issue)
+        // ... and the lane is forked first: the sinks the calls right behind it issue on the same inputs (the bias column
+        // sums of the layer) then run beside this product, not behind it
+        Block* rd[2] = {nd->src[0].block, nd->src[1].block};
+        DSC_TRY(lane_prefork(ctx, rd, 2));
         nd->refs++;
         const int st = lazy_materialize(nd);
         lazy_unref(nd);

@@ -201,6 +201,7 @@ struct Ctx {
     uint64_t lane_seq = 0;               // lane operations issued
     uint64_t lane_joined = 0;            // ... of which the compute stream is ordered after this many
     std::vector<Block*> lane_held;       // blocks lane operations touch: referenced (never recycled) until the next join
+    bool lane_fork_open = false;         // a fork has put the lane behind the compute stream and no join has followed yet
     bool on_lane = false;                // the context's stream / scratch members currently name the lane's (lane_enter .. lane_leave)
     bool main_gemm_half_once = false;    // a tensor-core product has just gone to the lane with half of the SMs: the next one on the compute stream takes the other half
     bool lanes_enabled = true;           // DSC_LANES=0 switches the sink lane off
@@ -318,6 +319,9 @@ bool lane_sees(Ctx* ctx, Block* const* reads, int n);
 int lane_enter(Ctx* ctx, Block* const* reads, int n, bool force_fork);
 void lane_leave(Ctx* ctx, Block* const* reads, int nr, Block* const* writes, int nw);
 int lane_join(Ctx* ctx);                                       // the compute stream waits for everything issued on the lane
+// Fork now, before the compute stream is given a long kernel: lane operations issued afterwards whose inputs are among `reads`
+// (or were visible before) start beside that kernel instead of behind it.
+int lane_prefork(Ctx* ctx, Block* const* reads, int n);
 inline bool lane_busy(const Ctx* ctx) { return ctx->lane_seq > ctx->lane_joined; }
 bool lane_debug();                                             // DSC_LANE_DEBUG=1: every lane decision on stderr
 // compute-stream work is about to read / write blk

@@ -87,8 +87,21 @@ int lane_enter(Ctx* ctx, Block* const* reads, int n, bool force_fork) {
         DSC_CUDA_CHECK(cudaEventRecord(ctx->ev_lane_fork, ctx->stream));
         DSC_CUDA_CHECK(cudaStreamWaitEvent(ctx->lane_stream, ctx->ev_lane_fork, 0));
         ctx->lane_fork_seq = ++ctx->order_seq;   // everything pinned so far (the inputs above included) is visible to the lane
+        ctx->lane_fork_open = true;
     }
     lane_swap(ctx);
+    return DSC_OK;
+}
+
+int lane_prefork(Ctx* ctx, Block* const* reads, int n) {
+    if (ctx->on_lane) return DSC_OK;
+    DSC_TRY(lane_ensure(ctx));
+    if (lane_sees(ctx, reads, n)) return DSC_OK;   // (pins the inputs) nothing to gain: the lane is already ordered after them
+    if (lane_debug()) fprintf(stderr, "[dsc lane] fork ahead of a compute-stream kernel\n");
+    DSC_CUDA_CHECK(cudaEventRecord(ctx->ev_lane_fork, ctx->stream));
+    DSC_CUDA_CHECK(cudaStreamWaitEvent(ctx->lane_stream, ctx->ev_lane_fork, 0));
+    ctx->lane_fork_seq = ++ctx->order_seq;
+    ctx->lane_fork_open = true;
     return DSC_OK;
 }
 
@@ -112,7 +125,7 @@ void lane_leave(Ctx* ctx, Block* const* reads, int nr, Block* const* writes, int
 
 int lane_join(Ctx* ctx) {
     if (ctx->on_lane) return fail(DSC_E_INVALID, "lane_join while on the lane");
-    if (ctx->lane_seq == ctx->lane_joined) return DSC_OK;
+    if (ctx->lane_seq == ctx->lane_joined && !ctx->lane_fork_open) return DSC_OK;   // (a fork without work still has to be joined: a captured graph may not end with a dangling branch)
     int st = DSC_OK;
     if (cudaEventRecord(ctx->ev_lane_done, ctx->lane_stream) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, ctx->ev_lane_done, 0) != cudaSuccess) {
         cudaGetLastError();
@@ -120,6 +133,7 @@ int lane_join(Ctx* ctx) {
     }
     if (lane_debug()) fprintf(stderr, "[dsc lane] join (%llu operations)\n", (unsigned long long)(ctx->lane_seq - ctx->lane_joined));
     ctx->lane_joined = ctx->lane_seq;
+    ctx->lane_fork_open = false;
     ctx->main_gemm_half_once = false;
     std::vector<Block*> held;
     held.swap(ctx->lane_held);

@@ -486,12 +486,12 @@ static int colsum_impl(dsc_ctx_t c, int32_t m, int32_t n, dsc_buf_t Mh, dsc_buf_
         lazy_unref(z);
         DSC_TRY(pool_alloc(ctx, (size_t)n * sizeof(T), &v->block));
         v->off = 0;
-        // A sink of the reverse sweep (AD.Float32.fs:4255): while the second compute lane is busy with this sweep's weight
-        // adjoints and already ordered after the matrix (the weight adjoint of the same layer read it), the sums are taken
-        // there — behind that product, not behind whatever the compute stream has been given since.
+        // A sink of the reverse sweep (AD.Float32.fs:4255): when the second compute lane is already ordered after the matrix
+        // (the weight adjoint of the same layer read it, or the lane was forked in front of that product), the sums are
+        // taken there — beside whatever the compute stream has been given since, not behind it.
         Block* rd[1] = {M->block};
         if (lane_debug()) fprintf(stderr, "[dsc lane] column sums %d x %d of %p: lane busy %d, lane-written %d\n", m, n, M->block->ptr, (int)lane_busy(ctx), (int)(M->block->lane_w > ctx->lane_joined));
-        if (ctx->lanes_enabled && !ctx->on_lane && lane_busy(ctx) && M->block->lane_w <= ctx->lane_joined && lane_sees(ctx, rd, 1)) {
+        if (ctx->lanes_enabled && !ctx->on_lane && M->block->lane_w <= ctx->lane_joined && lane_sees(ctx, rd, 1)) {
             DSC_TRY(lane_enter(ctx, rd, 1, false));
             const int st = colsum_launch<T>(ctx, M->ptr<T>(), v->ptr<T>(), m, n, false);
             Block* wr[1] = {v->block};
