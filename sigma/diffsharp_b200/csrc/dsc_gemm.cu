@@ -399,16 +399,6 @@ static int try_sink_product(Ctx* ctx, LazyNode* nd) {
     // then overlaps the rest of the sweep.
     if (nd->m < 128 || nd->n < 32 || nd->k < 32) return 1;
     if (ctx->nranks == 1 && (!small(nd) || !small(partner))) return 1;
-    // The partner will read its operands' companions on the compute stream.  One that the lane wrote earlier (a prefetch during
-    // the forward pass) and that is not joined yet would make the partner wait for EVERYTHING on the lane — this product
-    // included — the moment it looks the companion up: join now, while the lane holds only work that is long finished.
-    for (int i = 0; i < partner->nsrc && i < 2; ++i) {
-        Block* b = partner->src[i].block;
-        if (b && b->lo && b->lo->lane_w > ctx->lane_joined) {
-            DSC_TRY(lane_join(ctx));
-            break;
-        }
-    }
     DSC_TRY(run_on_lane(ctx, nd, ctx->sm_count / 2));
     ctx->main_gemm_half_once = true;   // the partner takes the other half when the compute stream reaches it
     ctx->stats_co_scheduled++;

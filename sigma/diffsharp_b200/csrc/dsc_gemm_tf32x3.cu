@@ -1323,59 +1323,6 @@ static bool make_plan(const PlanIn& in, PlanOut& out) {
 
 }  // namespace tf32x3
 
-// Attach (or re-use) the operand-split companion block of M's block and mark it valid for `count` elements from M's window
-// start; the caller launches the kernel that fills it.  Null when the block is unknown or the allocation fails.
-static float* attach_companion(Ctx* ctx, const MatRef& M, size_t count) {
-    Block* blk = M.block;
-    if (!blk) return nullptr;
-    if (!blk->lo) {
-        Block* lo = nullptr;
-        if (pool_alloc(ctx, blk->bytes, &lo) != DSC_OK) return nullptr;
-        blk->lo = lo;
-    } else if (lane_gate_write(ctx, blk->lo) != DSC_OK) {
-        return nullptr;
-    }
-    blk->lo_epoch = ctx->cache_epoch;
-    blk->lo_begin = M.off;
-    blk->lo_end = M.off + count;
-    return reinterpret_cast<float*>(blk->lo->ptr) + M.off;
-}
-
-static int prefetch_mode() {   // DSC_GEMM_PREFETCH: 0 off, 1 (default) B operands, 2 A and B operands
-    static const int mode = [] { const char* e = getenv("DSC_GEMM_PREFETCH"); return e ? atoi(e) : 1; }();
-    return mode;
-}
-
-// A B operand (a weight matrix) this product converted in the kernel — no companion in HBM — is, in a reverse sweep, read again
-// by the input-adjoint product of the same tape node (dZ W^T, AD.Float32.fs:4127-4130).  Its companion is prepared on the second
-// compute lane, which idles during the forward pass, so that the adjoint product finds it ready instead of running the pre-pass
-// on the critical path.  Measured on one box, same session (tools/step_timeline.py, 1024 rows): 122.4 / 124.6 us against
-// 125.6 / 125.5 us without; doing the same for A operands (X, read again by X^T dZ) lost: 131.0 / 127.0 us — the extra
-// lane work during the forward pass costs more than the 2-CTA kernel gains for the last weight adjoint.
-static void prefetch_companion(Ctx* ctx, const MatRef& M, const float* src, int rows, int k, int kp, const tf32x3::OperandPlan& plan) {
-    using namespace tf32x3;
-    if (!ctx->lanes_enabled || ctx->on_lane || !ctx->fuse || !M.block || !plan.direct) return;
-    if (M.block->lo && M.block->lo_epoch == ctx->cache_epoch) return;
-    if ((size_t)rows * k < (size_t)128 * 128) return;
-    Block* rd[1] = {M.block};
-    if (lane_enter(ctx, rd, 1, false) != DSC_OK) return;
-    float* lo = attach_companion(ctx, M, (size_t)rows * k);
-    Block* wr[1] = {nullptr};
-    if (lo) {
-        SplitJob ja{src, nullptr, lo, rows, plan.mode, split_blocks(plan, rows, k, kp)};
-        SplitJob jb{src, nullptr, lo, rows, plan.mode, 0};
-        split_pair_kernel<<<ja.blocks, 256, 0, ctx->stream>>>(ja, jb, k, kp);
-        ctx->stats.kernel_launches++;
-        if (cudaPeekAtLastError() != cudaSuccess) {
-            cudaGetLastError();
-            M.block->lo_epoch = 0;   // not filled: no companion
-        } else {
-            wr[0] = M.block->lo;
-        }
-    }
-    lane_leave(ctx, rd, 1, wr, 1);
-}
-
 int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, MatRef Am, MatRef Bm, const float* bias, float* C, const GemmEpilogue* ep) {
     using namespace tf32x3;
     const float* A = reinterpret_cast<const float*>(Am.ptr);
@@ -1490,9 +1437,24 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, MatRef Am
     // Where each operand's lo plane lives: a ready companion; a NEW companion attached to the operand's block (direct operands:
     // the split below fills it and later products of the same matrix find it); or the context workspace (operands TMA cannot
     // address in place: hi + lo padded planes).
+    auto new_companion = [&](const MatRef& M, size_t count) -> float* {
+        Block* blk = M.block;
+        if (!blk) return nullptr;
+        if (!blk->lo) {
+            Block* lo = nullptr;
+            if (pool_alloc(ctx, blk->bytes, &lo) != DSC_OK) return nullptr;
+            blk->lo = lo;
+        } else if (lane_gate_write(ctx, blk->lo) != DSC_OK) {
+            return nullptr;
+        }
+        blk->lo_epoch = ctx->cache_epoch;
+        blk->lo_begin = M.off;
+        blk->lo_end = M.off + count;
+        return reinterpret_cast<float*>(blk->lo->ptr) + M.off;
+    };
     const bool a_split = !a_fused && !a_comp, b_split = !b_fused && !b_comp;   // this call runs the split for the operand
-    if (a_split && pa.direct) a_comp = attach_companion(ctx, Am, (size_t)m * k);
-    if (b_split && pb.direct) b_comp = attach_companion(ctx, Bm, (size_t)n * k);
+    if (a_split && pa.direct) a_comp = new_companion(Am, (size_t)m * k);
+    if (b_split && pb.direct) b_comp = new_companion(Bm, (size_t)n * k);
     const size_t a_floats = (a_fused || a_comp) ? 0 : (pa.ws_floats + 255) & ~size_t(255), b_floats = (b_fused || b_comp) ? 0 : (pb.ws_floats + 255) & ~size_t(255);
     const size_t planes_bytes = (a_floats + b_floats) * sizeof(float);
     const size_t slot_bytes = (size_t)grid * (pair ? 2 : 1) * 2 * BM * bn * sizeof(float);
@@ -1583,8 +1545,6 @@ int gemm_tf32x3_tcgen05(Ctx* ctx, int ta, int tb, int m, int n, int k, MatRef Am
     }
     if (s != DSC_OK) return s;
     ctx->stats.gemm_tcgen05++;
-    if (a_fused && prefetch_mode() >= 2) prefetch_companion(ctx, Am, A, m, k, kp, pa);
-    if (b_fused && prefetch_mode() >= 1) prefetch_companion(ctx, Bm, B, n, k, kp, pb);
     return (ep && ep->mode != GEMM_EP_NONE && !ep_in_kernel) ? 2 : DSC_OK;   // 2: product stored, the caller applies the epilogue as a second pass
 }
 

@@ -22,8 +22,11 @@
 //     hands them to compute-stream work the lane could still race with.
 //   * the lane has its own GEMM workspace, tickets and reduction scratch.
 //
-// The lane also prepares, during the forward pass (when it idles), the operand-split companion of a weight matrix that a forward
-// product converted in its kernel, for the input-adjoint product of the reverse sweep (prefetch_companion, dsc_gemm_tf32x3.cu).
+// Measured and not adopted (round 2): preparing, on the idle lane during the forward pass, the operand-split companions of the
+// operands a forward product converted in its kernel (X, W) so that the adjoint products find them ready.  The weight adjoint
+// of the first layer got 1.5 us faster (2-CTA kernel instead of in-kernel conversion) and the pre-pass in front of the input
+// adjoint disappeared, but that pre-pass already ran beside the lane's weight adjoint and the paired products got ~1 us slower:
+// 127.2 us against 126.3 us per 1024-row step, 503 against 497 us at 8192 rows.
 #include <stdlib.h>
 
 #include <algorithm>
