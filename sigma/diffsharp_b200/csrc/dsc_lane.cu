@@ -26,7 +26,10 @@
 // operands a forward product converted in its kernel (X, W) so that the adjoint products find them ready.  The weight adjoint
 // of the first layer got 1.5 us faster (2-CTA kernel instead of in-kernel conversion) and the pre-pass in front of the input
 // adjoint disappeared, but that pre-pass already ran beside the lane's weight adjoint and the paired products got ~1 us slower:
-// 127.2 us against 126.3 us per 1024-row step, 503 against 497 us at 8192 rows.
+// 127.2 us against 126.3 us per 1024-row step, 503 against 497 us at 8192 rows.  Re-measured A/B on single boxes (weights only,
+// after the launch or when the product is created, so that the forward product itself can take the 2-CTA kernel): 122.4 / 124.6
+// against 125.5 us on one box, 121.1 / 121.9 / 118.4-122.3 against 120.5 us on another — inside the box-to-box and run-to-run
+// spread (2-3 %), not worth the code.
 #include <stdlib.h>
 
 #include <algorithm>
