@@ -393,12 +393,13 @@ static int try_sink_product(Ctx* ctx, LazyNode* nd) {
     }
     if (ctx->flags & DSC_FLAG_GEMM_FP32_SIMT) return 1;
     auto small = [&](const LazyNode* x) { return x->m >= 128 && x->n >= 32 && x->k >= 32 && ((x->m + 127) / 128) * ((x->n + 127) / 128) <= ctx->sm_count / 2; };
-    // One rank: side by side only pays when neither product fills the GPU by itself (the weight adjoints of a large batch pair
-    // up with each other at the end of the sweep instead, co_schedule_pending_gemms).  Several ranks: the weight adjoint always
-    // goes ahead on the lane — what is gained is not the packing but the all-reduce of the finished layers' adjoints, which
-    // then overlaps the rest of the sweep.
+    // The weight adjoint goes ahead on the lane with half of the SMs and the partner (the input adjoint of the same tape node,
+    // or an earlier weight adjoint still waiting) takes the other half — also when one of them would fill the GPU by itself:
+    // measured A/B on one box (tools/step_timeline.py, DSC_SINK_ALWAYS), step at 2048 / 4096 / 8192 rows 184.3 / 292.7 / 483.6 us
+    // against 190.9 / 288.2 / 490.5 us when only products that are both small share the SMs.
     if (nd->m < 128 || nd->n < 32 || nd->k < 32) return 1;
-    if (ctx->nranks == 1 && (!small(nd) || !small(partner))) return 1;
+    static const bool small_only = [] { const char* e = getenv("DSC_SINK_ALWAYS"); return e && *e == '0'; }();
+    if (small_only && (!small(nd) || !small(partner))) return 1;
     DSC_TRY(run_on_lane(ctx, nd, ctx->sm_count / 2));
     ctx->main_gemm_half_once = true;   // the partner takes the other half when the compute stream reaches it
     ctx->stats_co_scheduled++;
