@@ -913,6 +913,7 @@ int dsc_comm_join(dsc_ctx_t c) {
     if (!ctx_ok(c)) return fail(DSC_E_INVALID, "bad context");
     Ctx* ctx = as_ctx(c);
     DSC_TRY(p2p_check_error(ctx));
+    DSC_TRY(lane_join(ctx));   // "the compute stream is ordered after every side stream": the second compute lane included
     if (!ctx->comm_pending) return DSC_OK;
     DSC_CUDA_CHECK(cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
     DSC_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));

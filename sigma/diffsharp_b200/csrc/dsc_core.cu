@@ -802,7 +802,7 @@ int dsc_buf_download(dsc_buf_t h, int32_t off, void* host, int32_t n) {
     Ctx* ctx = b->ctx;
     if (ctx->capturing) return fail(DSC_E_INVALID, "synchronous download while capturing a graph");
     DSC_TRY(buf_resolve(b));
-    DSC_TRY(dsc_comm_join(reinterpret_cast<dsc_ctx_t>(ctx)));
+    DSC_TRY(dsc_comm_join(reinterpret_cast<dsc_ctx_t>(ctx)));   // (joins the second compute lane as well)
     size_t es = dtype_size(b->dtype);
     const char* src = reinterpret_cast<const char*>(b->block->ptr) + (b->off + off) * es;
     DSC_CUDA_CHECK(cudaMemcpyAsync(host, src, (size_t)n * es, cudaMemcpyDeviceToHost, ctx->stream));

@@ -84,6 +84,11 @@ bool lane_sees(Ctx* ctx, Block* const* reads, int n) {
 int lane_enter(Ctx* ctx, Block* const* reads, int n, bool force_fork) {
     if (ctx->on_lane) return fail(DSC_E_INVALID, "lane_enter: already on the lane");
     DSC_TRY(lane_ensure(ctx));
+    // The blocks lane operations touch stay referenced until the next join.  A host loop that never reaches a synchronisation
+    // point (no loss read, no download, no dsc_sync) would pile them up — and every allocation of the following steps would
+    // miss the pool: after kLaneMaxUnjoined operations the lane is joined before it is given more.
+    constexpr uint64_t kLaneMaxUnjoined = 24;
+    if (ctx->lane_seq - ctx->lane_joined >= kLaneMaxUnjoined) DSC_TRY(lane_join(ctx));
     const bool fork = force_fork || !lane_sees(ctx, reads, n);
     if (lane_debug()) fprintf(stderr, "[dsc lane] enter: %s\n", fork ? "fork" : "no fork");
     if (fork) {

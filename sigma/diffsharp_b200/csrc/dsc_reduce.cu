@@ -286,6 +286,7 @@ template <typename T>
 static int fetch_scalar(Ctx* ctx, const void* dev, T* out) {
     if (ctx->capturing)
         return fail(DSC_E_INVALID, "host-scalar reduction while capturing a graph: use the *_dev variant");
+    DSC_TRY(lane_join(ctx));   // the host is about to wait anyway: the second compute lane is drained with the stream (and releases the blocks it holds)
     DSC_CUDA_CHECK(cudaMemcpyAsync(ctx->red_host, dev, sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
     DSC_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     *out = *reinterpret_cast<T*>(ctx->red_host);
