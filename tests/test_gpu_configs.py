@@ -236,3 +236,31 @@ def test_graph_replay_equals_eager(cuda_provider, use_provider):
         assert np.array_equal(a.ToArray(), e)
     assert abs(float(loss_bufs[0].SubData[0]) - float(L)) <= 1e-6 * abs(float(L))
     ctx.graph_destroy(g)
+
+
+def test_eager_loop_without_sync_points_keeps_the_pool_bounded(cuda_provider, use_provider):
+    """A host loop that never reads anything back (no loss read, no download, no dsc_sync) still issues sinks to the second
+    compute lane every step; the blocks those operations hold must not pile up (regression: every allocation of the
+    following steps then missed the pool and the step took 20x longer)."""
+    use_provider(cuda_provider)
+    ctx = cuda_provider.ctx
+    b32 = cuda_provider.GetBackend(np.float32(0)).BackendHandle
+    X, Y, Ws, bs = wl.mlp_inputs([160, 256, 192, 10], 512, seed=9)
+    dX, dY = wl.to_DM(X), wl.to_DM(Y)
+    dWs, dbs = [wl.to_DM(w) for w in Ws], [wl.to_DV(b) for b in bs]
+    b32.capture_scalars = []          # the loss stays on the device: no synchronisation point inside a step
+    try:
+        for _ in range(4):
+            wl.mlp_grad(dX, dY, dWs, dbs)
+        ctx.sync()
+        s0 = ctx.stats()
+        for _ in range(60):
+            wl.mlp_grad(dX, dY, dWs, dbs)
+            b32.capture_scalars.clear()
+        s1 = ctx.stats()
+        ctx.sync()
+    finally:
+        b32.capture_scalars = None
+    assert s1["lane_ops"] - s0["lane_ops"] >= 60 * 3                      # the sinks did go to the lane
+    assert s1["pool_misses"] - s0["pool_misses"] <= 40                    # ... and the pool reached a steady state
+    assert s1["pool_bytes_reserved"] <= 4 * max(s0["pool_bytes_reserved"], 1 << 20)
