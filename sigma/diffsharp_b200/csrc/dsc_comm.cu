@@ -666,6 +666,7 @@ static int allreduce_impl(dsc_ctx_t c, int32_t count, const dsc_buf_t* bufs) {
     if (!ctx->nccl_comm) return fail(DSC_E_NCCL, "allreduce: dsc_comm_init has not been called");
     DSC_TRY(p2p_check_error(ctx));
     DSC_TRY(co_schedule_pending_gemms(ctx));   // the weight adjoints about to be summed are usually still-deferred products: run them side by side
+    DSC_TRY(flush_colsums_on_lane(ctx));       // ... and deferred bias column sums belong beside the last weight adjoint, not behind it
     // The collective runs on the compute stream, on every SM: measured (tools/step_timeline.py, 2 GPUs), an all-reduce confined
     // to the few SMs a concurrent GEMM leaves free pushes ~5 GB/s per SM over NVLink (outstanding remote writes per SM), i.e.
     // 40-46 us for the 4.2 MB of the later layers on 32 SMs against 17 us on all of them — running it beside the first layer's

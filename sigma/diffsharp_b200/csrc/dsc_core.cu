@@ -487,6 +487,7 @@ int dsc_destroy(dsc_ctx_t c) {
     if (ctx->lane_stream) {
         cudaStreamSynchronize(ctx->lane_stream);
         cudaEventDestroy(ctx->ev_lane_fork);
+        if (ctx->ev_lane_prefork) cudaEventDestroy(ctx->ev_lane_prefork);
         cudaEventDestroy(ctx->ev_lane_done);
         cudaStreamDestroy(ctx->lane_stream);
     }
@@ -615,6 +616,7 @@ int dsc_graph_begin(dsc_ctx_t c) {
     DSC_CUDA_CHECK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
     ctx->capturing = true;
     ctx->lane_fork_seq = 0;   // the lane is not part of this capture until its first fork
+    ctx->prefork_pending = false;
     ctx->cache_epoch++;   // operand-split companions computed before the capture are not trusted inside it: a replay must recompute what depends on replaced inputs
     ctx->cur_arena = ctx->next_arena++;
     ctx->arena_pool = Pool();
@@ -639,6 +641,7 @@ int dsc_graph_end(dsc_ctx_t c, dsc_graph_t* out) {
     }
     ctx->cache_epoch++;   // ... and companions computed inside it describe the capture-time values only
     ctx->lane_fork_seq = 0;
+    ctx->prefork_pending = false;
     if (ctx->comm_pending) {
         // join the communication stream back into the origin stream before ending the capture
         cudaEventRecord(ctx->ev_comm, ctx->comm_stream);

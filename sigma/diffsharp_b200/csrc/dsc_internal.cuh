@@ -83,6 +83,7 @@ enum LazyKind {
     LZ_HAD,        // src0 .* src1                   Mul_Had_M_M / Map2(Mul)                        :4240,4280-4281
     LZ_SCALAR,     // scalar broadcast op(kind, s, src0)   Add_S / Sub_S / Mul_S                    :4280-4281
     LZ_GEMM,       // op(src0) op(src1) [+ src2 rows]      Mul_M_M                                  :2382
+    LZ_COLSUM,     // column sums of src0 (m x n) stored into a fresh zero vector   Add_M_Colwise_V_InPlace  :4255 after :3640
 };
 
 struct Operand {          // an input of a deferred operation: a device window, or another deferred value
@@ -198,6 +199,12 @@ struct Ctx {
     cudaEvent_t ev_lane_fork = nullptr, ev_lane_done = nullptr;
     uint64_t order_seq = 0;              // counter behind Block::w_seq pins and lane forks
     uint64_t lane_fork_seq = 0;          // the lane is ordered after every compute-stream write pinned at or below this value
+    // A fork point recorded ahead of a long compute-stream kernel (lane_prefork) that the lane has NOT been made to wait for
+    // yet: lane operations whose inputs were visible before it keep running ahead; the wait is applied only for an operation
+    // that needs what the fork point covers (lane_apply_prefork).
+    cudaEvent_t ev_lane_prefork = nullptr;
+    bool prefork_pending = false;
+    uint64_t prefork_seq = 0;
     uint64_t lane_seq = 0;               // lane operations issued
     uint64_t lane_joined = 0;            // ... of which the compute stream is ordered after this many
     std::vector<Block*> lane_held;       // blocks lane operations touch: referenced (never recycled) until the next join
@@ -307,6 +314,7 @@ void lazy_set_result(LazyNode* nd, Block* blk, size_t off);    // a fused consum
 int buf_resolve(Buf* b);                                       // make b a plain device window
 int operand_resolve(Ctx* ctx, Operand& o);                     // make o a plain device window (materialises its node)
 int flush_pending(Ctx* ctx);                                   // run every deferred compute node nobody has consumed
+int flush_colsums_on_lane(Ctx* ctx);                           // deferred column sums whose matrix the second lane already sees: run them there
 int co_schedule_pending_gemms(Ctx* ctx);                       // pairs of small pending float32 products: one per compute lane, concurrently (dsc_gemm.cu)
 // ---- the sink lane (dsc_lane.cu) ----
 void lane_swap(Ctx* ctx);                                      // the lane's stream / workspace / scratch become the context's current ones (and back)
@@ -322,6 +330,8 @@ int lane_join(Ctx* ctx);                                       // the compute st
 // Fork now, before the compute stream is given a long kernel: lane operations issued afterwards whose inputs are among `reads`
 // (or were visible before) start beside that kernel instead of behind it.
 int lane_prefork(Ctx* ctx, Block* const* reads, int n);
+inline bool lane_prefork_covers(const Ctx* ctx, const Block* b) { return ctx->prefork_pending && b && b->w_seq != 0 && b->w_seq <= ctx->prefork_seq; }
+int lane_apply_prefork(Ctx* ctx);                              // the lane now waits for the recorded fork point
 inline bool lane_busy(const Ctx* ctx) { return ctx->lane_seq > ctx->lane_joined; }
 bool lane_debug();                                             // DSC_LANE_DEBUG=1: every lane decision on stderr
 // compute-stream work is about to read / write blk
@@ -374,6 +384,7 @@ template <typename T> int ew_fused_bwd(Ctx*, int kind, const T* dA, const T* p, 
 template <typename T> int ew_rows(Ctx*, int bop, int act, int m, int n, const T* A, const T* v, T* z, T* h, T* h_lo);
 template <typename T> int transpose_launch(Ctx* ctx, const T* A, T* B, int m, int n);             // dsc_layout.cu
 template <typename T> int repeat_rows_launch(Ctx* ctx, const T* v, T* out, int m, int n);
+template <typename T> int colsum_launch(Ctx* ctx, const T* M, T* v, int m, int n, bool accumulate);   // v[j] (+)= sum_i M[i,j]
 int fill_raw(Ctx* ctx, int dtype, void* base, size_t n, double v);                                // dsc_core.cu
 
 // ---- typed implementations (one template per op, instantiated for float and double) -------

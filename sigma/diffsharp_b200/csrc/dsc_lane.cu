@@ -95,6 +95,7 @@ int lane_enter(Ctx* ctx, Block* const* reads, int n, bool force_fork) {
         DSC_CUDA_CHECK(cudaEventRecord(ctx->ev_lane_fork, ctx->stream));
         DSC_CUDA_CHECK(cudaStreamWaitEvent(ctx->lane_stream, ctx->ev_lane_fork, 0));
         ctx->lane_fork_seq = ++ctx->order_seq;   // everything pinned so far (the inputs above included) is visible to the lane
+        ctx->prefork_pending = false;            // ... which includes whatever an earlier recorded fork point covered
         ctx->lane_fork_open = true;
     }
     lane_swap(ctx);
@@ -105,11 +106,20 @@ int lane_prefork(Ctx* ctx, Block* const* reads, int n) {
     if (ctx->on_lane) return DSC_OK;
     DSC_TRY(lane_ensure(ctx));
     if (lane_sees(ctx, reads, n)) return DSC_OK;   // (pins the inputs) nothing to gain: the lane is already ordered after them
-    if (lane_debug()) fprintf(stderr, "[dsc lane] fork ahead of a compute-stream kernel\n");
-    DSC_CUDA_CHECK(cudaEventRecord(ctx->ev_lane_fork, ctx->stream));
-    DSC_CUDA_CHECK(cudaStreamWaitEvent(ctx->lane_stream, ctx->ev_lane_fork, 0));
-    ctx->lane_fork_seq = ++ctx->order_seq;
+    if (lane_debug()) fprintf(stderr, "[dsc lane] fork point recorded ahead of a compute-stream kernel\n");
+    if (!ctx->ev_lane_prefork) DSC_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_lane_prefork, cudaEventDisableTiming));
+    DSC_CUDA_CHECK(cudaEventRecord(ctx->ev_lane_prefork, ctx->stream));
+    ctx->prefork_seq = ++ctx->order_seq;
+    ctx->prefork_pending = true;
+    return DSC_OK;
+}
+
+int lane_apply_prefork(Ctx* ctx) {
+    if (!ctx->prefork_pending) return DSC_OK;
+    DSC_CUDA_CHECK(cudaStreamWaitEvent(ctx->lane_stream, ctx->ev_lane_prefork, 0));
+    if (ctx->prefork_seq > ctx->lane_fork_seq) ctx->lane_fork_seq = ctx->prefork_seq;
     ctx->lane_fork_open = true;
+    ctx->prefork_pending = false;
     return DSC_OK;
 }
 
@@ -142,6 +152,7 @@ int lane_join(Ctx* ctx) {
     if (lane_debug()) fprintf(stderr, "[dsc lane] join (%llu operations)\n", (unsigned long long)(ctx->lane_seq - ctx->lane_joined));
     ctx->lane_joined = ctx->lane_seq;
     ctx->lane_fork_open = false;
+    ctx->prefork_pending = false;
     ctx->main_gemm_half_once = false;
     std::vector<Block*> held;
     held.swap(ctx->lane_held);

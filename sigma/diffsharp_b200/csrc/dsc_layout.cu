@@ -438,6 +438,8 @@ int repeat_rows_launch(Ctx* ctx, const T* v, T* out, int m, int n) {
     DSC_LAUNCH_CHECK(ctx);
     return DSC_OK;
 }
+template int colsum_launch<float>(Ctx*, const float*, float*, int, int, bool);
+template int colsum_launch<double>(Ctx*, const double*, double*, int, int, bool);
 template int repeat_rows_launch<float>(Ctx*, const float*, float*, int, int);
 template int repeat_rows_launch<double>(Ctx*, const double*, double*, int, int);
 
@@ -490,6 +492,20 @@ static int colsum_impl(dsc_ctx_t c, int32_t m, int32_t n, dsc_buf_t Mh, dsc_buf_
         // (the weight adjoint of the same layer read it, or the lane was forked in front of that product), the sums are
         // taken there — beside whatever the compute stream has been given since, not behind it.
         Block* rd[1] = {M->block};
+        // The matrix is the newest adjoint of the sweep: a fork point was recorded in front of the weight adjoint that reads it
+        // (lane_prefork), but the lane has not been made to wait for it — the column sums of the other layers, which the calls
+        // right behind this one issue and whose inputs have been ready for a long time, should not queue behind that wait.
+        // These sums are deferred (a pending value like any other); at the next flush they run on the lane, behind the others.
+        if (ctx->fuse && ctx->lanes_enabled && !ctx->on_lane && M->block->lane_w <= ctx->lane_joined && !lane_sees(ctx, rd, 1) &&
+            lane_prefork_covers(ctx, M->block)) {
+            block_release(v->block);
+            v->block = nullptr;
+            LazyNode* nd = lazy_new(ctx, LZ_COLSUM, v->dtype, n);
+            nd->m = m; nd->n = n;
+            lazy_set_operand(nd, 0, M);
+            v->lazy = nd;
+            return DSC_OK;
+        }
         if (lane_debug()) fprintf(stderr, "[dsc lane] column sums %d x %d of %p: lane busy %d, lane-written %d\n", m, n, M->block->ptr, (int)lane_busy(ctx), (int)(M->block->lane_w > ctx->lane_joined));
         if (ctx->lanes_enabled && !ctx->on_lane && M->block->lane_w <= ctx->lane_joined && lane_sees(ctx, rd, 1)) {
             DSC_TRY(lane_enter(ctx, rd, 1, false));

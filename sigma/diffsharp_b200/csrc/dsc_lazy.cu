@@ -26,7 +26,9 @@
 
 namespace dsc {
 
-static bool is_compute_kind(int kind) { return kind == LZ_ADD_ROWS || kind == LZ_MAP || kind == LZ_SECH || kind == LZ_HAD || kind == LZ_SCALAR || kind == LZ_GEMM; }
+static bool is_compute_kind(int kind) {
+    return kind == LZ_ADD_ROWS || kind == LZ_MAP || kind == LZ_SECH || kind == LZ_HAD || kind == LZ_SCALAR || kind == LZ_GEMM || kind == LZ_COLSUM;
+}
 
 LazyNode* lazy_new(Ctx* ctx, int kind, int dtype, int32_t len) {
     LazyNode* nd = new LazyNode();
@@ -206,6 +208,7 @@ static int materialize_typed(LazyNode* nd, Block* out) {
         case LZ_SECH: return ew_sech<T>(ctx, operand_ptr<T>(nd->src[0]), y, n);
         case LZ_HAD: return ew_map2<T>(ctx, DSC_OP_MUL, operand_ptr<T>(nd->src[0]), operand_ptr<T>(nd->src[1]), y, n);
         case LZ_SCALAR: return ew_scalar<T>(ctx, nd->op, (T)nd->s, operand_ptr<T>(nd->src[0]), y, n);
+        case LZ_COLSUM: return colsum_launch<T>(ctx, operand_ptr<T>(nd->src[0]), y, nd->m, nd->n, false);
         case LZ_GEMM: return gemm_run<T>(ctx, nd->ta, nd->tb, nd->m, nd->n, nd->k, operand_mat<T>(nd->src[0]), operand_mat<T>(nd->src[1]),
                                          nd->nsrc > 2 ? operand_ptr<T>(nd->src[2]) : nullptr, y, nullptr);
     }
@@ -237,8 +240,37 @@ void lazy_set_result(LazyNode* nd, Block* blk, size_t off) {
     pending_remove(nd);
 }
 
+// Deferred column sums (see colsum_impl) run on the second compute lane when it is already ordered after their matrix.
+int flush_colsums_on_lane(Ctx* ctx) {
+    if (!ctx->lanes_enabled || ctx->on_lane) return DSC_OK;
+    std::vector<LazyNode*> todo;
+    for (LazyNode* nd : ctx->pending)
+        if (nd->kind == LZ_COLSUM && !nd->result && nd->refs > 0 && !nd->src[0].node && nd->src[0].block) {
+            nd->refs++;
+            todo.push_back(nd);
+        }
+    int st = DSC_OK;
+    for (LazyNode* nd : todo) {
+        Block* rd[1] = {nd->src[0].block};
+        if (st == DSC_OK && !nd->result && rd[0]->lane_w <= ctx->lane_joined && !lane_sees(ctx, rd, 1) && lane_prefork_covers(ctx, rd[0])) st = lane_apply_prefork(ctx);
+        if (st == DSC_OK && !nd->result && rd[0]->lane_w <= ctx->lane_joined && lane_sees(ctx, rd, 1)) {
+            rd[0]->refs++;   // materialising releases the node's operand reference
+            st = lane_enter(ctx, rd, 1, false);
+            if (st == DSC_OK) {
+                st = lazy_materialize(nd);
+                Block* wr[1] = {st == DSC_OK ? nd->result : nullptr};
+                lane_leave(ctx, rd, 1, wr, 1);
+            }
+            block_release(rd[0]);
+        }
+        lazy_unref(nd);
+    }
+    return st;
+}
+
 int flush_pending(Ctx* ctx) {
     DSC_TRY(co_schedule_pending_gemms(ctx));
+    DSC_TRY(flush_colsums_on_lane(ctx));
     // materialising a node removes it (and possibly others) from the list: walk a snapshot, holding the nodes
     std::vector<LazyNode*> todo;
     for (LazyNode* nd : ctx->pending)
