@@ -311,7 +311,8 @@ DSC_API int dsc_comm_unique_id(uint8_t out[128]);
 DSC_API int dsc_comm_init(dsc_ctx_t ctx, int nranks, int rank, const uint8_t id[128]);
 DSC_API int dsc_comm_join(dsc_ctx_t ctx); /* compute stream waits for everything queued on the comm stream */
 /* %globaltimer (ns) at the phase boundaries of the last peer-memory all-reduce as CTA 0 saw them:
- * start, packed, barrier 1, reduced + broadcast, barrier 2, unpacked (tools/allreduce_bench.py). */
+ * start, packed, barrier 1, reduced + broadcast, barrier 2, unpacked (tools/allreduce_bench.py); the flag-in-data kernel
+ * has no barriers: stamps 1 = 2 and 3 = 4. */
 DSC_API int dsc_comm_debug_stamps(dsc_ctx_t ctx, uint64_t out[6]);
 /* the same for the last call (back = 0) or the one before it (back = 1): a step issues two all-reduces (dist.py) */
 DSC_API int dsc_comm_debug_stamps_at(dsc_ctx_t ctx, int back, uint64_t out[6]);

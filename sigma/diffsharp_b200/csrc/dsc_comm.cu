@@ -2,16 +2,17 @@
 // context (= per process = per GPU).
 //
 // Sum of the weight adjoints (dsc_?allreduce_sum), up to 8 GPUs of one NVSwitch node: ONE kernel over
-// peer memory.  Every rank owns a symmetric buffer (flags | region A | region B) that all peers map
+// peer memory.  Every rank owns a symmetric buffer (header | region A | region B) that all peers map
 // through CUDA IPC at dsc_comm_init.  The kernel (one CTA per SM on the compute stream, captured in
 // the step's CUDA graph like any other kernel) pushes: every byte that crosses NVLink is a store.
 //   0. scatter: slice q of the rank's (packed) adjoint buffers -> region A of rank q, slot [rank],
-//   1. barrier (one flag per peer, written into the peer's memory; relaxed stores and polls between
-//      two system fences),
 //   2. rank r adds the N slots of its region A (local) in rank order 0..N-1, so the sum is bit-identical
 //      on every rank and from run to run, and stores the result slice into region B of EVERY rank,
-//   3. barrier,
 //   4. unpacks region B into the adjoint buffers.
+// Two kernels implement it.  allreduce_ll_kernel (the default, further down): no barrier at all — every
+// 128-byte line carries its own flag and the receiver polls the data.  allreduce_p2p_kernel (round 1,
+// DSC_P2P_PROTO=barrier): phases 1 and 3 are grid-wide, system-scope barriers (one flag per peer,
+// written into the peer's memory; relaxed stores and polls between two system fences).
 // No staging copies on a second stream, no event hand-offs, deterministic.  Measured (7.45 MB,
 // tools/allreduce_bench.py): see profiles/README.md.
 // NCCL remains for the bootstrap (exchange of the IPC handles), for the Jacobian all-gather, and
