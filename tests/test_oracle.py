@@ -129,3 +129,13 @@ def test_oracle_reproduces_the_c3_full_size_digest(oracle_provider, use_provider
     use_provider(oracle_provider)
     loss, grads = mg.c3_full_step()
     assert mg.c3_digest_max_rel(loss, grads, GOLD) <= 1e-5 and loss == float(GOLD["c3_loss"][0])
+    # bench.py carries its own copy of the comparison (it may not import tests/): same verdict on the same data, and a
+    # perturbed adjoint is caught
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_for_test", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.digest_max_rel(loss, grads) <= 1e-5
+    bad = [g.copy() for g in grads]
+    bad[1].reshape(-1)[:16] *= np.float32(1.001)
+    assert bench.digest_max_rel(loss, bad) > 1e-5
